@@ -1,0 +1,134 @@
+// LBFGS.h -- LBFGSSolver<Scalar, LineSearch>: unconstrained L-BFGS with every n-vector in B200 HBM.
+//
+// Drop-in for the reference's include/LBFGS.h: same class template, same constructor / minimize() /
+// final_grad() / final_grad_norm() surface, same convergence rules and return values (reference LBFGS.h:78-173).
+// What changes is the Vector type (LBFGSpp::DeviceVector<Scalar>, device memory) and where the arithmetic runs:
+// every Eigen expression of the reference's loop body is a call into liblbfgs_b200 (include/lbfgs_b200.h).
+//
+//   reference (per iteration)                         here
+//   m_xp = x; m_gradp = m_grad        LBFGS.h:121-122  O(1) pointer rotation, no copy
+//   dg = m_grad.dot(m_drt)            LBFGS.h:123      comes out of the tail of apply_Hv (v.res)
+//   line search trials                LBFGS.h:127      one fused kernel per trial (built-in objectives)
+//   m_grad.norm(), x.norm()           LBFGS.h:130,137  by-products of the accepted trial's kernel
+//   s, y, gate, add_correction        LBFGS.h:159-162  one kernel, written straight into the ring slot
+//   apply_Hv(m_grad, -1, m_drt)       LBFGS.h:165      2c+1 fused stage kernels / Gram form / resident kernel
+//
+// The objective is any callable `Scalar f(const Vector& x, Vector& grad)` working on device vectors (taken by
+// non-const reference, called once per trial, exactly like the reference).  Objectives that additionally offer
+// fused_trial()/fused_value() (see LBFGSpp/DeviceObjectives.h) get the single-kernel trial.
+#ifndef LBFGSPP_B200_LBFGS_H
+#define LBFGSPP_B200_LBFGS_H
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "LBFGSpp/BFGSMat.h"
+#include "LBFGSpp/DeviceVector.h"
+#include "LBFGSpp/LineSearchBacktracking.h"
+#include "LBFGSpp/LineSearchBracketing.h"
+#include "LBFGSpp/LineSearchDriver.h"
+#include "LBFGSpp/LineSearchMoreThuente.h"
+#include "LBFGSpp/LineSearchNocedalWright.h"
+#include "LBFGSpp/Param.h"
+
+namespace LBFGSpp {
+
+template <typename Scalar, template <class> class LineSearch = LineSearchNocedalWright>
+class LBFGSSolver
+{
+public:
+    typedef DeviceVector<Scalar> Vector;
+
+private:
+    const LBFGSParam<Scalar>& m_param;  // held by reference, like the reference (LBFGS.h:29)
+    BFGSMat<Scalar> m_bfgs;
+    std::vector<Scalar> m_fx;           // ring of past objective values (host scalars)
+    Vector m_xp, m_grad, m_gradp, m_drt;
+    LineSearchWorkspace<Scalar> m_ws;
+    Scalar m_gnorm;
+    long m_nfev;
+
+    bool small_gradient(Scalar gg, Scalar xx)
+    {
+        m_gnorm = std::sqrt(gg);
+        return m_gnorm <= m_param.epsilon || m_gnorm <= m_param.epsilon_rel * std::sqrt(xx);
+    }
+
+public:
+    LBFGSSolver(const LBFGSParam<Scalar>& param) : m_param(param), m_gnorm(0), m_nfev(0) { m_param.check_param(); }
+
+    // apply_Hv implementation selector (LBFGS_B200_HV_*); not part of the reference API
+    void set_hv_algorithm(int algo) { m_bfgs.set_algorithm(algo); }
+
+    // Minimise f starting from x (device vector, updated in place; its storage may be exchanged with an internal
+    // buffer).  Returns the number of iterations; throws what the reference throws.
+    template <typename Foo>
+    inline int minimize(Foo& f, Vector& x, Scalar& fx)
+    {
+        using std::abs;
+        Device& dev = x.device();
+        const std::ptrdiff_t n = x.size();
+        const int fpast = m_param.past;
+
+        m_bfgs.reset(dev, n, m_param.m);
+        for (Vector* v : {&m_xp, &m_grad, &m_gradp, &m_drt, &m_ws.x_lo, &m_ws.grad_lo})
+        {
+            if (&v->device() != &dev) *v = Vector(dev);
+            v->resize(n);
+        }
+        if (fpast > 0) m_fx.assign(size_t(fpast), Scalar(0));
+        m_nfev = 0;
+
+        // first evaluation and early exit (LBFGS.h:91-103)
+        TrialValues<Scalar> at = detail::evaluate_point(f, static_cast<const Vector&>(x), m_grad);
+        m_nfev++;
+        fx = at.fx;
+        if (fpast > 0) m_fx[0] = fx;
+        if (small_gradient(at.gg, at.xx)) return 1;
+
+        // steepest-descent start: drt = -grad, first step 1/||drt||  (LBFGS.h:106-108)
+        dev.check(detail::Abi<Scalar>::scale_out(dev.ctx(), n, Scalar(-1), m_grad.data(), m_drt.data()));
+        Scalar step = Scalar(1) / m_gnorm;
+        Scalar dg = -at.gg;  // grad . (-grad): the same products as g.g, negated
+        m_ws.gg = at.gg;
+        m_ws.xx = at.xx;
+
+        int k = 1;
+        for (;;)
+        {
+            // the current point becomes the "previous" one: rotate buffers instead of copying
+            m_xp.swap(x);
+            m_gradp.swap(m_grad);
+
+            const Scalar step_max = m_param.max_step;
+            run_line_search<typename LineSearch<Scalar>::Machine>(f, m_param, m_xp, m_gradp, m_drt, step_max, step, fx, dg,
+                                                                  x, m_grad, m_ws);
+            m_nfev += m_ws.evaluations;
+
+            if (small_gradient(m_ws.gg, m_ws.xx)) return k;                 // LBFGS.h:137-140
+            if (fpast > 0)                                                   // LBFGS.h:142-149
+            {
+                const Scalar fxd = m_fx[size_t(k % fpast)];
+                if (k >= fpast && abs(fxd - fx) <= m_param.delta * std::max(std::max(abs(fx), abs(fxd)), Scalar(1))) return k;
+                m_fx[size_t(k % fpast)] = fx;
+            }
+            if (m_param.max_iterations != 0 && k >= m_param.max_iterations) return k;  // LBFGS.h:151-154
+
+            m_bfgs.update(x, m_xp, m_grad, m_gradp);                         // LBFGS.h:159-162
+            dg = m_bfgs.apply_Hv_dot(m_grad, -Scalar(1), m_drt);             // LBFGS.h:165 (+ :123 of the next pass)
+            step = Scalar(1);
+            k++;
+        }
+        return k;
+    }
+
+    const Vector& final_grad() const { return m_grad; }
+    Scalar final_grad_norm() const { return m_gnorm; }
+    // number of objective evaluations of the last minimize() call (not in the reference; used by tests/bench)
+    long num_evaluations() const { return m_nfev; }
+};
+
+}  // namespace LBFGSpp
+
+#endif  // LBFGSPP_B200_LBFGS_H

@@ -1,0 +1,149 @@
+/* lbfgs_b200.h -- C ABI of liblbfgs_b200.so: the L-BFGS hot path of LBFGSpp on NVIDIA B200 (sm_100a).
+ *
+ * The reference (yixuan/LBFGSpp @ ebef584) has no FFI: its boundary is a C++ template API whose
+ * floating-point work happens inside Eigen expressions.  This header is the contract between the
+ * header-only C++ front in include/LBFGS.h (same class names / template parameters as the reference)
+ * and the hand-written CUDA kernels.  Every entry point names the reference expression it replaces
+ * (paths relative to the reference root).  Conventions:
+ *   - plain C types only; device pointers are `void*`/typed pointers into memory obtained from
+ *     lbfgs_b200_malloc (256-byte aligned) -- never host memory unless the name says `_host`;
+ *   - every call returns a lbfgs_b200_status; no exception crosses the boundary; the text of the last
+ *     failure is available from lbfgs_b200_last_error();
+ *   - calls are stream-ordered on the context's stream; a call that returns scalars to the host
+ *     (`*_host` out-parameters) synchronises the stream before returning, all others are asynchronous;
+ *   - reductions are deterministic (fixed grid, fixed-order block partials, no floating-point atomics);
+ *     with a communicator attached (n sharded over ranks) every reduction is summed over all ranks;
+ *   - a context (and everything created from it) must be used by one host thread at a time;
+ *   - there is NO CPU fallback: without a CUDA device every call fails with LBFGS_B200_ERR_CUDA.
+ * `T` in {f64, f32} via the suffix.
+ */
+#ifndef LBFGS_B200_H
+#define LBFGS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    LBFGS_B200_OK = 0,
+    LBFGS_B200_ERR_INVALID = 1, /* bad argument (maps to std::invalid_argument in the C++ front) */
+    LBFGS_B200_ERR_CUDA = 2,    /* CUDA runtime / driver failure, or no device (std::runtime_error) */
+    LBFGS_B200_ERR_COMM = 3,    /* NCCL failure (std::runtime_error)                               */
+    LBFGS_B200_ERR_ALLOC = 4    /* out of device memory (std::bad_alloc)                           */
+} lbfgs_b200_status;
+
+typedef struct lbfgs_b200_ctx lbfgs_b200_ctx;   /* device + stream + reduction scratch + communicator */
+typedef struct lbfgs_b200_hist lbfgs_b200_hist; /* the S/Y ring of BFGSMat, resident in HBM           */
+
+/* built-in device objective functions (the reference's example functors) */
+enum {
+    LBFGS_B200_OBJ_ROSENBROCK_PAIRED = 0,  /* examples/example-rosenbrock.cpp:15-27      */
+    LBFGS_B200_OBJ_QUAD_SHIFT = 1,         /* examples/example-quadratic.cpp:9-19        */
+    LBFGS_B200_OBJ_ROSENBROCK_CHAINED = 2, /* examples/example-rosenbrock-box.cpp:18-33  */
+    LBFGS_B200_OBJ_QUAD_TRIDIAG = 3        /* f = 1/2 x'Ax - b'x, A = diag(d) + 1/2 tridiag(-1,2,-1); data0=d, data1=b */
+};
+
+/* apply_Hv algorithms */
+enum {
+    LBFGS_B200_HV_AUTO = 0,      /* RESIDENT when the shard fits on chip, else GRAM                           */
+    LBFGS_B200_HV_TWO_LOOP = 1,  /* literal two-loop recursion, one fused AXPY+dot stage kernel per history column */
+    LBFGS_B200_HV_GRAM = 2,      /* same recursion carried out on 2c coefficients (two passes over S,Y)        */
+    LBFGS_B200_HV_RESIDENT = 3   /* literal two-loop in ONE persistent cooperative kernel, q/r in registers    */
+};
+
+/* ---------------------------------------------------------------- context, memory, communicator */
+const char* lbfgs_b200_version(void);
+/* stream: a cudaStream_t to run on, or NULL to let the context create its own non-blocking stream. */
+lbfgs_b200_status lbfgs_b200_ctx_create(lbfgs_b200_ctx** out, int device, void* stream);
+void lbfgs_b200_ctx_destroy(lbfgs_b200_ctx* ctx);
+const char* lbfgs_b200_last_error(const lbfgs_b200_ctx* ctx); /* ctx may be NULL: creation errors */
+void* lbfgs_b200_stream(const lbfgs_b200_ctx* ctx);
+int lbfgs_b200_sm_count(const lbfgs_b200_ctx* ctx);
+uint64_t lbfgs_b200_launch_count(const lbfgs_b200_ctx* ctx); /* kernels launched so far by this context */
+
+lbfgs_b200_status lbfgs_b200_malloc(lbfgs_b200_ctx* ctx, void** dptr, size_t bytes); /* replaces Eigen resize(): LBFGS.h:40-50 */
+lbfgs_b200_status lbfgs_b200_free(lbfgs_b200_ctx* ctx, void* dptr);
+lbfgs_b200_status lbfgs_b200_malloc_host(lbfgs_b200_ctx* ctx, void** hptr, size_t bytes); /* pinned */
+lbfgs_b200_status lbfgs_b200_free_host(lbfgs_b200_ctx* ctx, void* hptr);
+lbfgs_b200_status lbfgs_b200_memcpy_h2d(lbfgs_b200_ctx* ctx, void* dst, const void* src_host, size_t bytes);
+lbfgs_b200_status lbfgs_b200_memcpy_d2h(lbfgs_b200_ctx* ctx, void* dst_host, const void* src, size_t bytes); /* synchronises */
+lbfgs_b200_status lbfgs_b200_memcpy_d2d(lbfgs_b200_ctx* ctx, void* dst, const void* src, size_t bytes);      /* `m_xp = x`, LBFGS.h:121-122 */
+lbfgs_b200_status lbfgs_b200_memset_zero(lbfgs_b200_ctx* ctx, void* dst, size_t bytes);
+lbfgs_b200_status lbfgs_b200_sync(lbfgs_b200_ctx* ctx);
+/* CUDA-event stopwatch on the context's stream (device time of everything enqueued in between) */
+lbfgs_b200_status lbfgs_b200_timer_start(lbfgs_b200_ctx* ctx);
+lbfgs_b200_status lbfgs_b200_timer_stop(lbfgs_b200_ctx* ctx, float* elapsed_ms_host); /* synchronises */
+/* n-sharding: global index of this rank's element 0 (used by objectives that depend on the coordinate index) */
+lbfgs_b200_status lbfgs_b200_set_index_offset(lbfgs_b200_ctx* ctx, int64_t offset);
+
+/* n-sharding over GPUs: rank r owns a contiguous block of every vector; all scalars replicated.
+ * unique_id is NCCL's 128-byte ncclUniqueId, created on one rank and shipped to the others by the caller. */
+lbfgs_b200_status lbfgs_b200_comm_unique_id(void* unique_id_128);
+lbfgs_b200_status lbfgs_b200_comm_init(lbfgs_b200_ctx* ctx, const void* unique_id_128, int rank, int nranks);
+int lbfgs_b200_comm_size(const lbfgs_b200_ctx* ctx);
+
+/* ---------------------------------------------------------------- level-1 kernels (f64 / f32) */
+#define LBFGS_B200_DECLARE_L1(T, SUF)                                                                          \
+    /* a.dot(b)                                   LBFGS.h:123,161; every LineSearch*.h `grad.dot(drt)` */      \
+    lbfgs_b200_status lbfgs_b200_dot_##SUF(lbfgs_b200_ctx*, int64_t n, const T* a, const T* b, T* out_host);   \
+    /* out3 = { g.d, g.g, x.x } in one pass       LineSearchMoreThuente.h:414 + LBFGS.h:130,137 */             \
+    lbfgs_b200_status lbfgs_b200_dot3_##SUF(lbfgs_b200_ctx*, int64_t n, const T* g, const T* d, const T* x,    \
+                                            T* out3_host);                                                    \
+    /* out = a + s*b  (out may alias a or b)      `x = xp + step*drt`, LineSearchMoreThuente.h:412 */          \
+    lbfgs_b200_status lbfgs_b200_axpy_out_##SUF(lbfgs_b200_ctx*, int64_t n, const T* a, T s, const T* b,       \
+                                                T* out);                                                      \
+    /* out = s*a                                  `m_drt = -m_grad`, LBFGS.h:106 */                            \
+    lbfgs_b200_status lbfgs_b200_scale_out_##SUF(lbfgs_b200_ctx*, int64_t n, T s, const T* a, T* out);         \
+    /* built-in objective: g = grad f(x), out4 = { f(x), 0, g.g, x.x }   (user functor, LBFGS.h:69-71,91-92) */ \
+    lbfgs_b200_status lbfgs_b200_objective_##SUF(lbfgs_b200_ctx*, int objective, const T* data0,               \
+                                                 const T* data1, int64_t n, const T* x, T* g, T* out4_host);   \
+    /* One line-search trial for a built-in objective in ONE kernel:                                           \
+     *   x = xp + step*d;  g = grad f(x);  out4 = { f(x), g.d, g.g, x.x }                                      \
+     * replaces LineSearchMoreThuente.h:412-414 (and the same three lines of the other three line searches)    \
+     * plus the norms of LBFGS.h:130,137. */                                                                   \
+    lbfgs_b200_status lbfgs_b200_trial_##SUF(lbfgs_b200_ctx*, int objective, const T* data0, const T* data1,   \
+                                             int64_t n, const T* xp, const T* d, T step, T* x, T* g,          \
+                                             T* out4_host);
+
+LBFGS_B200_DECLARE_L1(double, f64)
+LBFGS_B200_DECLARE_L1(float, f32)
+
+/* ---------------------------------------------------------------- the S/Y ring (BFGSMat, L-BFGS part) */
+/* elem_bytes: 8 (fp64) or 4 (fp32).  Replaces BFGSMat::reset's allocations, BFGSMat.h:61-78. */
+lbfgs_b200_status lbfgs_b200_hist_create(lbfgs_b200_ctx* ctx, lbfgs_b200_hist** out, int64_t n, int m,
+                                         int elem_bytes);
+void lbfgs_b200_hist_destroy(lbfgs_b200_hist* h);
+/* theta = 1, ncorr = 0 (no reallocation).  BFGSMat.h:61-78. */
+lbfgs_b200_status lbfgs_b200_hist_reset(lbfgs_b200_hist* h);
+int lbfgs_b200_hist_ncorr(const lbfgs_b200_hist* h);
+int lbfgs_b200_hist_m(const lbfgs_b200_hist* h);
+/* device pointers of logical column `age` (0 = newest) for inspection / tests; NULL if age >= ncorr */
+const void* lbfgs_b200_hist_s_col(const lbfgs_b200_hist* h, int age);
+const void* lbfgs_b200_hist_y_col(const lbfgs_b200_hist* h, int age);
+
+#define LBFGS_B200_DECLARE_HIST(T, SUF)                                                                        \
+    /* s = x - xp, y = g - gp written straight into the next ring slot, gate s'y > eps*y'y, ys, theta:         \
+     * LBFGS.h:159-162 + BFGSMat::add_correction BFGSMat.h:81-97, one kernel.  sy_yy_host (2 values) optional. */ \
+    lbfgs_b200_status lbfgs_b200_hist_update_##SUF(lbfgs_b200_hist* h, const T* x, const T* xp, const T* g,    \
+                                                   const T* gp, T eps, int* accepted_host, T* sy_yy_host);    \
+    /* add_correction(s, y) for explicit vectors (BFGSMat.h:81-97); no gate. */                                \
+    lbfgs_b200_status lbfgs_b200_hist_add_##SUF(lbfgs_b200_hist* h, const T* s, const T* y);                   \
+    /* res = a * H * v by the two-loop recursion, BFGSMat::apply_Hv BFGSMat.h:276-302.                         \
+     * gdotres_host (optional) receives v.res, i.e. `dg = m_grad.dot(m_drt)` of LBFGS.h:123 when v = grad.     \
+     * res must not alias v. */                                                                                \
+    lbfgs_b200_status lbfgs_b200_hist_apply_Hv_##SUF(lbfgs_b200_hist* h, const T* v, T a, T* res, int algo,    \
+                                                     T* vdotres_host);                                        \
+    /* host copies of theta and of ys/alpha by age (newest first), for tests */                                \
+    lbfgs_b200_status lbfgs_b200_hist_scalars_##SUF(lbfgs_b200_hist* h, T* theta_host, T* ys_host,             \
+                                                    T* alpha_host);
+
+LBFGS_B200_DECLARE_HIST(double, f64)
+LBFGS_B200_DECLARE_HIST(float, f32)
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBFGS_B200_H */

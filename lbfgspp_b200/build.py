@@ -1,0 +1,64 @@
+"""Build the two in-tree shared objects of the product (no JIT cache: the .so files travel with the snapshot).
+
+  liblbfgs_b200.so         hand-written sm_100a kernels + C ABI  (nvcc; include/lbfgs_b200.h)
+  liblbfgs_b200_driver.so  header-only C++ front (include/LBFGS.h ...) behind host-buffer entry points (g++)
+
+`python -m lbfgspp_b200.build` or lbfgspp_b200.build.build_all().
+"""
+import os
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "liblbfgs_b200.so")
+DRV = os.path.join(PKG, "liblbfgs_b200_driver.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+CXX = "/usr/bin/g++"
+
+NVCC_FLAGS = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-shared", "-ccbin", CXX]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def _sources(*dirs, exts=(".cu", ".cuh", ".h", ".cpp", ".hpp")):
+    out = []
+    for d in dirs:
+        for base, _, files in os.walk(d):
+            out += [os.path.join(base, f) for f in files if f.endswith(exts)]
+    return out
+
+
+def build_kernels(force=False, verbose=False):
+    srcs = _sources(CSRC, os.path.join(ROOT, "include"))
+    if not force and _newer(LIB, srcs):
+        return LIB
+    cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-o", LIB, os.path.join(CSRC, "lbfgs_b200.cu"), "-lnccl"]
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+def build_driver(force=False):
+    srcs = _sources(CSRC, os.path.join(ROOT, "include"))
+    if not force and _newer(DRV, srcs + [LIB]):
+        return DRV
+    cmd = [CXX, "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-o", DRV, os.path.join(CSRC, "driver.cpp"),
+           "-L", PKG, "-l:liblbfgs_b200.so", "-Wl,-rpath,$ORIGIN"]
+    subprocess.run(cmd, check=True)
+    return DRV
+
+
+def build_all(force=False, verbose=False):
+    return build_kernels(force, verbose), build_driver(force)
+
+
+if __name__ == "__main__":
+    print(build_all(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,173 @@
+// device_utils.cuh -- wide global-memory accessors and the deterministic grid reduction used by every
+// kernel of liblbfgs_b200.so (sm_100a only).
+//
+// Memory model of the path: all operands are long contiguous fp64/fp32 vectors streamed once per kernel,
+// so the kernels are HBM-bound.  Rules applied here (B200 guide, "HBM3e + on-chip memory"):
+//   * 256-bit accesses (LDG.E.256 / STG.E.256, new on sm_100): one pack = 4 doubles (or 8 floats handled as
+//     two 128-bit halves is not needed: fp32 packs are 4 floats = 128 bit);
+//   * history columns are read with L1::no_allocate + L2::evict_first (touched once per pass), the running
+//     vector q/r with L2::evict_last so that it can survive in the 126 MB L2 between consecutive stages;
+//   * grids are a multiple of the SM count; every thread keeps several independent packs in flight.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lb {
+
+constexpr int kThreads = 256;        // threads per CTA for all streaming kernels
+constexpr int kMaxRed = 8;           // max simultaneous reductions per kernel launch
+constexpr int kMaxBlocks = 148 * 8;  // upper bound on any reducing grid (partials buffer size)
+
+// ----------------------------------------------------------------------------- packs of 4 elements
+template <class T> struct Pack { T v[4]; };
+
+enum class Hint { Stream, Keep, Plain };
+
+template <Hint H> __device__ __forceinline__ Pack<double> ld_pack(const double* p)
+{
+    Pack<double> r;
+    if (H == Hint::Stream)
+        asm volatile("ld.global.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
+                     : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p));
+    else if (H == Hint::Keep)
+        asm volatile("ld.global.L1::no_allocate.L2::evict_last.v4.f64 {%0,%1,%2,%3}, [%4];"
+                     : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p));
+    else
+        asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                     : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p));
+    return r;
+}
+template <Hint H> __device__ __forceinline__ void st_pack(double* p, const Pack<double>& r)
+{
+    if (H == Hint::Stream)
+        asm volatile("st.global.L1::no_allocate.L2::evict_first.v4.f64 [%0], {%1,%2,%3,%4};"
+                     :: "l"(p), "d"(r.v[0]), "d"(r.v[1]), "d"(r.v[2]), "d"(r.v[3]) : "memory");
+    else if (H == Hint::Keep)
+        asm volatile("st.global.L1::no_allocate.L2::evict_last.v4.f64 [%0], {%1,%2,%3,%4};"
+                     :: "l"(p), "d"(r.v[0]), "d"(r.v[1]), "d"(r.v[2]), "d"(r.v[3]) : "memory");
+    else
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};"
+                     :: "l"(p), "d"(r.v[0]), "d"(r.v[1]), "d"(r.v[2]), "d"(r.v[3]) : "memory");
+}
+// fp32: 128-bit packs (L2 eviction-priority qualifiers exist only on the 256-bit forms)
+template <Hint H> __device__ __forceinline__ Pack<float> ld_pack(const float* p)
+{
+    Pack<float> r;
+    if (H == Hint::Plain)
+        asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p));
+    else
+        asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p));
+    return r;
+}
+template <Hint H> __device__ __forceinline__ void st_pack(float* p, const Pack<float>& r)
+{
+    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]) : "memory");
+}
+
+template <class T> __host__ __device__ __forceinline__ bool pack_aligned(const void* p)
+{
+    return (reinterpret_cast<uintptr_t>(p) & (sizeof(T) * 4 - 1)) == 0;
+}
+
+// Guarded pack access: full aligned packs take the wide path, the ragged tail (and misaligned callers)
+// go element by element.  `cnt` = number of valid elements (1..4); missing lanes read as 0.
+template <class T, Hint H, bool VEC> __device__ __forceinline__ Pack<T> load4(const T* base, int64_t i0, int cnt)
+{
+    if (VEC && cnt == 4) return ld_pack<H>(base + i0);
+    Pack<T> r;
+#pragma unroll
+    for (int k = 0; k < 4; k++) r.v[k] = (k < cnt) ? base[i0 + k] : T(0);
+    return r;
+}
+template <class T, Hint H, bool VEC> __device__ __forceinline__ void store4(T* base, int64_t i0, int cnt, const Pack<T>& r)
+{
+    if (VEC && cnt == 4) { st_pack<H>(base + i0, r); return; }
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (k < cnt) base[i0 + k] = r.v[k];
+}
+
+// ----------------------------------------------------------------------------- deterministic reduction
+// Every reducing kernel ends with grid_reduce<NV>():
+//   thread partials -> warp shuffle tree -> smem across warps -> one slot per (block, value) in `partials`
+//   -> integer ticket -> the LAST block to arrive sums the slots in a fixed order and writes `result[k]`.
+// The only atomic is the integer ticket, so the floating-point result depends on (n, grid) alone and is
+// reproducible run to run.  Accumulation across warps/blocks is in double also for fp32 inputs.
+struct ReduceBuf
+{
+    double* partials;    // [kMaxBlocks][kMaxRed]
+    unsigned* ticket;    // zero between launches (the last block resets it)
+    double* result;      // [kMaxRed] device result slots of this launch
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Returns true in the threads of the last block once result[] is final (so a caller can append a tiny
+// "finalizer" that consumes the reduced values in the same launch); false elsewhere.
+template <int NV> __device__ __forceinline__ bool grid_reduce(const double (&acc)[NV], const ReduceBuf& rb)
+{
+    __shared__ double s_part[NV][kThreads / 32];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; k++)
+    {
+        const double w = warp_sum(acc[k]);
+        if (lane == 0) s_part[k][warp] = w;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV)
+    {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; w++) t += s_part[threadIdx.x][w];
+        rb.partials[blockIdx.x * kMaxRed + threadIdx.x] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        const unsigned t = atomicAdd(rb.ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+    // last block: fixed-order sum over blocks: thread t takes blocks t, t+256, ...; then the block tree
+    double mine[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) mine[k] = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += kThreads)
+#pragma unroll
+        for (int k = 0; k < NV; k++) mine[k] += __ldcg(&rb.partials[b * kMaxRed + k]);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; k++)
+    {
+        const double w = warp_sum(mine[k]);
+        if (lane == 0) s_part[k][warp] = w;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV)
+    {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; w++) t += s_part[threadIdx.x][w];
+        rb.result[threadIdx.x] = t;
+    }
+    if (threadIdx.x == 0) *rb.ticket = 0u;
+    __threadfence();
+    __syncthreads();
+    return true;
+}
+
+}  // namespace lb

@@ -1,0 +1,978 @@
+// lbfgs_b200.cu -- kernels + C ABI of liblbfgs_b200.so (declared in include/lbfgs_b200.h).
+//
+// Build (see lbfgspp_b200/build.py):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC ... -lnccl
+//
+// Kernel inventory (all HBM-bound streaming kernels; algorithmic words moved per element in brackets):
+//   k_trial<OBJ>      x = xp + step*d ; g = grad f(x) ; {f, g.d, g.g, x.x}      [R 2 + W 2 (+data)]
+//   k_dot3 / k_dot    reductions for user functors                              [R 3 / R 2]
+//   k_axpy_out, k_scale_out                                                      [R 2 W 1 / R 1 W 1]
+//   k_update          s = x-xp, y = g-gp -> ring slot ; {s.y, y.y}               [R 4 + W 2]
+//   k_hv_stage<KIND>  one fused AXPY+dot stage of the two-loop recursion         [R 3 + W 1]
+//   (k_gram_*, k_hv_resident live in two_loop_fast.cuh)
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <string>
+
+#include "../../include/lbfgs_b200.h"
+#include "device_utils.cuh"
+#include "objectives.cuh"
+
+using namespace lb;
+
+// =====================================================================================================
+// context
+// =====================================================================================================
+struct lbfgs_b200_ctx
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    ReduceBuf rb{};                // device scratch for grid_reduce
+    double* h_result = nullptr;    // pinned mirror of rb.result (+ extra slots)
+    int* d_flag = nullptr;         // device int flags (accepted, ...)
+    int* h_flag = nullptr;         // pinned
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+    int64_t index_offset = 0;      // global index of this rank's element 0
+    uint64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+static lbfgs_b200_status fail(lbfgs_b200_ctx* ctx, lbfgs_b200_status st, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_err = buf;
+    return st;
+}
+
+#define CU(ctx, call)                                                                                      \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess)                                                                            \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? LBFGS_B200_ERR_ALLOC : LBFGS_B200_ERR_CUDA, \
+                        "%s failed: %s", #call, cudaGetErrorString(e__));                                  \
+    } while (0)
+
+#define NC(ctx, call)                                                                                      \
+    do {                                                                                                   \
+        ncclResult_t r__ = (call);                                                                         \
+        if (r__ != ncclSuccess)                                                                            \
+            return fail(ctx, LBFGS_B200_ERR_COMM, "%s failed: %s", #call, ncclGetErrorString(r__));        \
+    } while (0)
+
+#define REQUIRE(ctx, cond, ...)                                                                            \
+    do { if (!(cond)) return fail(ctx, LBFGS_B200_ERR_INVALID, __VA_ARGS__); } while (0)
+
+// grid for a streaming kernel over n elements: a multiple of the SM count, capped so that every CTA has
+// at least a few packs; 4 CTAs of 256 threads per SM are resident (register budget <= 64/thread).
+static int grid_for(const lbfgs_b200_ctx* ctx, int64_t n, int packs_per_thread = 4)
+{
+    const int64_t packs = (n + 3) / 4;
+    const int64_t want = (packs + (int64_t)kThreads * packs_per_thread - 1) / ((int64_t)kThreads * packs_per_thread);
+    const int64_t cap = (int64_t)ctx->sm_count * 8;
+    int64_t g = want < 1 ? 1 : want;
+    if (g > cap) g = cap;
+    if (g > ctx->sm_count) g = (g / ctx->sm_count) * ctx->sm_count;  // whole waves
+    if (g > kMaxBlocks) g = kMaxBlocks;
+    return (int)g;
+}
+
+static lbfgs_b200_status post_launch(lbfgs_b200_ctx* ctx, const char* what)
+{
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, LBFGS_B200_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    return LBFGS_B200_OK;
+}
+
+// sum the first `count` result slots over all ranks (no-op on one GPU)
+static lbfgs_b200_status allreduce_result(lbfgs_b200_ctx* ctx, int count)
+{
+    if (ctx->nranks > 1)
+        NC(ctx, ncclAllReduce(ctx->rb.result, ctx->rb.result, count, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+    return LBFGS_B200_OK;
+}
+
+// copy result slots to the host and wait
+static lbfgs_b200_status fetch_result(lbfgs_b200_ctx* ctx, int count)
+{
+    CU(ctx, cudaMemcpyAsync(ctx->h_result, ctx->rb.result, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return LBFGS_B200_OK;
+}
+
+// =====================================================================================================
+// level-1 kernels
+// =====================================================================================================
+template <class T, bool VEC>
+__global__ void __launch_bounds__(kThreads) k_axpy_out(int64_t n, const T* __restrict__ a, T s, const T* __restrict__ b, T* out)
+{
+    const int64_t packs = (n + 3) >> 2, stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x; p < packs; p += stride)
+    {
+        const int64_t i0 = p << 2;
+        const int cnt = (n - i0 >= 4) ? 4 : int(n - i0);
+        const Pack<T> pa = load4<T, Hint::Stream, VEC>(a, i0, cnt), pb = load4<T, Hint::Stream, VEC>(b, i0, cnt);
+        Pack<T> r;
+#pragma unroll
+        for (int k = 0; k < 4; k++) r.v[k] = pa.v[k] + s * pb.v[k];
+        store4<T, Hint::Plain, VEC>(out, i0, cnt, r);
+    }
+}
+
+template <class T, bool VEC>
+__global__ void __launch_bounds__(kThreads) k_scale_out(int64_t n, T s, const T* __restrict__ a, T* out)
+{
+    const int64_t packs = (n + 3) >> 2, stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x; p < packs; p += stride)
+    {
+        const int64_t i0 = p << 2;
+        const int cnt = (n - i0 >= 4) ? 4 : int(n - i0);
+        Pack<T> r = load4<T, Hint::Stream, VEC>(a, i0, cnt);
+#pragma unroll
+        for (int k = 0; k < 4; k++) r.v[k] = s * r.v[k];
+        store4<T, Hint::Plain, VEC>(out, i0, cnt, r);
+    }
+}
+
+// NV = 1: a.b ; NV = 3: {a.b, a.a, c.c}
+template <class T, int NV, bool VEC>
+__global__ void __launch_bounds__(kThreads) k_dots(int64_t n, const T* __restrict__ a, const T* __restrict__ b,
+                                                   const T* __restrict__ c, ReduceBuf rb)
+{
+    T acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) acc[k] = T(0);
+    const int64_t packs = (n + 3) >> 2, stride = (int64_t)gridDim.x * kThreads;
+#pragma unroll 2
+    for (int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x; p < packs; p += stride)
+    {
+        const int64_t i0 = p << 2;
+        const int cnt = (n - i0 >= 4) ? 4 : int(n - i0);
+        const Pack<T> pa = load4<T, Hint::Stream, VEC>(a, i0, cnt), pb = load4<T, Hint::Stream, VEC>(b, i0, cnt);
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc[0] += pa.v[k] * pb.v[k];
+        if constexpr (NV == 3)
+        {
+            const Pack<T> pc = load4<T, Hint::Stream, VEC>(c, i0, cnt);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+                acc[1] += pa.v[k] * pa.v[k];
+                acc[2] += pc.v[k] * pc.v[k];
+            }
+        }
+    }
+    double dacc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) dacc[k] = (double)acc[k];
+    grid_reduce<NV>(dacc, rb);
+}
+
+// =====================================================================================================
+// fused line-search trial  (x = xp + step*d ; g = grad f(x) ; {f, g.d, g.g, x.x})
+//   TRIAL = false: plain objective evaluation at x (no xp/d, no x store), reduces {f, -, g.g, x.x}
+// =====================================================================================================
+template <class T, class OBJ, bool TRIAL, bool VEC>
+__global__ void __launch_bounds__(kThreads) k_trial(OBJ obj, int64_t n, const T* __restrict__ xp, const T* __restrict__ d,
+                                                    T step, T* __restrict__ x, T* __restrict__ g, ReduceBuf rb)
+{
+    T acc[4] = {T(0), T(0), T(0), T(0)};
+    const int64_t packs = (n + 3) >> 2, stride = (int64_t)gridDim.x * kThreads;
+#pragma unroll 2
+    for (int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x; p < packs; p += stride)
+    {
+        const int64_t i0 = p << 2;
+        const int cnt = (n - i0 >= 4) ? 4 : int(n - i0);
+        T xv[4], dv[4] = {T(0), T(0), T(0), T(0)}, gv[4];
+        T xl = T(0), xr = T(0);
+        if (TRIAL)
+        {
+            const Pack<T> px = load4<T, Hint::Stream, VEC>(xp, i0, cnt), pd = load4<T, Hint::Stream, VEC>(d, i0, cnt);
+#pragma unroll
+            for (int k = 0; k < 4; k++) { dv[k] = pd.v[k]; xv[k] = px.v[k] + step * pd.v[k]; }
+            if (OBJ::kHalo)
+            {
+                if (i0 > 0) xl = xp[i0 - 1] + step * d[i0 - 1];
+                if (i0 + 4 < n) xr = xp[i0 + 4] + step * d[i0 + 4];
+            }
+        }
+        else
+        {
+            const Pack<T> px = load4<T, Hint::Stream, VEC>(x, i0, cnt);
+#pragma unroll
+            for (int k = 0; k < 4; k++) xv[k] = px.v[k];
+            if (OBJ::kHalo)
+            {
+                if (i0 > 0) xl = x[i0 - 1];
+                if (i0 + 4 < n) xr = x[i0 + 4];
+            }
+        }
+        acc[0] += obj.eval(i0, cnt, xv, xl, xr, gv);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            acc[1] += gv[k] * dv[k];
+            acc[2] += gv[k] * gv[k];
+            acc[3] += (k < cnt) ? xv[k] * xv[k] : T(0);
+        }
+        Pack<T> pg, pxo;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { pg.v[k] = gv[k]; pxo.v[k] = xv[k]; }
+        if (TRIAL) store4<T, Hint::Plain, VEC>(x, i0, cnt, pxo);
+        store4<T, Hint::Plain, VEC>(g, i0, cnt, pg);
+    }
+    double dacc[4] = {(double)acc[0], (double)acc[1], (double)acc[2], (double)acc[3]};
+    grid_reduce<4>(dacc, rb);
+}
+
+// =====================================================================================================
+// the S/Y ring
+// =====================================================================================================
+// Device-resident scalars of BFGSMat (BFGSMat.h:35-48): theta, ys[], alpha[] indexed by PHYSICAL slot.
+// The ring has M = m+1 physical columns so that the pair of an iteration can be written speculatively into
+// the free slot `head` before the curvature gate (LBFGS.h:161) is known; a rejected pair simply leaves
+// `head` where it was and the m older pairs untouched (the reference would not have called add_correction).
+template <class T> struct HistDev
+{
+    T* S;         // [M][ld]
+    T* Y;         // [M][ld]
+    T* ys;        // [M]
+    T* alpha;     // [M]
+    T* theta;     // [1]
+};
+
+struct lbfgs_b200_hist
+{
+    lbfgs_b200_ctx* ctx = nullptr;
+    int64_t n = 0, ld = 0;
+    int m = 0, M = 0, elem = 8;
+    void *S = nullptr, *Y = nullptr, *ys = nullptr, *alpha = nullptr, *theta = nullptr;
+    int head = 0;   // physical slot the next pair is written to
+    int ncorr = 0;  // valid pairs (<= m)
+    // physical slot of the pair with the given age (0 = newest)
+    int slot(int age) const { return ((head - 1 - age) % M + M) % M; }
+    template <class T> T* s_col(int phys) const { return static_cast<T*>(S) + (int64_t)phys * ld; }
+    template <class T> T* y_col(int phys) const { return static_cast<T*>(Y) + (int64_t)phys * ld; }
+};
+
+// s = x - xp ; y = g - gp -> slot ; {s.y, y.y}
+template <class T, bool VEC>
+__global__ void __launch_bounds__(kThreads) k_update(int64_t n, const T* __restrict__ x, const T* __restrict__ xp,
+                                                     const T* __restrict__ g, const T* __restrict__ gp,
+                                                     T* __restrict__ s_out, T* __restrict__ y_out, ReduceBuf rb)
+{
+    T acc[2] = {T(0), T(0)};
+    const int64_t packs = (n + 3) >> 2, stride = (int64_t)gridDim.x * kThreads;
+#pragma unroll 2
+    for (int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x; p < packs; p += stride)
+    {
+        const int64_t i0 = p << 2;
+        const int cnt = (n - i0 >= 4) ? 4 : int(n - i0);
+        const Pack<T> a = load4<T, Hint::Stream, VEC>(x, i0, cnt), b = load4<T, Hint::Stream, VEC>(xp, i0, cnt);
+        const Pack<T> c = load4<T, Hint::Stream, VEC>(g, i0, cnt), e = load4<T, Hint::Stream, VEC>(gp, i0, cnt);
+        Pack<T> s, y;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            s.v[k] = a.v[k] - b.v[k];
+            y.v[k] = c.v[k] - e.v[k];
+            acc[0] += s.v[k] * y.v[k];
+            acc[1] += y.v[k] * y.v[k];
+        }
+        store4<T, Hint::Plain, VEC>(s_out, i0, cnt, s);
+        store4<T, Hint::Plain, VEC>(y_out, i0, cnt, y);
+    }
+    double dacc[2] = {(double)acc[0], (double)acc[1]};
+    grid_reduce<2>(dacc, rb);
+}
+
+// {s.y, y.y} of an explicitly given pair while copying it into the slot (BFGSMat::add_correction)
+template <class T, bool VEC>
+__global__ void __launch_bounds__(kThreads) k_add_pair(int64_t n, const T* __restrict__ s, const T* __restrict__ y,
+                                                       T* __restrict__ s_out, T* __restrict__ y_out, ReduceBuf rb)
+{
+    T acc[2] = {T(0), T(0)};
+    const int64_t packs = (n + 3) >> 2, stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x; p < packs; p += stride)
+    {
+        const int64_t i0 = p << 2;
+        const int cnt = (n - i0 >= 4) ? 4 : int(n - i0);
+        const Pack<T> a = load4<T, Hint::Stream, VEC>(s, i0, cnt), c = load4<T, Hint::Stream, VEC>(y, i0, cnt);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            acc[0] += a.v[k] * c.v[k];
+            acc[1] += c.v[k] * c.v[k];
+        }
+        store4<T, Hint::Plain, VEC>(s_out, i0, cnt, a);
+        store4<T, Hint::Plain, VEC>(y_out, i0, cnt, c);
+    }
+    double dacc[2] = {(double)acc[0], (double)acc[1]};
+    grid_reduce<2>(dacc, rb);
+}
+
+// gate + ys/theta bookkeeping from the reduced {s.y, y.y}: one thread (runs after the all-reduce)
+template <class T>
+__global__ void k_commit_pair(const double* result, T eps, int gate, T* ys_slot, T* theta, int* accepted)
+{
+    const T sy = (T)result[0], yy = (T)result[1];
+    const bool ok = gate ? (sy > eps * yy) : true;
+    if (ok)
+    {
+        *ys_slot = sy;
+        *theta = yy / sy;
+    }
+    *accepted = ok ? 1 : 0;
+}
+
+// ----------------------------------------------------------------------------- literal two-loop stages
+// One launch per history column.  Stage kinds (q lives in `res`, updated in place):
+//   FIRST : q = a*v                                       ; dot(B, q)
+//   BACK  : alpha_j = dot_prev/ys_j ; q -= alpha_j*A      ; dot(B, q)          A = y_j, B = s_{j-1 older}
+//   MID   : alpha_j = dot_prev/ys_j ; q = (q - alpha_j*A)/theta ; dot(B, q)    A = y_oldest, B = y_oldest
+//   FWD   : beta = dot_prev/ys_j ; q += (alpha_j - beta)*A ; dot(B, q)         A = s_j, B = y_{j+1 newer} (or v)
+// The coefficient is recomputed from the previous stage's reduced dot by every thread (identical arithmetic),
+// so the only dependency between stages is stream order -- no host round trip (BFGSMat.h:283-301).
+enum { HV_FIRST = 0, HV_BACK = 1, HV_MID = 2, HV_FWD = 3, HV_ONLY = 4 };
+
+template <class T> struct StageArgs
+{
+    int64_t n;
+    const T* v;       // FIRST/ONLY: input vector
+    T a;              // FIRST/ONLY: scale
+    T* q;             // running vector (res)
+    const T* A;       // axpy column
+    const T* B;       // dot column (nullptr: no dot)
+    const double* dot_prev;  // reduced dot of the previous stage
+    const T* ys_j;    // &ys[j]
+    T* alpha_j;       // &alpha[j]
+    const T* theta;
+};
+
+template <class T, int KIND, bool VEC>
+__global__ void __launch_bounds__(kThreads) k_hv_stage(StageArgs<T> s, ReduceBuf rb)
+{
+    T coef = T(0), theta = T(1);
+    if (KIND == HV_BACK || KIND == HV_MID)
+    {
+        coef = (T)(*s.dot_prev) / *s.ys_j;  // alpha_j = s_j'q / ys_j   (BFGSMat.h:288, a division)
+        if (blockIdx.x == 0 && threadIdx.x == 0) *s.alpha_j = coef;
+    }
+    if (KIND == HV_FWD)
+    {
+        const T beta = (T)(*s.dot_prev) / *s.ys_j;  // BFGSMat.h:298
+        coef = *s.alpha_j - beta;
+    }
+    if (KIND == HV_MID || KIND == HV_ONLY) theta = *s.theta;
+
+    T acc = T(0);
+    const int64_t packs = (s.n + 3) >> 2, stride = (int64_t)gridDim.x * kThreads;
+#pragma unroll 2
+    for (int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x; p < packs; p += stride)
+    {
+        const int64_t i0 = p << 2;
+        const int cnt = (s.n - i0 >= 4) ? 4 : int(s.n - i0);
+        Pack<T> q;
+        if (KIND == HV_FIRST || KIND == HV_ONLY)
+        {
+            const Pack<T> pv = load4<T, Hint::Stream, VEC>(s.v, i0, cnt);
+#pragma unroll
+            for (int k = 0; k < 4; k++) q.v[k] = (KIND == HV_ONLY) ? (s.a * pv.v[k]) / theta : s.a * pv.v[k];
+        }
+        else
+        {
+            q = load4<T, Hint::Keep, VEC>(s.q, i0, cnt);
+            const Pack<T> pa = load4<T, Hint::Stream, VEC>(s.A, i0, cnt);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+                if (KIND == HV_BACK) q.v[k] = q.v[k] - coef * pa.v[k];
+                if (KIND == HV_MID) q.v[k] = (q.v[k] - coef * pa.v[k]) / theta;
+                if (KIND == HV_FWD) q.v[k] = q.v[k] + coef * pa.v[k];
+            }
+        }
+        if (s.B != nullptr)
+        {
+            const Pack<T> pb = load4<T, Hint::Stream, VEC>(s.B, i0, cnt);
+#pragma unroll
+            for (int k = 0; k < 4; k++) acc += pb.v[k] * q.v[k];
+        }
+        store4<T, Hint::Keep, VEC>(s.q, i0, cnt, q);
+    }
+    if (s.B != nullptr)
+    {
+        double dacc[1] = {(double)acc};
+        grid_reduce<1>(dacc, rb);
+    }
+}
+
+// =====================================================================================================
+// C ABI: context, memory, communicator
+// =====================================================================================================
+extern "C" {
+
+const char* lbfgs_b200_version(void) { return "lbfgs_b200 0.1 (sm_100a)"; }
+
+lbfgs_b200_status lbfgs_b200_ctx_create(lbfgs_b200_ctx** out, int device, void* stream)
+{
+    if (!out) return fail(nullptr, LBFGS_B200_ERR_INVALID, "ctx_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, LBFGS_B200_ERR_CUDA, "no CUDA device available (%s); liblbfgs_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= ndev) return fail(nullptr, LBFGS_B200_ERR_INVALID, "device %d out of range [0,%d)", device, ndev);
+    lbfgs_b200_ctx* ctx = new (std::nothrow) lbfgs_b200_ctx();
+    if (!ctx) return fail(nullptr, LBFGS_B200_ERR_ALLOC, "out of host memory");
+    ctx->device = device;
+#define CUC(call)                                                                                          \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess) {                                                                          \
+            fail(nullptr, LBFGS_B200_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));           \
+            lbfgs_b200_ctx_destroy(ctx);                                                                   \
+            return LBFGS_B200_ERR_CUDA;                                                                    \
+        }                                                                                                  \
+    } while (0)
+    CUC(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUC(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+    {
+        fail(nullptr, LBFGS_B200_ERR_CUDA, "device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+        lbfgs_b200_ctx_destroy(ctx);
+        return LBFGS_B200_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (stream) ctx->stream = static_cast<cudaStream_t>(stream);
+    else { CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    CUC(cudaMalloc(&ctx->rb.partials, sizeof(double) * kMaxBlocks * kMaxRed));
+    CUC(cudaMalloc(&ctx->rb.ticket, sizeof(unsigned)));
+    CUC(cudaMalloc(&ctx->rb.result, sizeof(double) * 256));
+    CUC(cudaMalloc(&ctx->d_flag, sizeof(int) * 16));
+    CUC(cudaMemsetAsync(ctx->rb.ticket, 0, sizeof(unsigned), ctx->stream));
+    CUC(cudaMemsetAsync(ctx->rb.result, 0, sizeof(double) * 256, ctx->stream));
+    CUC(cudaMallocHost(&ctx->h_result, sizeof(double) * 256));
+    CUC(cudaMallocHost(&ctx->h_flag, sizeof(int) * 16));
+    CUC(cudaEventCreate(&ctx->ev0));
+    CUC(cudaEventCreate(&ctx->ev1));
+    CUC(cudaStreamSynchronize(ctx->stream));
+#undef CUC
+    *out = ctx;
+    return LBFGS_B200_OK;
+}
+
+void lbfgs_b200_ctx_destroy(lbfgs_b200_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm) ncclCommDestroy(ctx->comm);
+    cudaFree(ctx->rb.partials);
+    cudaFree(ctx->rb.ticket);
+    cudaFree(ctx->rb.result);
+    cudaFree(ctx->d_flag);
+    if (ctx->h_result) cudaFreeHost(ctx->h_result);
+    if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* lbfgs_b200_last_error(const lbfgs_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+void* lbfgs_b200_stream(const lbfgs_b200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int lbfgs_b200_sm_count(const lbfgs_b200_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+uint64_t lbfgs_b200_launch_count(const lbfgs_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+lbfgs_b200_status lbfgs_b200_malloc(lbfgs_b200_ctx* ctx, void** dptr, size_t bytes)
+{
+    REQUIRE(ctx, ctx && dptr, "malloc: NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    // round up to a whole number of 256-byte lines so that ragged tails can be read as full packs by callers
+    const size_t padded = (bytes + 255) & ~size_t(255);
+    CU(ctx, cudaMalloc(dptr, padded ? padded : 256));
+    return LBFGS_B200_OK;
+}
+lbfgs_b200_status lbfgs_b200_free(lbfgs_b200_ctx* ctx, void* dptr)
+{
+    if (!dptr) return LBFGS_B200_OK;
+    CU(ctx, cudaFree(dptr));
+    return LBFGS_B200_OK;
+}
+lbfgs_b200_status lbfgs_b200_malloc_host(lbfgs_b200_ctx* ctx, void** hptr, size_t bytes)
+{
+    REQUIRE(ctx, ctx && hptr, "malloc_host: NULL argument");
+    CU(ctx, cudaMallocHost(hptr, bytes ? bytes : 1));
+    return LBFGS_B200_OK;
+}
+lbfgs_b200_status lbfgs_b200_free_host(lbfgs_b200_ctx* ctx, void* hptr)
+{
+    if (!hptr) return LBFGS_B200_OK;
+    CU(ctx, cudaFreeHost(hptr));
+    return LBFGS_B200_OK;
+}
+lbfgs_b200_status lbfgs_b200_memcpy_h2d(lbfgs_b200_ctx* ctx, void* dst, const void* src, size_t bytes)
+{
+    CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return LBFGS_B200_OK;
+}
+lbfgs_b200_status lbfgs_b200_memcpy_d2h(lbfgs_b200_ctx* ctx, void* dst, const void* src, size_t bytes)
+{
+    CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return LBFGS_B200_OK;
+}
+lbfgs_b200_status lbfgs_b200_memcpy_d2d(lbfgs_b200_ctx* ctx, void* dst, const void* src, size_t bytes)
+{
+    CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return LBFGS_B200_OK;
+}
+lbfgs_b200_status lbfgs_b200_memset_zero(lbfgs_b200_ctx* ctx, void* dst, size_t bytes)
+{
+    CU(ctx, cudaMemsetAsync(dst, 0, bytes, ctx->stream));
+    return LBFGS_B200_OK;
+}
+lbfgs_b200_status lbfgs_b200_sync(lbfgs_b200_ctx* ctx)
+{
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return LBFGS_B200_OK;
+}
+
+lbfgs_b200_status lbfgs_b200_timer_start(lbfgs_b200_ctx* ctx)
+{
+    CU(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    return LBFGS_B200_OK;
+}
+lbfgs_b200_status lbfgs_b200_timer_stop(lbfgs_b200_ctx* ctx, float* ms)
+{
+    CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(ctx, cudaEventSynchronize(ctx->ev1));
+    CU(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return LBFGS_B200_OK;
+}
+lbfgs_b200_status lbfgs_b200_set_index_offset(lbfgs_b200_ctx* ctx, int64_t offset)
+{
+    REQUIRE(ctx, ctx != nullptr, "set_index_offset: NULL context");
+    ctx->index_offset = offset;
+    return LBFGS_B200_OK;
+}
+
+lbfgs_b200_status lbfgs_b200_comm_unique_id(void* unique_id_128)
+{
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    ncclResult_t r = ncclGetUniqueId(&id);
+    if (r != ncclSuccess) return fail(nullptr, LBFGS_B200_ERR_COMM, "ncclGetUniqueId failed: %s", ncclGetErrorString(r));
+    memcpy(unique_id_128, &id, sizeof(id));
+    return LBFGS_B200_OK;
+}
+lbfgs_b200_status lbfgs_b200_comm_init(lbfgs_b200_ctx* ctx, const void* unique_id_128, int rank, int nranks)
+{
+    REQUIRE(ctx, ctx && unique_id_128 && nranks >= 1 && rank >= 0 && rank < nranks, "comm_init: bad arguments");
+    ncclUniqueId id;
+    memcpy(&id, unique_id_128, sizeof(id));
+    CU(ctx, cudaSetDevice(ctx->device));
+    NC(ctx, ncclCommInitRank(&ctx->comm, nranks, id, rank));
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    return LBFGS_B200_OK;
+}
+int lbfgs_b200_comm_size(const lbfgs_b200_ctx* ctx) { return ctx ? ctx->nranks : 0; }
+
+}  // extern "C"
+
+// =====================================================================================================
+// typed implementations behind the f64 / f32 entry points
+// =====================================================================================================
+template <class T> static bool all_aligned(std::initializer_list<const void*> ps)
+{
+    for (const void* p : ps)
+        if (p && !pack_aligned<T>(p)) return false;
+    return true;
+}
+
+template <class T>
+static lbfgs_b200_status do_dot(lbfgs_b200_ctx* ctx, int64_t n, const T* a, const T* b, T* out_host)
+{
+    REQUIRE(ctx, ctx && a && b && out_host && n >= 0, "dot: bad arguments");
+    const int grid = grid_for(ctx, n);
+    if (all_aligned<T>({a, b})) k_dots<T, 1, true><<<grid, kThreads, 0, ctx->stream>>>(n, a, b, nullptr, ctx->rb);
+    else k_dots<T, 1, false><<<grid, kThreads, 0, ctx->stream>>>(n, a, b, nullptr, ctx->rb);
+    if (auto st = post_launch(ctx, "k_dots<1>")) return st;
+    if (auto st = allreduce_result(ctx, 1)) return st;
+    if (auto st = fetch_result(ctx, 1)) return st;
+    *out_host = (T)ctx->h_result[0];
+    return LBFGS_B200_OK;
+}
+
+template <class T>
+static lbfgs_b200_status do_dot3(lbfgs_b200_ctx* ctx, int64_t n, const T* g, const T* d, const T* x, T* out3)
+{
+    REQUIRE(ctx, ctx && g && d && x && out3 && n >= 0, "dot3: bad arguments");
+    const int grid = grid_for(ctx, n);
+    if (all_aligned<T>({g, d, x})) k_dots<T, 3, true><<<grid, kThreads, 0, ctx->stream>>>(n, g, d, x, ctx->rb);
+    else k_dots<T, 3, false><<<grid, kThreads, 0, ctx->stream>>>(n, g, d, x, ctx->rb);
+    if (auto st = post_launch(ctx, "k_dots<3>")) return st;
+    if (auto st = allreduce_result(ctx, 3)) return st;
+    if (auto st = fetch_result(ctx, 3)) return st;
+    for (int k = 0; k < 3; k++) out3[k] = (T)ctx->h_result[k];
+    return LBFGS_B200_OK;
+}
+
+template <class T>
+static lbfgs_b200_status do_axpy_out(lbfgs_b200_ctx* ctx, int64_t n, const T* a, T s, const T* b, T* out)
+{
+    REQUIRE(ctx, ctx && a && b && out && n >= 0, "axpy_out: bad arguments");
+    const int grid = grid_for(ctx, n);
+    if (all_aligned<T>({a, b, out})) k_axpy_out<T, true><<<grid, kThreads, 0, ctx->stream>>>(n, a, s, b, out);
+    else k_axpy_out<T, false><<<grid, kThreads, 0, ctx->stream>>>(n, a, s, b, out);
+    return post_launch(ctx, "k_axpy_out");
+}
+
+template <class T>
+static lbfgs_b200_status do_scale_out(lbfgs_b200_ctx* ctx, int64_t n, T s, const T* a, T* out)
+{
+    REQUIRE(ctx, ctx && a && out && n >= 0, "scale_out: bad arguments");
+    const int grid = grid_for(ctx, n);
+    if (all_aligned<T>({a, out})) k_scale_out<T, true><<<grid, kThreads, 0, ctx->stream>>>(n, s, a, out);
+    else k_scale_out<T, false><<<grid, kThreads, 0, ctx->stream>>>(n, s, a, out);
+    return post_launch(ctx, "k_scale_out");
+}
+
+template <class T, class OBJ, bool TRIAL>
+static lbfgs_b200_status launch_trial(lbfgs_b200_ctx* ctx, const OBJ& obj, int64_t n, const T* xp, const T* d, T step,
+                                      T* x, T* g, bool vec)
+{
+    const int grid = grid_for(ctx, n, 2);
+    if (vec) k_trial<T, OBJ, TRIAL, true><<<grid, kThreads, 0, ctx->stream>>>(obj, n, xp, d, step, x, g, ctx->rb);
+    else k_trial<T, OBJ, TRIAL, false><<<grid, kThreads, 0, ctx->stream>>>(obj, n, xp, d, step, x, g, ctx->rb);
+    return post_launch(ctx, "k_trial");
+}
+
+template <class T, bool TRIAL>
+static lbfgs_b200_status do_trial(lbfgs_b200_ctx* ctx, int objective, const T* data0, const T* data1, int64_t n,
+                                  const T* xp, const T* d, T step, T* x, T* g, T* out_host)
+{
+    REQUIRE(ctx, ctx && x && g && out_host && n >= 1, "trial/objective: bad arguments");
+    if (TRIAL) REQUIRE(ctx, xp && d, "trial: xp/d are NULL");
+    REQUIRE(ctx, ctx->nranks == 1 || objective == LBFGS_B200_OBJ_ROSENBROCK_PAIRED || objective == LBFGS_B200_OBJ_QUAD_SHIFT,
+            "objective %d couples neighbouring coordinates: n-sharding needs a halo exchange (not implemented)", objective);
+    const bool vec = all_aligned<T>({xp, d, x, g});
+    lbfgs_b200_status st = LBFGS_B200_OK;
+    switch (objective)
+    {
+    case LBFGS_B200_OBJ_ROSENBROCK_PAIRED:
+    {
+        REQUIRE(ctx, n % 2 == 0, "paired Rosenbrock needs an even n (got %lld)", (long long)n);
+        RosenbrockPaired<T> o{n};
+        st = launch_trial<T, RosenbrockPaired<T>, TRIAL>(ctx, o, n, xp, d, step, x, g, vec);
+        break;
+    }
+    case LBFGS_B200_OBJ_QUAD_SHIFT:
+    {
+        QuadShift<T> o{n, ctx->index_offset};
+        st = launch_trial<T, QuadShift<T>, TRIAL>(ctx, o, n, xp, d, step, x, g, vec);
+        break;
+    }
+    case LBFGS_B200_OBJ_ROSENBROCK_CHAINED:
+    {
+        REQUIRE(ctx, n >= 2, "chained Rosenbrock needs n >= 2");
+        RosenbrockChained<T> o{n};
+        st = launch_trial<T, RosenbrockChained<T>, TRIAL>(ctx, o, n, xp, d, step, x, g, vec);
+        break;
+    }
+    case LBFGS_B200_OBJ_QUAD_TRIDIAG:
+    {
+        REQUIRE(ctx, data0 && data1, "quad_tridiag needs data0 = diag, data1 = rhs");
+        QuadTridiag<T> o{n, data0, data1};
+        st = launch_trial<T, QuadTridiag<T>, TRIAL>(ctx, o, n, xp, d, step, x, g, vec);
+        break;
+    }
+    default: return fail(ctx, LBFGS_B200_ERR_INVALID, "unknown objective id %d", objective);
+    }
+    if (st) return st;
+    if (auto s2 = allreduce_result(ctx, 4)) return s2;
+    if (auto s2 = fetch_result(ctx, 4)) return s2;
+    for (int k = 0; k < 4; k++) out_host[k] = (T)ctx->h_result[k];
+    if (!TRIAL) out_host[1] = T(0);
+    return LBFGS_B200_OK;
+}
+
+// ----------------------------------------------------------------------------- history
+template <class T> static lbfgs_b200_status hist_check(lbfgs_b200_hist* h)
+{
+    if (!h || !h->ctx) return LBFGS_B200_ERR_INVALID;
+    if (h->elem != (int)sizeof(T)) return fail(h->ctx, LBFGS_B200_ERR_INVALID, "history holds %d-byte elements, called with %zu-byte type", h->elem, sizeof(T));
+    return LBFGS_B200_OK;
+}
+
+template <class T>
+static lbfgs_b200_status commit_pair(lbfgs_b200_hist* h, T eps, int gate, int* accepted_host, T* sy_yy_host)
+{
+    lbfgs_b200_ctx* ctx = h->ctx;
+    if (auto st = allreduce_result(ctx, 2)) return st;
+    T* ys = static_cast<T*>(h->ys) + h->head;
+    k_commit_pair<T><<<1, 1, 0, ctx->stream>>>(ctx->rb.result, eps, gate, ys, static_cast<T*>(h->theta), ctx->d_flag);
+    if (auto st = post_launch(ctx, "k_commit_pair")) return st;
+    CU(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (auto st = fetch_result(ctx, 2)) return st;  // synchronises
+    const int ok = ctx->h_flag[0];
+    if (ok)
+    {
+        h->head = (h->head + 1) % h->M;
+        if (h->ncorr < h->m) h->ncorr++;
+    }
+    if (accepted_host) *accepted_host = ok;
+    if (sy_yy_host) { sy_yy_host[0] = (T)ctx->h_result[0]; sy_yy_host[1] = (T)ctx->h_result[1]; }
+    return LBFGS_B200_OK;
+}
+
+template <class T>
+static lbfgs_b200_status do_hist_update(lbfgs_b200_hist* h, const T* x, const T* xp, const T* g, const T* gp, T eps,
+                                        int* accepted_host, T* sy_yy_host)
+{
+    if (auto st = hist_check<T>(h)) return st;
+    lbfgs_b200_ctx* ctx = h->ctx;
+    REQUIRE(ctx, x && xp && g && gp, "hist_update: NULL vector");
+    T* s_out = h->s_col<T>(h->head);
+    T* y_out = h->y_col<T>(h->head);
+    const int grid = grid_for(ctx, h->n, 2);
+    if (all_aligned<T>({x, xp, g, gp}))
+        k_update<T, true><<<grid, kThreads, 0, ctx->stream>>>(h->n, x, xp, g, gp, s_out, y_out, ctx->rb);
+    else
+        k_update<T, false><<<grid, kThreads, 0, ctx->stream>>>(h->n, x, xp, g, gp, s_out, y_out, ctx->rb);
+    if (auto st = post_launch(ctx, "k_update")) return st;
+    return commit_pair<T>(h, eps, 1, accepted_host, sy_yy_host);
+}
+
+template <class T> static lbfgs_b200_status do_hist_add(lbfgs_b200_hist* h, const T* s, const T* y)
+{
+    if (auto st = hist_check<T>(h)) return st;
+    lbfgs_b200_ctx* ctx = h->ctx;
+    REQUIRE(ctx, s && y, "hist_add: NULL vector");
+    const int grid = grid_for(ctx, h->n, 2);
+    if (all_aligned<T>({s, y}))
+        k_add_pair<T, true><<<grid, kThreads, 0, ctx->stream>>>(h->n, s, y, h->s_col<T>(h->head), h->y_col<T>(h->head), ctx->rb);
+    else
+        k_add_pair<T, false><<<grid, kThreads, 0, ctx->stream>>>(h->n, s, y, h->s_col<T>(h->head), h->y_col<T>(h->head), ctx->rb);
+    if (auto st = post_launch(ctx, "k_add_pair")) return st;
+    return commit_pair<T>(h, T(0), 0, nullptr, nullptr);
+}
+
+template <class T, int KIND>
+static lbfgs_b200_status launch_stage(lbfgs_b200_ctx* ctx, const StageArgs<T>& s, bool vec)
+{
+    const int grid = grid_for(ctx, s.n, 2);
+    if (vec) k_hv_stage<T, KIND, true><<<grid, kThreads, 0, ctx->stream>>>(s, ctx->rb);
+    else k_hv_stage<T, KIND, false><<<grid, kThreads, 0, ctx->stream>>>(s, ctx->rb);
+    if (auto st = post_launch(ctx, "k_hv_stage")) return st;
+    if (s.B != nullptr) return allreduce_result(ctx, 1);
+    return LBFGS_B200_OK;
+}
+
+// literal two-loop recursion, one stage kernel per column visit (2c+1 launches, no host sync in between)
+template <class T>
+static lbfgs_b200_status hv_two_loop(lbfgs_b200_hist* h, const T* v, T a, T* res, bool want_vdot)
+{
+    lbfgs_b200_ctx* ctx = h->ctx;
+    const int c = h->ncorr;
+    const bool vec = all_aligned<T>({v, res});
+    T* ys = static_cast<T*>(h->ys);
+    T* al = static_cast<T*>(h->alpha);
+    StageArgs<T> s{};
+    s.n = h->n; s.v = v; s.a = a; s.q = res; s.dot_prev = ctx->rb.result; s.theta = static_cast<T*>(h->theta);
+    if (c == 0)
+    {
+        s.B = want_vdot ? v : nullptr;
+        return launch_stage<T, HV_ONLY>(ctx, s, vec);
+    }
+    // FIRST: q = a*v ; dot(s_newest, q)
+    s.B = h->s_col<T>(h->slot(0));
+    if (auto st = launch_stage<T, HV_FIRST>(ctx, s, vec)) return st;
+    // backward sweep, newest -> oldest (BFGSMat.h:285-290)
+    for (int age = 0; age < c; age++)
+    {
+        const int j = h->slot(age);
+        s.A = h->y_col<T>(j);
+        s.ys_j = ys + j;
+        s.alpha_j = al + j;
+        if (age + 1 < c)
+        {
+            s.B = h->s_col<T>(h->slot(age + 1));
+            if (auto st = launch_stage<T, HV_BACK>(ctx, s, vec)) return st;
+        }
+        else
+        {
+            s.B = h->y_col<T>(j);  // the forward sweep starts at the oldest pair (BFGSMat.h:293-298)
+            if (auto st = launch_stage<T, HV_MID>(ctx, s, vec)) return st;
+        }
+    }
+    // forward sweep, oldest -> newest (BFGSMat.h:296-301)
+    for (int age = c - 1; age >= 0; age--)
+    {
+        const int j = h->slot(age);
+        s.A = h->s_col<T>(j);
+        s.ys_j = ys + j;
+        s.alpha_j = al + j;
+        s.B = (age > 0) ? h->y_col<T>(h->slot(age - 1)) : (want_vdot ? v : nullptr);
+        if (auto st = launch_stage<T, HV_FWD>(ctx, s, vec)) return st;
+    }
+    return LBFGS_B200_OK;
+}
+
+template <class T>
+static lbfgs_b200_status do_hist_apply_Hv(lbfgs_b200_hist* h, const T* v, T a, T* res, int algo, T* vdot_host)
+{
+    if (auto st = hist_check<T>(h)) return st;
+    lbfgs_b200_ctx* ctx = h->ctx;
+    REQUIRE(ctx, v && res && v != res, "apply_Hv: v/res NULL or aliased");
+    REQUIRE(ctx, algo >= LBFGS_B200_HV_AUTO && algo <= LBFGS_B200_HV_RESIDENT, "apply_Hv: unknown algorithm %d", algo);
+    lbfgs_b200_status st = hv_two_loop<T>(h, v, a, res, vdot_host != nullptr);
+    if (st) return st;
+    if (vdot_host)
+    {
+        if (auto s2 = fetch_result(ctx, 1)) return s2;
+        *vdot_host = (T)ctx->h_result[0];
+    }
+    return LBFGS_B200_OK;
+}
+
+template <class T>
+static lbfgs_b200_status do_hist_scalars(lbfgs_b200_hist* h, T* theta_host, T* ys_host, T* alpha_host)
+{
+    if (auto st = hist_check<T>(h)) return st;
+    lbfgs_b200_ctx* ctx = h->ctx;
+    T tmp[2 * 65 + 1];
+    REQUIRE(ctx, h->M <= 65, "hist_scalars: m too large for the inspection buffer");
+    CU(ctx, cudaMemcpyAsync(tmp, h->ys, sizeof(T) * h->M, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(tmp + 65, h->alpha, sizeof(T) * h->M, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(tmp + 130, h->theta, sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (theta_host) *theta_host = tmp[130];
+    for (int age = 0; age < h->ncorr; age++)
+    {
+        if (ys_host) ys_host[age] = tmp[h->slot(age)];
+        if (alpha_host) alpha_host[age] = tmp[65 + h->slot(age)];
+    }
+    return LBFGS_B200_OK;
+}
+
+// =====================================================================================================
+// C ABI: typed entry points
+// =====================================================================================================
+extern "C" {
+
+#define DEFINE_L1(T, SUF)                                                                                      \
+    lbfgs_b200_status lbfgs_b200_dot_##SUF(lbfgs_b200_ctx* c, int64_t n, const T* a, const T* b, T* o)         \
+    { return do_dot<T>(c, n, a, b, o); }                                                                       \
+    lbfgs_b200_status lbfgs_b200_dot3_##SUF(lbfgs_b200_ctx* c, int64_t n, const T* g, const T* d, const T* x,  \
+                                            T* o) { return do_dot3<T>(c, n, g, d, x, o); }                     \
+    lbfgs_b200_status lbfgs_b200_axpy_out_##SUF(lbfgs_b200_ctx* c, int64_t n, const T* a, T s, const T* b,     \
+                                                T* o) { return do_axpy_out<T>(c, n, a, s, b, o); }             \
+    lbfgs_b200_status lbfgs_b200_scale_out_##SUF(lbfgs_b200_ctx* c, int64_t n, T s, const T* a, T* o)          \
+    { return do_scale_out<T>(c, n, s, a, o); }                                                                 \
+    lbfgs_b200_status lbfgs_b200_objective_##SUF(lbfgs_b200_ctx* c, int obj, const T* d0, const T* d1,         \
+                                                 int64_t n, const T* x, T* g, T* fx)                           \
+    { return do_trial<T, false>(c, obj, d0, d1, n, nullptr, nullptr, T(0), const_cast<T*>(x), g, fx); }        \
+    lbfgs_b200_status lbfgs_b200_trial_##SUF(lbfgs_b200_ctx* c, int obj, const T* d0, const T* d1, int64_t n,  \
+                                             const T* xp, const T* d, T step, T* x, T* g, T* out4)             \
+    { return do_trial<T, true>(c, obj, d0, d1, n, xp, d, step, x, g, out4); }
+
+DEFINE_L1(double, f64)
+DEFINE_L1(float, f32)
+
+lbfgs_b200_status lbfgs_b200_hist_create(lbfgs_b200_ctx* ctx, lbfgs_b200_hist** out, int64_t n, int m, int elem_bytes)
+{
+    REQUIRE(ctx, ctx && out, "hist_create: NULL argument");
+    *out = nullptr;
+    REQUIRE(ctx, n >= 1 && m >= 1 && m <= 64, "hist_create: need n >= 1 and 1 <= m <= 64 (got n=%lld m=%d)", (long long)n, m);
+    REQUIRE(ctx, elem_bytes == 8 || elem_bytes == 4, "hist_create: elem_bytes must be 8 or 4");
+    lbfgs_b200_hist* h = new (std::nothrow) lbfgs_b200_hist();
+    if (!h) return fail(ctx, LBFGS_B200_ERR_ALLOC, "out of host memory");
+    h->ctx = ctx; h->n = n; h->m = m; h->M = m + 1; h->elem = elem_bytes;
+    h->ld = (n + 31) & ~int64_t(31);  // columns start on 256-byte (fp64) / 128-byte (fp32) boundaries
+    const size_t colbytes = (size_t)h->ld * elem_bytes * h->M;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e == cudaSuccess) e = cudaMalloc(&h->S, colbytes);
+    if (e == cudaSuccess) e = cudaMalloc(&h->Y, colbytes);
+    if (e == cudaSuccess) e = cudaMalloc(&h->ys, (size_t)elem_bytes * h->M);
+    if (e == cudaSuccess) e = cudaMalloc(&h->alpha, (size_t)elem_bytes * h->M);
+    if (e == cudaSuccess) e = cudaMalloc(&h->theta, 8);
+    if (e != cudaSuccess)
+    {
+        lbfgs_b200_hist_destroy(h);
+        return fail(ctx, e == cudaErrorMemoryAllocation ? LBFGS_B200_ERR_ALLOC : LBFGS_B200_ERR_CUDA,
+                    "hist_create(n=%lld, m=%d): %s", (long long)n, m, cudaGetErrorString(e));
+    }
+    *out = h;
+    return lbfgs_b200_hist_reset(h);
+}
+
+void lbfgs_b200_hist_destroy(lbfgs_b200_hist* h)
+{
+    if (!h) return;
+    if (h->ctx && h->ctx->stream) cudaStreamSynchronize(h->ctx->stream);
+    cudaFree(h->S); cudaFree(h->Y); cudaFree(h->ys); cudaFree(h->alpha); cudaFree(h->theta);
+    delete h;
+}
+
+lbfgs_b200_status lbfgs_b200_hist_reset(lbfgs_b200_hist* h)
+{
+    if (!h || !h->ctx) return LBFGS_B200_ERR_INVALID;
+    lbfgs_b200_ctx* ctx = h->ctx;
+    h->head = 0;
+    h->ncorr = 0;
+    CU(ctx, cudaMemsetAsync(h->ys, 0, (size_t)h->elem * h->M, ctx->stream));
+    CU(ctx, cudaMemsetAsync(h->alpha, 0, (size_t)h->elem * h->M, ctx->stream));
+    if (h->elem == 8) { const double one = 1.0; CU(ctx, cudaMemcpyAsync(h->theta, &one, 8, cudaMemcpyHostToDevice, ctx->stream)); }
+    else { const float one = 1.0f; CU(ctx, cudaMemcpyAsync(h->theta, &one, 4, cudaMemcpyHostToDevice, ctx->stream)); }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));  // `one` lives on this stack frame
+    return LBFGS_B200_OK;
+}
+
+int lbfgs_b200_hist_ncorr(const lbfgs_b200_hist* h) { return h ? h->ncorr : 0; }
+int lbfgs_b200_hist_m(const lbfgs_b200_hist* h) { return h ? h->m : 0; }
+const void* lbfgs_b200_hist_s_col(const lbfgs_b200_hist* h, int age)
+{
+    if (!h || age < 0 || age >= h->ncorr) return nullptr;
+    return static_cast<const char*>(h->S) + (size_t)h->slot(age) * h->ld * h->elem;
+}
+const void* lbfgs_b200_hist_y_col(const lbfgs_b200_hist* h, int age)
+{
+    if (!h || age < 0 || age >= h->ncorr) return nullptr;
+    return static_cast<const char*>(h->Y) + (size_t)h->slot(age) * h->ld * h->elem;
+}
+
+#define DEFINE_HIST(T, SUF)                                                                                    \
+    lbfgs_b200_status lbfgs_b200_hist_update_##SUF(lbfgs_b200_hist* h, const T* x, const T* xp, const T* g,    \
+                                                   const T* gp, T eps, int* acc, T* sy_yy)                     \
+    { return do_hist_update<T>(h, x, xp, g, gp, eps, acc, sy_yy); }                                            \
+    lbfgs_b200_status lbfgs_b200_hist_add_##SUF(lbfgs_b200_hist* h, const T* s, const T* y)                    \
+    { return do_hist_add<T>(h, s, y); }                                                                        \
+    lbfgs_b200_status lbfgs_b200_hist_apply_Hv_##SUF(lbfgs_b200_hist* h, const T* v, T a, T* res, int algo,    \
+                                                     T* vdot) { return do_hist_apply_Hv<T>(h, v, a, res, algo, vdot); } \
+    lbfgs_b200_status lbfgs_b200_hist_scalars_##SUF(lbfgs_b200_hist* h, T* th, T* ys, T* al)                   \
+    { return do_hist_scalars<T>(h, th, ys, al); }
+
+DEFINE_HIST(double, f64)
+DEFINE_HIST(float, f32)
+
+}  // extern "C"
