@@ -48,10 +48,11 @@ enum {
 
 /* apply_Hv algorithms */
 enum {
-    LBFGS_B200_HV_AUTO = 0,      /* RESIDENT when the shard fits on chip, else GRAM                           */
-    LBFGS_B200_HV_TWO_LOOP = 1,  /* literal two-loop recursion, one fused AXPY+dot stage kernel per history column */
-    LBFGS_B200_HV_GRAM = 2,      /* same recursion carried out on 2c coefficients (two passes over S,Y)        */
-    LBFGS_B200_HV_RESIDENT = 3   /* literal two-loop in ONE persistent cooperative kernel, q/r in registers    */
+    LBFGS_B200_HV_AUTO = 0,      /* currently GRAM                                                             */
+    LBFGS_B200_HV_TWO_LOOP = 1,  /* literal two-loop recursion, one fused AXPY+dot stage kernel per history column:
+                                    (8c+4) n words of traffic, 2c+1 launches, 2c collectives when sharded      */
+    LBFGS_B200_HV_GRAM = 2       /* the same recursion carried out on 2c coefficients: two passes over S,Y,
+                                    (4c+3) n words, 3 launches, 1 collective; differs from TWO_LOOP by rounding */
 };
 
 /* ---------------------------------------------------------------- context, memory, communicator */
@@ -76,6 +77,13 @@ lbfgs_b200_status lbfgs_b200_sync(lbfgs_b200_ctx* ctx);
 /* CUDA-event stopwatch on the context's stream (device time of everything enqueued in between) */
 lbfgs_b200_status lbfgs_b200_timer_start(lbfgs_b200_ctx* ctx);
 lbfgs_b200_status lbfgs_b200_timer_stop(lbfgs_b200_ctx* ctx, float* elapsed_ms_host); /* synchronises */
+/* Optional device-time accounting per phase (0 = apply_Hv, 1 = line-search trial, 2 = history update): when
+ * enabled every such call is bracketed by a CUDA event pair on the context's stream; profile_read synchronises,
+ * returns the accumulated milliseconds / call count and optionally clears them. */
+lbfgs_b200_status lbfgs_b200_profile_enable(lbfgs_b200_ctx* ctx, int on);
+lbfgs_b200_status lbfgs_b200_profile_read(lbfgs_b200_ctx* ctx, int phase, double* total_ms_host, uint64_t* calls_host, int reset);
+/* algorithmic bytes of the profiled calls: apply_Hv w*n*(4c+2), trial w*n*4 (+2 for data vectors), update w*n*6 */
+lbfgs_b200_status lbfgs_b200_profile_bytes(lbfgs_b200_ctx* ctx, int phase, double* alg_bytes_host, int reset);
 /* n-sharding: global index of this rank's element 0 (used by objectives that depend on the coordinate index) */
 lbfgs_b200_status lbfgs_b200_set_index_offset(lbfgs_b200_ctx* ctx, int64_t offset);
 

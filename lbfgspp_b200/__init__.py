@@ -20,7 +20,7 @@ from . import build as _build
 PKG = os.path.dirname(os.path.abspath(__file__))
 
 OBJ_ROSENBROCK_PAIRED, OBJ_QUAD_SHIFT, OBJ_ROSENBROCK_CHAINED, OBJ_QUAD_TRIDIAG = 0, 1, 2, 3
-HV_AUTO, HV_TWO_LOOP, HV_GRAM, HV_RESIDENT = 0, 1, 2, 3
+HV_AUTO, HV_TWO_LOOP, HV_GRAM = 0, 1, 2
 LINE_SEARCHES = {"Backtracking": 0, "Bracketing": 1, "NocedalWright": 2, "MoreThuente": 3}
 LBFGS_LINESEARCH_BACKTRACKING_ARMIJO = 1
 LBFGS_LINESEARCH_BACKTRACKING = 2
@@ -78,6 +78,9 @@ def abi():
     lib.lbfgs_b200_timer_start.argtypes = [vp]
     lib.lbfgs_b200_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     lib.lbfgs_b200_set_index_offset.argtypes = [vp, i64]
+    lib.lbfgs_b200_profile_enable.argtypes = [vp, ci]
+    lib.lbfgs_b200_profile_read.argtypes = [vp, ci, C.POINTER(C.c_double), C.POINTER(C.c_uint64), ci]
+    lib.lbfgs_b200_profile_bytes.argtypes = [vp, ci, C.POINTER(C.c_double), ci]
     lib.lbfgs_b200_comm_unique_id.argtypes = [vp]
     lib.lbfgs_b200_comm_init.argtypes = [vp, vp, ci, ci]
     lib.lbfgs_b200_comm_size.argtypes = [vp]
@@ -133,6 +136,15 @@ def driver():
                                             C.c_int, fp, fp, dp, C.c_long, C.POINTER(_DrvResult)]
     lib.lbfgsb200_drv_ctx.restype = C.c_void_p
     lib.lbfgsb200_drv_ctx.argtypes = [C.c_int]
+    lib.lbfgsb200_drv_session_create.restype = C.c_void_p
+    lib.lbfgsb200_drv_session_create.argtypes = [C.c_int, C.c_int, dp, dp, C.c_long, C.c_int, C.POINTER(_DrvParam), C.c_int, dp,
+                                                 C.c_char_p, C.c_int]
+    lib.lbfgsb200_drv_session_destroy.argtypes = [C.c_void_p]
+    lib.lbfgsb200_drv_session_destroy.restype = None
+    lib.lbfgsb200_drv_session_solve.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(_DrvResult)]
+    lib.lbfgsb200_drv_session_result.restype = dp
+    lib.lbfgsb200_drv_session_result.argtypes = [C.c_void_p]
+    lib.lbfgsb200_drv_comm_init.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_char_p, C.c_int]
     lib._typed = True
     return lib
 
@@ -375,6 +387,65 @@ class History:
         out = np.empty(self.n, dtype=self.dtype)
         self.ctx.check(self.ctx.lib.lbfgs_b200_memcpy_d2h(self.ctx.h, out.ctypes.data_as(C.c_void_p), p, out.nbytes))
         return out
+
+
+class Session:
+    """A solver and its vectors kept resident on one GPU (bench.py): solve() repeats the same problem."""
+
+    def __init__(self, objective, x0, param, linesearch="MoreThuente", device=0, hv_algo=HV_AUTO, data0=None, data1=None):
+        self.drv = driver()
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        self.n = x0.size
+        dp = C.POINTER(C.c_double)
+        ptr = lambda a: a.ctypes.data_as(dp) if a is not None else None
+        d0 = None if data0 is None else np.ascontiguousarray(data0, dtype=np.float64)
+        d1 = None if data1 is None else np.ascontiguousarray(data1, dtype=np.float64)
+        err = C.create_string_buffer(256)
+        p = param._c()
+        ls = LINE_SEARCHES[linesearch] if isinstance(linesearch, str) else int(linesearch)
+        self.h = self.drv.lbfgsb200_drv_session_create(device, objective, ptr(d0), ptr(d1), self.n, ls, C.byref(p), hv_algo,
+                                                       ptr(x0), err, 256)
+        if not self.h:
+            raise RuntimeError("session_create failed: " + err.value.decode())
+
+    def solve(self, from_host=False, to_host=False):
+        res = _DrvResult()
+        self.drv.lbfgsb200_drv_session_solve(self.h, int(from_host), int(to_host), C.byref(res))
+        if res.status:
+            raise RuntimeError(res.msg.decode())
+        return dict(niter=res.niter, nfev=res.nfev, fx=res.fx, gnorm=res.gnorm, launches=res.launches,
+                    h2d_bytes=res.h2d_bytes, d2h_bytes=res.d2h_bytes)
+
+    def result(self):
+        p = self.drv.lbfgsb200_drv_session_result(self.h)
+        return np.ctypeslib.as_array(p, shape=(self.n,)).copy()
+
+    def close(self):
+        if self.h:
+            self.drv.lbfgsb200_drv_session_destroy(self.h)
+            self.h = None
+
+
+def driver_ctx(device=0):
+    """The lbfgs_b200_ctx* the driver uses for `device` (so that the raw ABI / profiling can address it)."""
+    return C.c_void_p(driver().lbfgsb200_drv_ctx(device))
+
+
+def comm_init(device, unique_id_bytes, rank, nranks, index_offset=0):
+    """Attach an NCCL communicator to the driver's context of `device`: n is sharded over `nranks` GPUs."""
+    err = C.create_string_buffer(256)
+    buf = C.create_string_buffer(bytes(unique_id_bytes), 128)
+    st = driver().lbfgsb200_drv_comm_init(device, buf, rank, nranks, index_offset, err, 256)
+    if st:
+        raise RuntimeError("comm_init failed: " + err.value.decode())
+
+
+def comm_unique_id():
+    buf = C.create_string_buffer(128)
+    st = abi().lbfgs_b200_comm_unique_id(buf)
+    if st:
+        raise RuntimeError("ncclGetUniqueId failed")
+    return buf.raw
 
 
 def build_all(force=False):

@@ -246,3 +246,130 @@ void* lbfgsb200_drv_ctx(int device_ordinal)
 void lbfgsb200_drv_shutdown(void) { devices().clear(); }
 
 }  // extern "C"
+
+// ----------------------------------------------------------------------------------------------------------
+// Sessions: a solver + its vectors kept alive across solves (what a long-running user of the C++ front does;
+// the reference re-allocates everything per minimize() call, LBFGS.h:40-50).  bench.py times these.
+// ----------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Session
+{
+    Device* dev;
+    long n;
+    int ls;
+    LBFGSParam<double> prm;
+    DeviceVector<double> x0, x, d0, d1;
+    BuiltinObjective<double> obj;
+    // one solver per line-search policy (only the selected one is used)
+    LBFGSSolver<double, LineSearchBacktracking> s_bt;
+    LBFGSSolver<double, LineSearchBracketing> s_br;
+    LBFGSSolver<double, LineSearchNocedalWright> s_nw;
+    LBFGSSolver<double, LineSearchMoreThuente> s_mt;
+    double* pinned_in;   // host staging (pinned): x0 for the end-to-end path
+    double* pinned_out;  // host staging (pinned): result x
+    Session(Device& d, long n_, int ls_, const drv_param* q, int objective) :
+        dev(&d), n(n_), ls(ls_), prm(to_param<double>(q)), x0(d), x(d), d0(d), d1(d), obj(objective),
+        s_bt(prm), s_br(prm), s_nw(prm), s_mt(prm), pinned_in(nullptr), pinned_out(nullptr) {}
+};
+
+}  // namespace
+
+extern "C" {
+
+// x0_host (n) is uploaded once and kept on the device; data0/data1 (n each, optional) likewise.
+void* lbfgsb200_drv_session_create(int device_ordinal, int objective, const double* data0_host, const double* data1_host,
+                                   long n, int ls, const drv_param* prm, int hv_algo, const double* x0_host, char* err, int errlen)
+{
+    try
+    {
+        Device& dev = device(device_ordinal);
+        std::unique_ptr<Session> s(new Session(dev, n, ls, prm, objective));
+        s->x0.copy_from_host(x0_host, n);
+        s->x.resize(n);
+        if (data0_host) s->d0.copy_from_host(data0_host, n);
+        if (data1_host) s->d1.copy_from_host(data1_host, n);
+        s->obj = BuiltinObjective<double>(objective, s->d0.data(), s->d1.data());
+        void* p = nullptr;
+        dev.check(lbfgs_b200_malloc_host(dev.ctx(), &p, sizeof(double) * size_t(n)));
+        s->pinned_in = static_cast<double*>(p);
+        dev.check(lbfgs_b200_malloc_host(dev.ctx(), &p, sizeof(double) * size_t(n)));
+        s->pinned_out = static_cast<double*>(p);
+        std::memcpy(s->pinned_in, x0_host, sizeof(double) * size_t(n));
+        s->s_bt.set_hv_algorithm(hv_algo);
+        s->s_br.set_hv_algorithm(hv_algo);
+        s->s_nw.set_hv_algorithm(hv_algo);
+        s->s_mt.set_hv_algorithm(hv_algo);
+        return s.release();
+    }
+    catch (const std::exception& e)
+    {
+        if (err && errlen > 0) { std::strncpy(err, e.what(), size_t(errlen) - 1); err[errlen - 1] = 0; }
+        return nullptr;
+    }
+}
+
+void lbfgsb200_drv_session_destroy(void* handle)
+{
+    Session* s = static_cast<Session*>(handle);
+    if (!s) return;
+    lbfgs_b200_free_host(s->dev->ctx(), s->pinned_in);
+    lbfgs_b200_free_host(s->dev->ctx(), s->pinned_out);
+    delete s;
+}
+
+// One solve.  from_host = 1: the start point is copied host(pinned) -> device inside the call (end-to-end path);
+// from_host = 0: it is copied device -> device from the resident x0.  to_host = 1: the result x is copied back to
+// pinned host memory before returning.  No stream synchronisation is added beyond what minimize() itself needs,
+// except for the final download.
+int lbfgsb200_drv_session_solve(void* handle, int from_host, int to_host, drv_result* out)
+{
+    Session* s = static_cast<Session*>(handle);
+    return guarded(out, [&]() {
+        Device& dev = *s->dev;
+        const size_t bytes = sizeof(double) * size_t(s->n);
+        if (from_host) dev.check(lbfgs_b200_memcpy_h2d(dev.ctx(), s->x.data(), s->pinned_in, bytes));
+        else dev.check(lbfgs_b200_memcpy_d2d(dev.ctx(), s->x.data(), s->x0.data(), bytes));
+        const unsigned long long launches0 = lbfgs_b200_launch_count(dev.ctx());
+        double fx = 0;
+        int niter = 0;
+        long nfev = 0;
+        double gnorm = 0;
+        switch (s->ls)
+        {
+        case DRV_LS_BACKTRACKING: niter = s->s_bt.minimize(s->obj, s->x, fx); nfev = s->s_bt.num_evaluations(); gnorm = s->s_bt.final_grad_norm(); break;
+        case DRV_LS_BRACKETING: niter = s->s_br.minimize(s->obj, s->x, fx); nfev = s->s_br.num_evaluations(); gnorm = s->s_br.final_grad_norm(); break;
+        case DRV_LS_NOCEDAL_WRIGHT: niter = s->s_nw.minimize(s->obj, s->x, fx); nfev = s->s_nw.num_evaluations(); gnorm = s->s_nw.final_grad_norm(); break;
+        default: niter = s->s_mt.minimize(s->obj, s->x, fx); nfev = s->s_mt.num_evaluations(); gnorm = s->s_mt.final_grad_norm(); break;
+        }
+        if (to_host) dev.check(lbfgs_b200_memcpy_d2h(dev.ctx(), s->pinned_out, s->x.data(), bytes));
+        out->niter = niter;
+        out->nfev = nfev;
+        out->fx = fx;
+        out->gnorm = gnorm;
+        out->launches = lbfgs_b200_launch_count(dev.ctx()) - launches0;
+        out->h2d_bytes = from_host ? long(bytes) : 0;
+        out->d2h_bytes = to_host ? long(bytes) : 0;
+    });
+}
+
+const double* lbfgsb200_drv_session_result(void* handle) { return static_cast<Session*>(handle)->pinned_out; }
+
+}  // extern "C"
+
+extern "C" int lbfgsb200_drv_comm_init(int device_ordinal, const void* unique_id_128, int rank, int nranks, long long index_offset,
+                                       char* err, int errlen)
+{
+    try
+    {
+        Device& dev = device(device_ordinal);
+        dev.check(lbfgs_b200_comm_init(dev.ctx(), unique_id_128, rank, nranks));
+        dev.check(lbfgs_b200_set_index_offset(dev.ctx(), index_offset));
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        if (err && errlen > 0) { std::strncpy(err, e.what(), size_t(errlen) - 1); err[errlen - 1] = 0; }
+        return 1;
+    }
+}

@@ -19,10 +19,12 @@
 #include <limits>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/lbfgs_b200.h"
 #include "device_utils.cuh"
 #include "objectives.cuh"
+#include "two_loop_gram.cuh"
 
 using namespace lb;
 
@@ -37,6 +39,8 @@ struct lbfgs_b200_ctx
     int sm_count = 148;
     ReduceBuf rb{};                // device scratch for grid_reduce
     double* h_result = nullptr;    // pinned mirror of rb.result (+ extra slots)
+    double* gram_partials = nullptr;  // [sm_count][kMaxM*kGramVals] block partials of k_gram_dots
+    double* gram_raw = nullptr;    // [kMaxM*kGramVals] reduced dots
     int* d_flag = nullptr;         // device int flags (accepted, ...)
     int* h_flag = nullptr;         // pinned
     ncclComm_t comm = nullptr;
@@ -44,7 +48,41 @@ struct lbfgs_b200_ctx
     int64_t index_offset = 0;      // global index of this rank's element 0
     uint64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // optional per-phase device timing (lbfgs_b200_profile_*): event pairs recorded around each call
+    bool profiling = false;
+    struct Span { cudaEvent_t a, b; };
+    std::vector<Span> spans[3];   // recorded, not yet read
+    std::vector<Span> free_spans;
+    double prof_ms[3] = {0, 0, 0};
+    uint64_t prof_calls[3] = {0, 0, 0};
+    double prof_bytes[3] = {0, 0, 0};   // algorithmic bytes of the calls made while profiling
     std::string err;
+};
+
+enum { PH_APPLY_HV = 0, PH_TRIAL = 1, PH_UPDATE = 2 };
+
+// RAII span: records an event pair on the context's stream around a C-ABI call when profiling is on
+struct ProfSpan
+{
+    lbfgs_b200_ctx* ctx;
+    int phase;
+    lbfgs_b200_ctx::Span sp{nullptr, nullptr};
+    ProfSpan(lbfgs_b200_ctx* c, int ph, double alg_bytes = 0.0) : ctx(c), phase(ph)
+    {
+        if (!ctx || !ctx->profiling) return;
+        ctx->prof_bytes[ph] += alg_bytes;
+        if (!ctx->free_spans.empty()) { sp = ctx->free_spans.back(); ctx->free_spans.pop_back(); }
+        else { cudaEventCreate(&sp.a); cudaEventCreate(&sp.b); }
+        cudaEventRecord(sp.a, ctx->stream);
+    }
+    void stop()
+    {
+        if (!sp.a) return;
+        cudaEventRecord(sp.b, ctx->stream);
+        ctx->spans[phase].push_back(sp);
+        sp.a = nullptr;
+    }
+    ~ProfSpan() { stop(); }
 };
 
 static thread_local std::string g_create_err;
@@ -263,6 +301,8 @@ struct lbfgs_b200_hist
     int64_t n = 0, ld = 0;
     int m = 0, M = 0, elem = 8;
     void *S = nullptr, *Y = nullptr, *ys = nullptr, *alpha = nullptr, *theta = nullptr;
+    void *SY = nullptr, *YY = nullptr, *coef = nullptr;  // Gram matrices [M][M] and combination coefficients [2m+1]
+    int pending = -1;  // physical slot of the newest pair whose Gram row/column has not been folded in yet
     int head = 0;   // physical slot the next pair is written to
     int ncorr = 0;  // valid pairs (<= m)
     // physical slot of the pair with the given age (0 = newest)
@@ -467,6 +507,8 @@ lbfgs_b200_status lbfgs_b200_ctx_create(lbfgs_b200_ctx** out, int device, void* 
     CUC(cudaMalloc(&ctx->rb.ticket, sizeof(unsigned)));
     CUC(cudaMalloc(&ctx->rb.result, sizeof(double) * 256));
     CUC(cudaMalloc(&ctx->d_flag, sizeof(int) * 16));
+    CUC(cudaMalloc(&ctx->gram_partials, sizeof(double) * (size_t)ctx->sm_count * kMaxM * kGramVals));
+    CUC(cudaMalloc(&ctx->gram_raw, sizeof(double) * kMaxM * kGramVals));
     CUC(cudaMemsetAsync(ctx->rb.ticket, 0, sizeof(unsigned), ctx->stream));
     CUC(cudaMemsetAsync(ctx->rb.result, 0, sizeof(double) * 256, ctx->stream));
     CUC(cudaMallocHost(&ctx->h_result, sizeof(double) * 256));
@@ -489,8 +531,12 @@ void lbfgs_b200_ctx_destroy(lbfgs_b200_ctx* ctx)
     cudaFree(ctx->rb.ticket);
     cudaFree(ctx->rb.result);
     cudaFree(ctx->d_flag);
+    cudaFree(ctx->gram_partials);
+    cudaFree(ctx->gram_raw);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+    for (int ph = 0; ph < 3; ph++) for (auto& sp : ctx->spans[ph]) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto& sp : ctx->free_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -566,6 +612,37 @@ lbfgs_b200_status lbfgs_b200_timer_stop(lbfgs_b200_ctx* ctx, float* ms)
     CU(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     CU(ctx, cudaEventSynchronize(ctx->ev1));
     CU(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return LBFGS_B200_OK;
+}
+lbfgs_b200_status lbfgs_b200_profile_enable(lbfgs_b200_ctx* ctx, int on)
+{
+    REQUIRE(ctx, ctx != nullptr, "profile_enable: NULL context");
+    ctx->profiling = on != 0;
+    return LBFGS_B200_OK;
+}
+lbfgs_b200_status lbfgs_b200_profile_read(lbfgs_b200_ctx* ctx, int phase, double* total_ms, uint64_t* calls, int reset)
+{
+    REQUIRE(ctx, ctx && phase >= 0 && phase < 3, "profile_read: bad arguments");
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& sp : ctx->spans[phase])
+    {
+        float ms = 0.f;
+        CU(ctx, cudaEventElapsedTime(&ms, sp.a, sp.b));
+        ctx->prof_ms[phase] += ms;
+        ctx->prof_calls[phase]++;
+        ctx->free_spans.push_back(sp);
+    }
+    ctx->spans[phase].clear();
+    if (total_ms) *total_ms = ctx->prof_ms[phase];
+    if (calls) *calls = ctx->prof_calls[phase];
+    if (reset) { ctx->prof_ms[phase] = 0; ctx->prof_calls[phase] = 0; }
+    return LBFGS_B200_OK;
+}
+lbfgs_b200_status lbfgs_b200_profile_bytes(lbfgs_b200_ctx* ctx, int phase, double* alg_bytes, int reset)
+{
+    REQUIRE(ctx, ctx && phase >= 0 && phase < 3 && alg_bytes, "profile_bytes: bad arguments");
+    *alg_bytes = ctx->prof_bytes[phase];
+    if (reset) ctx->prof_bytes[phase] = 0;
     return LBFGS_B200_OK;
 }
 lbfgs_b200_status lbfgs_b200_set_index_offset(lbfgs_b200_ctx* ctx, int64_t offset)
@@ -677,6 +754,7 @@ static lbfgs_b200_status do_trial(lbfgs_b200_ctx* ctx, int objective, const T* d
             "objective %d couples neighbouring coordinates: n-sharding needs a halo exchange (not implemented)", objective);
     const bool vec = all_aligned<T>({xp, d, x, g});
     lbfgs_b200_status st = LBFGS_B200_OK;
+    ProfSpan span(ctx, PH_TRIAL, double(sizeof(T)) * double(n) * ((TRIAL ? 4.0 : 2.0) + (objective == LBFGS_B200_OBJ_QUAD_TRIDIAG ? 2.0 : 0.0)));
     switch (objective)
     {
     case LBFGS_B200_OBJ_ROSENBROCK_PAIRED:
@@ -710,6 +788,7 @@ static lbfgs_b200_status do_trial(lbfgs_b200_ctx* ctx, int objective, const T* d
     }
     if (st) return st;
     if (auto s2 = allreduce_result(ctx, 4)) return s2;
+    span.stop();
     if (auto s2 = fetch_result(ctx, 4)) return s2;
     for (int k = 0; k < 4; k++) out_host[k] = (T)ctx->h_result[k];
     if (!TRIAL) out_host[1] = T(0);
@@ -724,6 +803,8 @@ template <class T> static lbfgs_b200_status hist_check(lbfgs_b200_hist* h)
     return LBFGS_B200_OK;
 }
 
+template <class T> static lbfgs_b200_status gram_refresh(lbfgs_b200_hist* h);
+
 template <class T>
 static lbfgs_b200_status commit_pair(lbfgs_b200_hist* h, T eps, int gate, int* accepted_host, T* sy_yy_host)
 {
@@ -737,8 +818,12 @@ static lbfgs_b200_status commit_pair(lbfgs_b200_hist* h, T eps, int gate, int* a
     const int ok = ctx->h_flag[0];
     if (ok)
     {
+        const int written = h->head;
         h->head = (h->head + 1) % h->M;
         if (h->ncorr < h->m) h->ncorr++;
+        if (h->pending >= 0)  // two pairs appended back to back: fold the earlier one now
+            if (auto st = gram_refresh<T>(h)) return st;
+        h->pending = written;
     }
     if (accepted_host) *accepted_host = ok;
     if (sy_yy_host) { sy_yy_host[0] = (T)ctx->h_result[0]; sy_yy_host[1] = (T)ctx->h_result[1]; }
@@ -754,12 +839,14 @@ static lbfgs_b200_status do_hist_update(lbfgs_b200_hist* h, const T* x, const T*
     REQUIRE(ctx, x && xp && g && gp, "hist_update: NULL vector");
     T* s_out = h->s_col<T>(h->head);
     T* y_out = h->y_col<T>(h->head);
+    ProfSpan span(ctx, PH_UPDATE, double(sizeof(T)) * double(h->n) * 6.0);
     const int grid = grid_for(ctx, h->n, 2);
     if (all_aligned<T>({x, xp, g, gp}))
         k_update<T, true><<<grid, kThreads, 0, ctx->stream>>>(h->n, x, xp, g, gp, s_out, y_out, ctx->rb);
     else
         k_update<T, false><<<grid, kThreads, 0, ctx->stream>>>(h->n, x, xp, g, gp, s_out, y_out, ctx->rb);
     if (auto st = post_launch(ctx, "k_update")) return st;
+    span.stop();
     return commit_pair<T>(h, eps, 1, accepted_host, sy_yy_host);
 }
 
@@ -838,14 +925,108 @@ static lbfgs_b200_status hv_two_loop(lbfgs_b200_hist* h, const T* v, T a, T* res
     return LBFGS_B200_OK;
 }
 
+// ----------------------------------------------------------------------------- Gram-form apply_Hv
+template <class T> static void fill_slots(const lbfgs_b200_hist* h, unsigned char* slots)
+{
+    for (int age = 0; age < h->ncorr; age++) slots[age] = (unsigned char)h->slot(age);
+}
+
+// [S Y]'[v s_new y_new] (+ all-reduce).  v == nullptr: only the new pair's Gram row/column ("refresh").
+template <class T>
+static lbfgs_b200_status gram_dots(lbfgs_b200_hist* h, const T* v)
+{
+    lbfgs_b200_ctx* ctx = h->ctx;
+    const int c = h->ncorr;
+    GramDotsArgs<T> a{};
+    a.n = h->n; a.ld = h->ld; a.v = v;
+    a.S = static_cast<const T*>(h->S); a.Y = static_cast<const T*>(h->Y);
+    a.c = c; a.new_slot = h->pending;
+    int split = 1;
+    while (c * split * 2 <= kGramWarps && split * 2 <= 8) split *= 2;
+    a.split = split;
+    a.use_tma = (v == nullptr || (reinterpret_cast<uintptr_t>(v) & 15) == 0) ? 1 : 0;
+    fill_slots<T>(h, a.slots);
+    const int per_round = kGramWarps / split;
+    const int rounds = (c + per_round - 1) / per_round;
+    const int64_t ntiles = (h->n + kGramTE - 1) / kGramTE;
+    const int grid = (int)(ntiles < ctx->sm_count ? ntiles : ctx->sm_count);
+    const size_t smem = (size_t)kGramStages * 3 * kGramTE * sizeof(T);
+#define LAUNCH_GRAM(R)                                                                                       \
+    do {                                                                                                     \
+        static bool attr_set = false;                                                                        \
+        if (!attr_set) {                                                                                     \
+            CU(ctx, cudaFuncSetAttribute(k_gram_dots<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            attr_set = true;                                                                                 \
+        }                                                                                                    \
+        k_gram_dots<T, R><<<grid, kGramThreads, smem, ctx->stream>>>(a, ctx->gram_partials, ctx->rb.ticket, ctx->gram_raw); \
+    } while (0)
+    if (rounds <= 1) LAUNCH_GRAM(1);
+    else if (rounds == 2) LAUNCH_GRAM(2);
+    else LAUNCH_GRAM(4);
+#undef LAUNCH_GRAM
+    if (auto st = post_launch(ctx, "k_gram_dots")) return st;
+    if (ctx->nranks > 1)
+        NC(ctx, ncclAllReduce(ctx->gram_raw, ctx->gram_raw, c * kGramVals, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+    return LBFGS_B200_OK;
+}
+
+template <class T>
+static lbfgs_b200_status gram_solve(lbfgs_b200_hist* h, T a_scale, bool with_v)
+{
+    lbfgs_b200_ctx* ctx = h->ctx;
+    GramSolveArgs<T> g{};
+    g.c = h->ncorr; g.M = h->M; g.new_slot = h->pending; g.with_v = with_v ? 1 : 0; g.a = a_scale;
+    g.raw = ctx->gram_raw;
+    g.SY = static_cast<T*>(h->SY); g.YY = static_cast<T*>(h->YY);
+    g.ys = static_cast<const T*>(h->ys); g.alpha = static_cast<T*>(h->alpha);
+    g.theta = static_cast<const T*>(h->theta); g.coef = static_cast<T*>(h->coef);
+    fill_slots<T>(h, g.slots);
+    k_gram_solve<T><<<1, 32, 0, ctx->stream>>>(g);
+    if (auto st = post_launch(ctx, "k_gram_solve")) return st;
+    h->pending = -1;
+    return LBFGS_B200_OK;
+}
+
+// fold a pending pair into SY/YY without an apply_Hv (only needed when pairs are appended back to back)
+template <class T> static lbfgs_b200_status gram_refresh(lbfgs_b200_hist* h)
+{
+    if (h->pending < 0 || h->ncorr == 0) { h->pending = -1; return LBFGS_B200_OK; }
+    if (auto st = gram_dots<T>(h, nullptr)) return st;
+    return gram_solve<T>(h, T(0), false);
+}
+
+template <class T>
+static lbfgs_b200_status hv_gram(lbfgs_b200_hist* h, const T* v, T a, T* res, bool want_vdot)
+{
+    lbfgs_b200_ctx* ctx = h->ctx;
+    const int c = h->ncorr;
+    if (auto st = gram_dots<T>(h, v)) return st;
+    if (auto st = gram_solve<T>(h, a, true)) return st;
+    GramCombineArgs<T> k{};
+    k.n = h->n; k.ld = h->ld; k.v = v;
+    k.S = static_cast<const T*>(h->S); k.Y = static_cast<const T*>(h->Y);
+    k.res = res; k.coef = static_cast<const T*>(h->coef); k.c = c; k.want_dot = want_vdot ? 1 : 0;
+    fill_slots<T>(h, k.slots);
+    const int grid = grid_for(ctx, h->n, 1);
+    if (all_aligned<T>({v, res})) k_gram_combine<T, true><<<grid, kThreads, 0, ctx->stream>>>(k, ctx->rb);
+    else k_gram_combine<T, false><<<grid, kThreads, 0, ctx->stream>>>(k, ctx->rb);
+    if (auto st = post_launch(ctx, "k_gram_combine")) return st;
+    if (want_vdot) return allreduce_result(ctx, 1);
+    return LBFGS_B200_OK;
+}
+
 template <class T>
 static lbfgs_b200_status do_hist_apply_Hv(lbfgs_b200_hist* h, const T* v, T a, T* res, int algo, T* vdot_host)
 {
     if (auto st = hist_check<T>(h)) return st;
     lbfgs_b200_ctx* ctx = h->ctx;
     REQUIRE(ctx, v && res && v != res, "apply_Hv: v/res NULL or aliased");
-    REQUIRE(ctx, algo >= LBFGS_B200_HV_AUTO && algo <= LBFGS_B200_HV_RESIDENT, "apply_Hv: unknown algorithm %d", algo);
-    lbfgs_b200_status st = hv_two_loop<T>(h, v, a, res, vdot_host != nullptr);
+    REQUIRE(ctx, algo >= LBFGS_B200_HV_AUTO && algo <= LBFGS_B200_HV_GRAM, "apply_Hv: unknown algorithm %d", algo);
+    const bool gram = (algo != LBFGS_B200_HV_TWO_LOOP) && h->ncorr > 0;
+    ProfSpan span(ctx, PH_APPLY_HV, double(sizeof(T)) * double(h->n) * (4.0 * h->ncorr + 2.0));
+    lbfgs_b200_status st = gram ? hv_gram<T>(h, v, a, res, vdot_host != nullptr)
+                                : hv_two_loop<T>(h, v, a, res, vdot_host != nullptr);
+    span.stop();
     if (st) return st;
     if (vdot_host)
     {
@@ -916,6 +1097,9 @@ lbfgs_b200_status lbfgs_b200_hist_create(lbfgs_b200_ctx* ctx, lbfgs_b200_hist** 
     if (e == cudaSuccess) e = cudaMalloc(&h->ys, (size_t)elem_bytes * h->M);
     if (e == cudaSuccess) e = cudaMalloc(&h->alpha, (size_t)elem_bytes * h->M);
     if (e == cudaSuccess) e = cudaMalloc(&h->theta, 8);
+    if (e == cudaSuccess) e = cudaMalloc(&h->SY, (size_t)elem_bytes * h->M * h->M);
+    if (e == cudaSuccess) e = cudaMalloc(&h->YY, (size_t)elem_bytes * h->M * h->M);
+    if (e == cudaSuccess) e = cudaMalloc(&h->coef, (size_t)elem_bytes * (2 * h->M + 1));
     if (e != cudaSuccess)
     {
         lbfgs_b200_hist_destroy(h);
@@ -931,6 +1115,7 @@ void lbfgs_b200_hist_destroy(lbfgs_b200_hist* h)
     if (!h) return;
     if (h->ctx && h->ctx->stream) cudaStreamSynchronize(h->ctx->stream);
     cudaFree(h->S); cudaFree(h->Y); cudaFree(h->ys); cudaFree(h->alpha); cudaFree(h->theta);
+    cudaFree(h->SY); cudaFree(h->YY); cudaFree(h->coef);
     delete h;
 }
 
@@ -940,6 +1125,9 @@ lbfgs_b200_status lbfgs_b200_hist_reset(lbfgs_b200_hist* h)
     lbfgs_b200_ctx* ctx = h->ctx;
     h->head = 0;
     h->ncorr = 0;
+    h->pending = -1;
+    CU(ctx, cudaMemsetAsync(h->SY, 0, (size_t)h->elem * h->M * h->M, ctx->stream));
+    CU(ctx, cudaMemsetAsync(h->YY, 0, (size_t)h->elem * h->M * h->M, ctx->stream));
     CU(ctx, cudaMemsetAsync(h->ys, 0, (size_t)h->elem * h->M, ctx->stream));
     CU(ctx, cudaMemsetAsync(h->alpha, 0, (size_t)h->elem * h->M, ctx->stream));
     if (h->elem == 8) { const double one = 1.0; CU(ctx, cudaMemcpyAsync(h->theta, &one, 8, cudaMemcpyHostToDevice, ctx->stream)); }
