@@ -138,6 +138,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--hv", default="auto", choices=["auto", "two_loop", "gram"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-mode", action="store_true", help="timed region only (for runs under ncu; numbers are not bench values)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -222,12 +223,12 @@ def main():
     abi.lbfgs_b200_profile_enable(ctx, 0)
 
     # ---- timed region 2: end to end (pinned host -> device every step, result back to the host) --------------------
-    for _ in range(2):
+    for _ in range(0 if args.profile_mode else 2):
         sess.solve(from_host=True, to_host=True)
     barrier()
     t0 = time.perf_counter()
     e2e_iters, h2d, d2h = 0, 0, 0
-    for _ in range(args.steps):
+    for _ in range(1 if args.profile_mode else args.steps):
         r2 = sess.solve(from_host=True, to_host=True)
         e2e_iters += r2["niter"]
         h2d, d2h = r2["h2d_bytes"], r2["d2h_bytes"] + 8  # + the fx scalar
@@ -242,7 +243,7 @@ def main():
     blk = rng.standard_normal(1 << 20)
     def noise(seed):
         return np.resize(np.roll(blk, seed * 7919), n_local)
-    if world == 1:  # the microbenchmark uses a private context without a communicator: N = 1 only
+    if world == 1 and not args.profile_mode:  # the microbenchmark uses a private context without a communicator: N = 1 only
         for k in range(M_HIST):
             s = noise(k)
             hist.add(mctx.array(s), mctx.array(s + 0.1 * noise(100 + k)))
@@ -288,7 +289,7 @@ def main():
         "phase_gb_per_s": {k: (v["alg_bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None) for k, v in phases.items()},
     }
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.profile_mode:
         po, orc = load_oracle(native=True)
         r_cpu, wall = cpu_solve(po, orc, po.SUM_LANES8)
         line["cpu_baseline"] = {"value": r_cpu["niter"] / r_cpu["seconds"], "unit": "iters/s", "cores": 1, "kind": "port",

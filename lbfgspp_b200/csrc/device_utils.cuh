@@ -28,13 +28,13 @@ template <Hint H> __device__ __forceinline__ Pack<double> ld_pack(const double* 
 {
     Pack<double> r;
     if (H == Hint::Stream)
-        asm volatile("ld.global.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
+        asm("ld.global.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
                      : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p));
     else if (H == Hint::Keep)
-        asm volatile("ld.global.L1::no_allocate.L2::evict_last.v4.f64 {%0,%1,%2,%3}, [%4];"
+        asm("ld.global.L1::no_allocate.L2::evict_last.v4.f64 {%0,%1,%2,%3}, [%4];"
                      : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p));
     else
-        asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+        asm("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
                      : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p));
     return r;
 }
@@ -55,10 +55,10 @@ template <Hint H> __device__ __forceinline__ Pack<float> ld_pack(const float* p)
 {
     Pack<float> r;
     if (H == Hint::Plain)
-        asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+        asm("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];"
                      : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p));
     else
-        asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+        asm("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                      : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p));
     return r;
 }

@@ -301,7 +301,9 @@ struct lbfgs_b200_hist
     int64_t n = 0, ld = 0;
     int m = 0, M = 0, elem = 8;
     void *S = nullptr, *Y = nullptr, *ys = nullptr, *alpha = nullptr, *theta = nullptr;
-    void *SY = nullptr, *YY = nullptr, *coef = nullptr;  // Gram matrices [M][M] and combination coefficients [2m+1]
+    void* SY[2] = {nullptr, nullptr};  // Gram matrices [M][M] by physical slot, double-buffered (see k_gram_combine)
+    void* YY[2] = {nullptr, nullptr};
+    int gram_cur = 0;  // which buffer is current
     int pending = -1;  // physical slot of the newest pair whose Gram row/column has not been folded in yet
     int head = 0;   // physical slot the next pair is written to
     int ncorr = 0;  // valid pairs (<= m)
@@ -818,11 +820,12 @@ static lbfgs_b200_status commit_pair(lbfgs_b200_hist* h, T eps, int gate, int* a
     const int ok = ctx->h_flag[0];
     if (ok)
     {
+        // two pairs appended back to back: fold the earlier one while it is still the newest (age 0)
+        if (h->pending >= 0)
+            if (auto st = gram_refresh<T>(h)) return st;
         const int written = h->head;
         h->head = (h->head + 1) % h->M;
         if (h->ncorr < h->m) h->ncorr++;
-        if (h->pending >= 0)  // two pairs appended back to back: fold the earlier one now
-            if (auto st = gram_refresh<T>(h)) return st;
         h->pending = written;
     }
     if (accepted_host) *accepted_host = ok;
@@ -941,13 +944,15 @@ static lbfgs_b200_status gram_dots(lbfgs_b200_hist* h, const T* v)
     a.n = h->n; a.ld = h->ld; a.v = v;
     a.S = static_cast<const T*>(h->S); a.Y = static_cast<const T*>(h->Y);
     a.c = c; a.new_slot = h->pending;
-    int split = 1;
-    while (c * split * 2 <= kGramWarps && split * 2 <= 8) split *= 2;
+    // warps = (column pairs in flight) x (warps per column pair); as many of the 24 warp slots as divide evenly
+    int split = 8;
+    while (split > 1 && c * split > kGramMaxWarps) split >>= 1;
     a.split = split;
+    a.cols_per_round = c < kGramMaxWarps / split ? c : kGramMaxWarps / split;
     a.use_tma = (v == nullptr || (reinterpret_cast<uintptr_t>(v) & 15) == 0) ? 1 : 0;
     fill_slots<T>(h, a.slots);
-    const int per_round = kGramWarps / split;
-    const int rounds = (c + per_round - 1) / per_round;
+    const int rounds = (c + a.cols_per_round - 1) / a.cols_per_round;
+    const int threads = a.cols_per_round * split * 32;
     const int64_t ntiles = (h->n + kGramTE - 1) / kGramTE;
     const int grid = (int)(ntiles < ctx->sm_count ? ntiles : ctx->sm_count);
     const size_t smem = (size_t)kGramStages * 3 * kGramTE * sizeof(T);
@@ -958,11 +963,11 @@ static lbfgs_b200_status gram_dots(lbfgs_b200_hist* h, const T* v)
             CU(ctx, cudaFuncSetAttribute(k_gram_dots<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             attr_set = true;                                                                                 \
         }                                                                                                    \
-        k_gram_dots<T, R><<<grid, kGramThreads, smem, ctx->stream>>>(a, ctx->gram_partials, ctx->rb.ticket, ctx->gram_raw); \
+        k_gram_dots<T, R><<<grid, threads, smem, ctx->stream>>>(a, ctx->gram_partials, ctx->rb.ticket, ctx->gram_raw); \
     } while (0)
     if (rounds <= 1) LAUNCH_GRAM(1);
     else if (rounds == 2) LAUNCH_GRAM(2);
-    else LAUNCH_GRAM(4);
+    else LAUNCH_GRAM(3);
 #undef LAUNCH_GRAM
     if (auto st = post_launch(ctx, "k_gram_dots")) return st;
     if (ctx->nranks > 1)
@@ -970,47 +975,65 @@ static lbfgs_b200_status gram_dots(lbfgs_b200_hist* h, const T* v)
     return LBFGS_B200_OK;
 }
 
-template <class T>
-static lbfgs_b200_status gram_solve(lbfgs_b200_hist* h, T a_scale, bool with_v)
+template <class T> static GramSolveArgs<T> make_solve_args(lbfgs_b200_hist* h, T a_scale, bool with_v)
 {
     lbfgs_b200_ctx* ctx = h->ctx;
     GramSolveArgs<T> g{};
     g.c = h->ncorr; g.M = h->M; g.new_slot = h->pending; g.with_v = with_v ? 1 : 0; g.a = a_scale;
     g.raw = ctx->gram_raw;
-    g.SY = static_cast<T*>(h->SY); g.YY = static_cast<T*>(h->YY);
+    const int in = h->gram_cur, out = (h->pending >= 0) ? 1 - h->gram_cur : h->gram_cur;
+    g.SY_in = static_cast<const T*>(h->SY[in]); g.YY_in = static_cast<const T*>(h->YY[in]);
+    g.SY_out = static_cast<T*>(h->SY[out]); g.YY_out = static_cast<T*>(h->YY[out]);
     g.ys = static_cast<const T*>(h->ys); g.alpha = static_cast<T*>(h->alpha);
-    g.theta = static_cast<const T*>(h->theta); g.coef = static_cast<T*>(h->coef);
+    g.theta = static_cast<const T*>(h->theta);
     fill_slots<T>(h, g.slots);
-    k_gram_solve<T><<<1, 32, 0, ctx->stream>>>(g);
-    if (auto st = post_launch(ctx, "k_gram_solve")) return st;
+    return g;
+}
+// after a kernel that folded the pending pair: the freshly written buffer becomes current
+static void gram_folded(lbfgs_b200_hist* h)
+{
+    if (h->pending >= 0) h->gram_cur = 1 - h->gram_cur;
     h->pending = -1;
-    return LBFGS_B200_OK;
 }
 
 // fold a pending pair into SY/YY without an apply_Hv (only needed when pairs are appended back to back)
 template <class T> static lbfgs_b200_status gram_refresh(lbfgs_b200_hist* h)
 {
     if (h->pending < 0 || h->ncorr == 0) { h->pending = -1; return LBFGS_B200_OK; }
+    lbfgs_b200_ctx* ctx = h->ctx;
     if (auto st = gram_dots<T>(h, nullptr)) return st;
-    return gram_solve<T>(h, T(0), false);
+    const GramSolveArgs<T> g = make_solve_args<T>(h, T(0), false);
+    const size_t smem = gram_solve_smem_elems(h->ncorr) * sizeof(T);
+    if (smem > 48 * 1024)
+        CU(ctx, cudaFuncSetAttribute(k_gram_fold<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_gram_fold<T><<<1, 256, smem, ctx->stream>>>(g);
+    if (auto st = post_launch(ctx, "k_gram_fold")) return st;
+    gram_folded(h);
+    return LBFGS_B200_OK;
 }
 
 template <class T>
 static lbfgs_b200_status hv_gram(lbfgs_b200_hist* h, const T* v, T a, T* res, bool want_vdot)
 {
     lbfgs_b200_ctx* ctx = h->ctx;
-    const int c = h->ncorr;
     if (auto st = gram_dots<T>(h, v)) return st;
-    if (auto st = gram_solve<T>(h, a, true)) return st;
     GramCombineArgs<T> k{};
     k.n = h->n; k.ld = h->ld; k.v = v;
     k.S = static_cast<const T*>(h->S); k.Y = static_cast<const T*>(h->Y);
-    k.res = res; k.coef = static_cast<const T*>(h->coef); k.c = c; k.want_dot = want_vdot ? 1 : 0;
-    fill_slots<T>(h, k.slots);
+    k.res = res; k.want_dot = want_vdot ? 1 : 0;
+    k.solve = make_solve_args<T>(h, a, true);
     const int grid = grid_for(ctx, h->n, 1);
-    if (all_aligned<T>({v, res})) k_gram_combine<T, true><<<grid, kThreads, 0, ctx->stream>>>(k, ctx->rb);
-    else k_gram_combine<T, false><<<grid, kThreads, 0, ctx->stream>>>(k, ctx->rb);
+    const size_t smem = gram_solve_smem_elems(h->ncorr) * sizeof(T);
+    const bool vec = all_aligned<T>({v, res});
+    if (smem > 40 * 1024)
+    {
+        if (vec) CU(ctx, cudaFuncSetAttribute(k_gram_combine<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else CU(ctx, cudaFuncSetAttribute(k_gram_combine<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    if (vec) k_gram_combine<T, true><<<grid, kThreads, smem, ctx->stream>>>(k, ctx->rb);
+    else k_gram_combine<T, false><<<grid, kThreads, smem, ctx->stream>>>(k, ctx->rb);
     if (auto st = post_launch(ctx, "k_gram_combine")) return st;
+    gram_folded(h);
     if (want_vdot) return allreduce_result(ctx, 1);
     return LBFGS_B200_OK;
 }
@@ -1097,9 +1120,11 @@ lbfgs_b200_status lbfgs_b200_hist_create(lbfgs_b200_ctx* ctx, lbfgs_b200_hist** 
     if (e == cudaSuccess) e = cudaMalloc(&h->ys, (size_t)elem_bytes * h->M);
     if (e == cudaSuccess) e = cudaMalloc(&h->alpha, (size_t)elem_bytes * h->M);
     if (e == cudaSuccess) e = cudaMalloc(&h->theta, 8);
-    if (e == cudaSuccess) e = cudaMalloc(&h->SY, (size_t)elem_bytes * h->M * h->M);
-    if (e == cudaSuccess) e = cudaMalloc(&h->YY, (size_t)elem_bytes * h->M * h->M);
-    if (e == cudaSuccess) e = cudaMalloc(&h->coef, (size_t)elem_bytes * (2 * h->M + 1));
+    for (int b = 0; b < 2; b++)
+    {
+        if (e == cudaSuccess) e = cudaMalloc(&h->SY[b], (size_t)elem_bytes * h->M * h->M);
+        if (e == cudaSuccess) e = cudaMalloc(&h->YY[b], (size_t)elem_bytes * h->M * h->M);
+    }
     if (e != cudaSuccess)
     {
         lbfgs_b200_hist_destroy(h);
@@ -1115,7 +1140,7 @@ void lbfgs_b200_hist_destroy(lbfgs_b200_hist* h)
     if (!h) return;
     if (h->ctx && h->ctx->stream) cudaStreamSynchronize(h->ctx->stream);
     cudaFree(h->S); cudaFree(h->Y); cudaFree(h->ys); cudaFree(h->alpha); cudaFree(h->theta);
-    cudaFree(h->SY); cudaFree(h->YY); cudaFree(h->coef);
+    for (int b = 0; b < 2; b++) { cudaFree(h->SY[b]); cudaFree(h->YY[b]); }
     delete h;
 }
 
@@ -1126,8 +1151,12 @@ lbfgs_b200_status lbfgs_b200_hist_reset(lbfgs_b200_hist* h)
     h->head = 0;
     h->ncorr = 0;
     h->pending = -1;
-    CU(ctx, cudaMemsetAsync(h->SY, 0, (size_t)h->elem * h->M * h->M, ctx->stream));
-    CU(ctx, cudaMemsetAsync(h->YY, 0, (size_t)h->elem * h->M * h->M, ctx->stream));
+    h->gram_cur = 0;
+    for (int b = 0; b < 2; b++)
+    {
+        CU(ctx, cudaMemsetAsync(h->SY[b], 0, (size_t)h->elem * h->M * h->M, ctx->stream));
+        CU(ctx, cudaMemsetAsync(h->YY[b], 0, (size_t)h->elem * h->M * h->M, ctx->stream));
+    }
     CU(ctx, cudaMemsetAsync(h->ys, 0, (size_t)h->elem * h->M, ctx->stream));
     CU(ctx, cudaMemsetAsync(h->alpha, 0, (size_t)h->elem * h->M, ctx->stream));
     if (h->elem == 8) { const double one = 1.0; CU(ctx, cudaMemcpyAsync(h->theta, &one, 8, cudaMemcpyHostToDevice, ctx->stream)); }

@@ -26,8 +26,8 @@ namespace lb {
 
 constexpr int kGramTE = 2048;      // tile length in elements (16 KB of fp64 per staged vector)
 constexpr int kGramStages = 3;
-constexpr int kGramWarps = 16;
-constexpr int kGramThreads = kGramWarps * 32;
+constexpr int kGramMaxWarps = 24;  // 768 threads, one CTA per SM (85 registers per thread available)
+constexpr int kGramMaxThreads = kGramMaxWarps * 32;
 constexpr int kMaxM = 64;
 constexpr int kGramVals = 5;       // per column pair: s.v, y.v, s.ynew, y.ynew, y.snew
 
@@ -39,8 +39,9 @@ template <class T> struct GramDotsArgs
     const T* Y;
     int c;             // number of valid pairs
     int new_slot;      // physical slot of the pair whose Gram row/column is still missing, or -1
-    int split;         // warps cooperating on one column pair (power of two)
-    int use_tma;       // v / columns 16-byte aligned
+    int split;         // warps cooperating on one column pair (1, 2, 4 or 8)
+    int cols_per_round;  // column pairs processed concurrently by one CTA (warps = cols_per_round * split)
+    int use_tma;       // v 16-byte aligned
     unsigned char slots[kMaxM];  // physical slot by age (0 = newest)
 };
 
@@ -74,33 +75,48 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                  :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// pack of 4 from shared memory (two 128-bit LDS)
-template <class T> __device__ __forceinline__ Pack<T> lds_pack(const T* p)
+// Pack of 4 consecutive elements owned by this lane, read from a staged tile.  A lane's pack is 32 bytes, so the
+// two 128-bit halves of neighbouring lanes would collide on the same banks; lanes whose (lane>>2) is odd fetch
+// their upper half first, which makes both LDS.128 wavefronts conflict-free.
+__device__ __forceinline__ Pack<double> lds_pack(const double* p, int lane)
 {
-    Pack<T> r;
-#pragma unroll
-    for (int k = 0; k < 4; k++) r.v[k] = p[k];
+    const int flip = (lane >> 2) & 1;
+    const double2 a = *reinterpret_cast<const double2*>(p + 2 * flip);
+    const double2 b = *reinterpret_cast<const double2*>(p + 2 * (1 - flip));
+    Pack<double> r;
+    r.v[0] = flip ? b.x : a.x;
+    r.v[1] = flip ? b.y : a.y;
+    r.v[2] = flip ? a.x : b.x;
+    r.v[3] = flip ? a.y : b.y;
+    return r;
+}
+__device__ __forceinline__ Pack<float> lds_pack(const float* p, int)
+{
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    Pack<float> r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
     return r;
 }
 
 template <class T, int ROUNDS>
-__global__ void __launch_bounds__(kGramThreads, 1) k_gram_dots(GramDotsArgs<T> a, double* partials, unsigned* ticket, double* result)
+__global__ void __launch_bounds__(kGramMaxThreads, 1) k_gram_dots(GramDotsArgs<T> a, double* partials, unsigned* ticket, double* result)
 {
     extern __shared__ __align__(128) unsigned char gram_smem[];
     T* tiles = reinterpret_cast<T*>(gram_smem);                  // [stage][3][TE]
     __shared__ __align__(8) uint64_t full_bar[kGramStages];
-    __shared__ double s_red[kGramWarps][ROUNDS * kGramVals];
+    __shared__ double s_red[kGramMaxWarps][ROUNDS * kGramVals];
+    __shared__ unsigned char s_slots[kMaxM];
     __shared__ bool s_last;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
     const bool with_v = a.v != nullptr, with_new = a.new_slot >= 0;
     const T* snew = with_new ? a.S + (int64_t)a.new_slot * a.ld : nullptr;
     const T* ynew = with_new ? a.Y + (int64_t)a.new_slot * a.ld : nullptr;
     const int64_t ntiles = (a.n + kGramTE - 1) / kGramTE;
-    const int cols_per_round = kGramWarps / a.split;
     const int my_col = warp / a.split, my_part = warp % a.split;
     const int part_len = kGramTE / a.split;                        // elements of a tile handled by this warp
 
+    if (tid < kMaxM) s_slots[tid] = a.slots[tid];
     if (tid == 0)
     {
         for (int s = 0; s < kGramStages; s++) mbar_init(&full_bar[s], 1);
@@ -129,7 +145,7 @@ __global__ void __launch_bounds__(kGramThreads, 1) k_gram_dots(GramDotsArgs<T> a
         }
         else
         {
-            for (int i = tid; i < kGramTE; i += kGramThreads)
+            for (int i = tid; i < kGramTE; i += nthreads)
             {
                 const bool ok = i < len;
                 dst[i] = (with_v && ok) ? a.v[e0 + i] : T(0);
@@ -167,17 +183,20 @@ __global__ void __launch_bounds__(kGramThreads, 1) k_gram_dots(GramDotsArgs<T> a
         const T* ynt = vt + 2 * kGramTE;
         const int64_t e0 = tile * kGramTE;
         const int64_t len = (a.n - e0 < kGramTE) ? (a.n - e0) : kGramTE;
-        const bool full_tile = (len == kGramTE) && a.use_tma;
+        const bool full_tile = (len == kGramTE);
 
 #pragma unroll
         for (int r = 0; r < ROUNDS; r++)
         {
-            const int j = r * cols_per_round + my_col;
-            if (j < a.c)
+            const int j = r * a.cols_per_round + my_col;
+            if (my_col < a.cols_per_round && j < a.c)
             {
-                const T* scol = a.S + (int64_t)a.slots[j] * a.ld + e0;
-                const T* ycol = a.Y + (int64_t)a.slots[j] * a.ld + e0;
+                const int slot = s_slots[j];
+                const bool is_new = with_new && slot == a.new_slot;   // this column is already staged in shared memory
+                const T* scol = a.S + (int64_t)slot * a.ld + e0;
+                const T* ycol = a.Y + (int64_t)slot * a.ld + e0;
                 // this warp's part of the tile, 2 packs (8 elements) per lane per step
+#pragma unroll 2
                 for (int base = my_part * part_len + lane * 4; base < (my_part + 1) * part_len; base += 256)
                 {
                     Pack<T> ps[2], py[2];
@@ -185,7 +204,12 @@ __global__ void __launch_bounds__(kGramThreads, 1) k_gram_dots(GramDotsArgs<T> a
                     for (int u = 0; u < 2; u++)
                     {
                         const int off = base + u * 128;
-                        if (full_tile)
+                        if (is_new)
+                        {
+                            ps[u] = lds_pack(snt + off, lane);
+                            py[u] = lds_pack(ynt + off, lane);
+                        }
+                        else if (full_tile)
                         {
                             ps[u] = ld_pack<Hint::Stream>(scol + off);
                             py[u] = ld_pack<Hint::Stream>(ycol + off);
@@ -207,7 +231,7 @@ __global__ void __launch_bounds__(kGramThreads, 1) k_gram_dots(GramDotsArgs<T> a
                         const int off = base + u * 128;
                         if (with_v)
                         {
-                            const Pack<T> pv = lds_pack(vt + off);
+                            const Pack<T> pv = lds_pack(vt + off, lane);
 #pragma unroll
                             for (int k = 0; k < 4; k++)
                             {
@@ -217,7 +241,7 @@ __global__ void __launch_bounds__(kGramThreads, 1) k_gram_dots(GramDotsArgs<T> a
                         }
                         if (with_new)
                         {
-                            const Pack<T> pyn = lds_pack(ynt + off), psn = lds_pack(snt + off);
+                            const Pack<T> pyn = lds_pack(ynt + off, lane), psn = lds_pack(snt + off, lane);
 #pragma unroll
                             for (int k = 0; k < 4; k++)
                             {
@@ -247,10 +271,10 @@ __global__ void __launch_bounds__(kGramThreads, 1) k_gram_dots(GramDotsArgs<T> a
         }
     __syncthreads();
     const int nvals = a.c * kGramVals;
-    for (int idx = tid; idx < nvals; idx += kGramThreads)
+    for (int idx = tid; idx < nvals; idx += nthreads)
     {
         const int j = idx / kGramVals, k = idx % kGramVals;
-        const int r = j / cols_per_round, col = j % cols_per_round;
+        const int r = j / a.cols_per_round, col = j % a.cols_per_round;
         double t = 0.0;
         for (int p = 0; p < a.split; p++) t += s_red[col * a.split + p][r * kGramVals + k];
         partials[(size_t)blockIdx.x * (kMaxM * kGramVals) + idx] = t;
@@ -261,7 +285,7 @@ __global__ void __launch_bounds__(kGramThreads, 1) k_gram_dots(GramDotsArgs<T> a
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    for (int idx = tid; idx < nvals; idx += kGramThreads)
+    for (int idx = tid; idx < nvals; idx += nthreads)
     {
         double t = 0.0;
         for (unsigned b = 0; b < gridDim.x; b++) t += __ldcg(&partials[(size_t)b * (kMaxM * kGramVals) + idx]);
@@ -270,69 +294,92 @@ __global__ void __launch_bounds__(kGramThreads, 1) k_gram_dots(GramDotsArgs<T> a
     if (tid == 0) *ticket = 0u;
 }
 
-// ---- the O(c^2) recursion on coefficients: one thread ----------------------------------------------------
+// ---- the O(c^2) recursion on coefficients ---------------------------------------------------------------------
+// Runs in shared memory in the prologue of EVERY CTA of the combine kernel (identical arithmetic everywhere, ~2 us,
+// no extra launch); CTA 0 also writes the folded Gram matrices and the alphas back for the next call.
 template <class T> struct GramSolveArgs
 {
     int c, M, new_slot, with_v;
     T a;                     // scale of v
     const double* raw;       // [c][5] reduced dots (after the all-reduce)
-    T* SY;                   // [M][M] by physical slot: SY[i*M+j] = s_i'y_j
-    T* YY;                   // [M][M]
+    const T* SY_in;          // [M][M] by physical slot: SY[i*M+j] = s_i'y_j
+    const T* YY_in;          // [M][M]
+    T* SY_out;               // folded matrices (a second buffer: other CTAs may still be reading *_in)
+    T* YY_out;
     const T* ys;             // [M]
     T* alpha;                // [M]
     const T* theta;
-    T* coef;                 // out: [0] = cv, [1 + age] = cy_age, [1 + c + age] = cs_age   (age order, newest first)
     unsigned char slots[kMaxM];
 };
 
-template <class T> __global__ void k_gram_solve(GramSolveArgs<T> g)
+// smem layout (T units): SY[c*c] | YY[c*c] | coef[2c+1] | alpha[c] ; everything indexed by AGE (0 = newest).
+inline size_t gram_solve_smem_elems(int c) { return (size_t)2 * c * c + 3 * c + 1; }
+
+template <class T>
+__device__ void gram_solve_in_smem(const GramSolveArgs<T>& g, T* sm, bool writer)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const int c = g.c, M = g.M;
-    // 1. fold the new pair's row/column into the Gram matrices
-    if (g.new_slot >= 0)
+    const int c = g.c, M = g.M, tid = threadIdx.x, nt = blockDim.x;
+    T* sSY = sm;
+    T* sYY = sm + c * c;
+    T* coef = sm + 2 * c * c;
+    T* al = coef + 2 * c + 1;
+    // the pending pair is always the newest one: age 0
+    for (int idx = tid; idx < c * c; idx += nt)
     {
-        const int nw = g.new_slot;
-        for (int i = 0; i < c; i++)
+        const int i = idx / c, j = idx % c;
+        const int pi = g.slots[i], pj = g.slots[j];
+        T sy = g.SY_in[pi * M + pj], yy = g.YY_in[pi * M + pj];
+        if (g.new_slot >= 0)
         {
-            const int j = g.slots[i];
-            g.SY[j * M + nw] = (T)g.raw[i * kGramVals + 2];   // s_j'y_new
-            g.YY[j * M + nw] = (T)g.raw[i * kGramVals + 3];   // y_j'y_new
-            g.YY[nw * M + j] = (T)g.raw[i * kGramVals + 3];
-            g.SY[nw * M + j] = (T)g.raw[i * kGramVals + 4];   // s_new'y_j
+            if (j == 0) { sy = (T)g.raw[i * kGramVals + 2]; yy = (T)g.raw[i * kGramVals + 3]; }       // s_i'y_new, y_i'y_new
+            else if (i == 0) { sy = (T)g.raw[j * kGramVals + 4]; yy = (T)g.raw[j * kGramVals + 3]; }  // s_new'y_j, y_new'y_j
+        }
+        sSY[idx] = sy;
+        sYY[idx] = yy;
+        if (writer && g.new_slot >= 0)
+        {
+            g.SY_out[pi * M + pj] = sy;
+            g.YY_out[pi * M + pj] = yy;
         }
     }
-    if (!g.with_v) return;
-    const T theta = *g.theta;
-    T cs[kMaxM];
-    // 2. backward sweep (BFGSMat.h:285-290): alpha_j = s_j'q / ys_j with q = a*v - sum_{newer t} alpha_t y_t
-    for (int i = 0; i < c; i++)
+    __syncthreads();
+    if (tid == 0 && g.with_v)
     {
-        const int j = g.slots[i];
-        T sq = g.a * (T)g.raw[i * kGramVals + 0];
-        for (int t = 0; t < i; t++) sq -= g.alpha[g.slots[t]] * g.SY[j * M + g.slots[t]];
-        g.alpha[j] = sq / g.ys[j];
+        const T theta = *g.theta;
+        // backward sweep (BFGSMat.h:285-290): alpha_i = s_i'q / ys_i with q = a*v - sum_{newer t} alpha_t y_t
+        for (int i = 0; i < c; i++)
+        {
+            T sq = g.a * (T)g.raw[i * kGramVals + 0];
+            for (int t = 0; t < i; t++) sq -= al[t] * sSY[i * c + t];
+            al[i] = sq / g.ys[g.slots[i]];
+        }
+        // forward sweep (BFGSMat.h:293-301): r = q/theta + sum_{older t} (alpha_t - beta_t) s_t ; beta_i = y_i'r / ys_i
+        T* cs = coef + 1 + c;
+        for (int i = c - 1; i >= 0; i--)
+        {
+            T yq = g.a * (T)g.raw[i * kGramVals + 1];
+            for (int t = 0; t < c; t++) yq -= al[t] * sYY[i * c + t];
+            T yr = yq / theta;
+            for (int t = c - 1; t > i; t--) yr += cs[t] * sSY[t * c + i];
+            const T beta = yr / g.ys[g.slots[i]];
+            cs[i] = al[i] - beta;
+        }
+        coef[0] = g.a / theta;
+        for (int i = 0; i < c; i++) coef[1 + i] = -(al[i] / theta);
+        if (writer)
+            for (int i = 0; i < c; i++) g.alpha[g.slots[i]] = al[i];
     }
-    // 3. forward sweep (BFGSMat.h:293-301): r = q/theta + sum_{older t} (alpha_t - beta_t) s_t ; beta_j = y_j'r / ys_j
-    for (int i = c - 1; i >= 0; i--)
-    {
-        const int j = g.slots[i];
-        T yq = g.a * (T)g.raw[i * kGramVals + 1];
-        for (int t = 0; t < c; t++) yq -= g.alpha[g.slots[t]] * g.YY[j * M + g.slots[t]];
-        T yr = yq / theta;
-        for (int t = c - 1; t > i; t--) yr += cs[t] * g.SY[g.slots[t] * M + j];
-        const T beta = yr / g.ys[j];
-        cs[i] = g.alpha[j] - beta;
-    }
-    g.coef[0] = g.a / theta;
-    for (int i = 0; i < c; i++)
-    {
-        g.coef[1 + i] = -(g.alpha[g.slots[i]] / theta);
-        g.coef[1 + c + i] = cs[i];
-    }
+    __syncthreads();
 }
 
-// ---- res = cv*v + sum_j cy_j*y_j + cs_j*s_j  (+ v.res) ----------------------------------------------------
+// fold only (pairs appended back to back without an apply_Hv in between)
+template <class T> __global__ void k_gram_fold(GramSolveArgs<T> g)
+{
+    extern __shared__ __align__(16) unsigned char fold_smem[];
+    gram_solve_in_smem<T>(g, reinterpret_cast<T*>(fold_smem), true);
+}
+
+// ---- res = cv*v + sum_j cy_j*y_j + cs_j*s_j  (+ v.res), preceded by the coefficient recursion -----------------
 template <class T> struct GramCombineArgs
 {
     int64_t n, ld;
@@ -340,17 +387,25 @@ template <class T> struct GramCombineArgs
     const T* S;
     const T* Y;
     T* res;
-    const T* coef;
-    int c;
     int want_dot;
-    unsigned char slots[kMaxM];
+    GramSolveArgs<T> solve;
 };
 
 template <class T, bool VEC>
 __global__ void __launch_bounds__(kThreads) k_gram_combine(GramCombineArgs<T> a, ReduceBuf rb)
 {
-    __shared__ T s_coef[2 * kMaxM + 1];
-    for (int i = threadIdx.x; i < 2 * a.c + 1; i += kThreads) s_coef[i] = a.coef[i];
+    extern __shared__ __align__(16) unsigned char comb_smem[];
+    T* sm = reinterpret_cast<T*>(comb_smem);
+    const int c = a.solve.c;
+    gram_solve_in_smem<T>(a.solve, sm, blockIdx.x == 0);
+    const T* s_coef = sm + 2 * c * c;
+    __shared__ const T* s_ycol[kMaxM];
+    __shared__ const T* s_scol[kMaxM];
+    for (int j = threadIdx.x; j < c; j += kThreads)
+    {
+        s_ycol[j] = a.Y + (int64_t)a.solve.slots[j] * a.ld;
+        s_scol[j] = a.S + (int64_t)a.solve.slots[j] * a.ld;
+    }
     __syncthreads();
     const T cv = s_coef[0];
     T dot = T(0);
@@ -365,18 +420,18 @@ __global__ void __launch_bounds__(kThreads) k_gram_combine(GramCombineArgs<T> a,
         for (int k = 0; k < 4; k++) r[k] = cv * pv.v[k];
         // y terms newest -> oldest, then s terms oldest -> newest (the order the recursion would add them)
 #pragma unroll 4
-        for (int j = 0; j < a.c; j++)
+        for (int j = 0; j < c; j++)
         {
-            const Pack<T> py = load4<T, Hint::Stream, VEC>(a.Y + (int64_t)a.slots[j] * a.ld, i0, cnt);
+            const Pack<T> py = load4<T, Hint::Stream, VEC>(s_ycol[j], i0, cnt);
             const T cy = s_coef[1 + j];
 #pragma unroll
             for (int k = 0; k < 4; k++) r[k] += cy * py.v[k];
         }
 #pragma unroll 4
-        for (int j = a.c - 1; j >= 0; j--)
+        for (int j = c - 1; j >= 0; j--)
         {
-            const Pack<T> ps = load4<T, Hint::Stream, VEC>(a.S + (int64_t)a.slots[j] * a.ld, i0, cnt);
-            const T cs = s_coef[1 + a.c + j];
+            const Pack<T> ps = load4<T, Hint::Stream, VEC>(s_scol[j], i0, cnt);
+            const T cs = s_coef[1 + c + j];
 #pragma unroll
             for (int k = 0; k < 4; k++) r[k] += cs * ps.v[k];
         }
