@@ -137,6 +137,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--hv", default="auto", choices=["auto", "two_loop", "gram"])
+    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: in-kernel all-reduce over NVLink peer memory (default) or one ncclAllReduce per reduction")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-mode", action="store_true", help="timed region only (for runs under ncu; numbers are not bench values)")
     args = ap.parse_args()
@@ -174,14 +176,20 @@ def main():
         return float(t.item())
 
     # ---- n-sharding: rank r owns an even-length contiguous block; scalars replicated; every dot is all-reduced ----
-    assert N_GLOBAL % (2 * world) == 0
-    n_local = N_GLOBAL // world
-    if world > 1:
+    from lbfgspp_b200.sharding import shard_bounds
+    lo, hi = shard_bounds(N_GLOBAL, rank, world)
+    n_local = hi - lo
+    if world > 1 and args.comm == "nccl":
         ident = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             ident = torch.tensor(list(lb.comm_unique_id()), dtype=torch.uint8, device="cuda")
         dist.broadcast(ident, src=0)
-        lb.comm_init(local_rank, bytes(ident.cpu().numpy().tobytes()), rank, world, index_offset=rank * n_local)
+        lb.comm_init(local_rank, bytes(ident.cpu().numpy().tobytes()), rank, world, index_offset=lo)
+    elif world > 1:
+        mine = torch.tensor(list(lb.p2p_export(local_rank)), dtype=torch.uint8, device="cuda")
+        allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        dist.all_gather(allh, mine)
+        lb.p2p_attach(local_rank, b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh), rank, world, index_offset=lo)
 
     hv = {"auto": lb.HV_AUTO, "two_loop": lb.HV_TWO_LOOP, "gram": lb.HV_GRAM}[args.hv]
     prm = lb.LBFGSParam(m=M_HIST)
@@ -275,7 +283,8 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "n": N_GLOBAL, "n_per_gpu": n_local, "m": M_HIST, "line_search": "MoreThuente",
                    "step": "one full minimize(): %d iterations, %d objective evaluations" % (niter, nfev),
-                   "apply_Hv": args.hv, "sharding": "n split over %d rank(s), dots all-reduced (NCCL)" % world,
+                   "apply_Hv": args.hv, "sharding": "n split over %d rank(s); reductions all-reduced %s" % (
+                       world, "in-kernel over NVLink peer memory" if args.comm == "p2p" else "with ncclAllReduce"),
                    "l2": "inputs larger than L2 (S,Y = %.2f GB per GPU)" % (2 * 8 * n_local * (M_HIST + 1) / 1e9)},
         "clocks": clocks,
         "e2e": {"value": e2e_iters / e2e_seconds, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

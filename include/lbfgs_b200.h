@@ -92,6 +92,13 @@ lbfgs_b200_status lbfgs_b200_set_index_offset(lbfgs_b200_ctx* ctx, int64_t offse
 lbfgs_b200_status lbfgs_b200_comm_unique_id(void* unique_id_128);
 lbfgs_b200_status lbfgs_b200_comm_init(lbfgs_b200_ctx* ctx, const void* unique_id_128, int rank, int nranks);
 int lbfgs_b200_comm_size(const lbfgs_b200_ctx* ctx);
+/* In-kernel all-reduce over NVLink peer memory (one process per GPU, same node), replacing the per-reduction NCCL call:
+ * every rank exports its inbox (64-byte cudaIpcMemHandle), the application gathers the nranks handles in rank order and
+ * every rank attaches them.  From then on the last CTA of every reducing kernel pushes its partial sums into all peers'
+ * inboxes, waits for theirs and adds them in rank order: deterministic, identical bits on all ranks, no extra launch.
+ * All ranks must issue the same sequence of library calls (they do: the host logic is replicated). */
+lbfgs_b200_status lbfgs_b200_comm_p2p_export(lbfgs_b200_ctx* ctx, void* ipc_handle_64);
+lbfgs_b200_status lbfgs_b200_comm_p2p_attach(lbfgs_b200_ctx* ctx, const void* all_handles_nranks_x_64, int rank, int nranks);
 
 /* ---------------------------------------------------------------- level-1 kernels (f64 / f32) */
 #define LBFGS_B200_DECLARE_L1(T, SUF)                                                                          \

@@ -145,6 +145,8 @@ def driver():
     lib.lbfgsb200_drv_session_result.restype = dp
     lib.lbfgsb200_drv_session_result.argtypes = [C.c_void_p]
     lib.lbfgsb200_drv_comm_init.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_char_p, C.c_int]
+    lib.lbfgsb200_drv_p2p_export.argtypes = [C.c_int, C.c_void_p, C.c_char_p, C.c_int]
+    lib.lbfgsb200_drv_p2p_attach.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_char_p, C.c_int]
     lib._typed = True
     return lib
 
@@ -438,6 +440,23 @@ def comm_init(device, unique_id_bytes, rank, nranks, index_offset=0):
     st = driver().lbfgsb200_drv_comm_init(device, buf, rank, nranks, index_offset, err, 256)
     if st:
         raise RuntimeError("comm_init failed: " + err.value.decode())
+
+
+def p2p_export(device):
+    """64-byte cudaIpc handle of this rank's inbox for the in-kernel NVLink all-reduce."""
+    err = C.create_string_buffer(256)
+    buf = C.create_string_buffer(64)
+    if driver().lbfgsb200_drv_p2p_export(device, buf, err, 256):
+        raise RuntimeError("p2p_export failed: " + err.value.decode())
+    return buf.raw
+
+
+def p2p_attach(device, all_handles, rank, nranks, index_offset=0):
+    """all_handles: the nranks 64-byte handles concatenated in rank order."""
+    err = C.create_string_buffer(256)
+    buf = C.create_string_buffer(bytes(all_handles), 64 * nranks)
+    if driver().lbfgsb200_drv_p2p_attach(device, buf, rank, nranks, index_offset, err, 256):
+        raise RuntimeError("p2p_attach failed: " + err.value.decode())
 
 
 def comm_unique_id():

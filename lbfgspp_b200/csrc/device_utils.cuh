@@ -97,12 +97,83 @@ template <class T, Hint H, bool VEC> __device__ __forceinline__ void store4(T* b
 //   -> integer ticket -> the LAST block to arrive sums the slots in a fixed order and writes `result[k]`.
 // The only atomic is the integer ticket, so the floating-point result depends on (n, grid) alone and is
 // reproducible run to run.  Accumulation across warps/blocks is in double also for fp32 inputs.
+// ---- cross-GPU exchange fused into the tail of a reducing kernel ------------------------------------------------
+// n-sharded mode: after the last CTA has the local sums it pushes them straight into every peer's inbox over NVLink
+// (peer-mapped memory, cudaIpc), raises a per-source flag carrying the collective's epoch, waits for all sources'
+// flags in its own inbox and adds the contributions in RANK ORDER -- every rank ends with the same bits and the kernel
+// that follows can consume result[] without a separate all-reduce launch.  Inboxes form a ring of kXRing epochs.
+constexpr int kXMaxRanks = 8;
+constexpr int kXRing = 4;
+constexpr int kXMaxVals = 384;   // >= kMaxM * (values per column pair of k_gram_dots)
+
+struct XInbox
+{
+    double vals[kXRing][kXMaxRanks][kXMaxVals];
+    unsigned long long flag[kXRing][kXMaxRanks];
+};
+
+struct XComm
+{
+    XInbox* inbox[kXMaxRanks];   // inbox[r] = rank r's inbox as mapped into THIS process (inbox[rank] is local)
+    int rank, nranks;
+};
+
 struct ReduceBuf
 {
     double* partials;    // [kMaxBlocks][kMaxRed]
     unsigned* ticket;    // zero between launches (the last block resets it)
     double* result;      // [kMaxRed] device result slots of this launch
+    const XComm* xc;     // nullptr on a single GPU (or when NCCL does the all-reduce)
+    unsigned long long epoch;  // sequence number of this launch's exchange (identical on all ranks)
 };
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_volatile_f64(const double* p)
+{
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Called by ALL threads of the last CTA once result[0..nv) holds the local sums.  On return result[] holds the
+// rank-ordered global sums (visible to the kernels that follow on this stream).
+__device__ __forceinline__ void xrank_allreduce(double* result, int nv, const XComm* xc, unsigned long long epoch)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int slot = (int)(epoch % kXRing), me = xc->rank, R = xc->nranks;
+    __syncthreads();
+    for (int i = tid; i < nv * R; i += nt)
+    {
+        const int dst = i / nv, k = i % nv;
+        xc->inbox[dst]->vals[slot][me][k] = result[k];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < R) st_release_sys(&xc->inbox[tid]->flag[slot][me], epoch);
+    if (tid < R)
+    {
+        const unsigned long long* f = &xc->inbox[me]->flag[slot][tid];
+        while (ld_acquire_sys(f) != epoch) {}
+    }
+    __syncthreads();
+    for (int k = tid; k < nv; k += nt)
+    {
+        double t = 0.0;
+        for (int r = 0; r < R; r++) t += ld_volatile_f64(&xc->inbox[me]->vals[slot][r][k]);
+        result[k] = t;
+    }
+    __threadfence();
+    __syncthreads();
+}
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -167,6 +238,7 @@ template <int NV> __device__ __forceinline__ bool grid_reduce(const double (&acc
     if (threadIdx.x == 0) *rb.ticket = 0u;
     __threadfence();
     __syncthreads();
+    if (rb.xc != nullptr) xrank_allreduce(rb.result, NV, rb.xc, rb.epoch);
     return true;
 }
 

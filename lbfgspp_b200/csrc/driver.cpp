@@ -373,3 +373,35 @@ extern "C" int lbfgsb200_drv_comm_init(int device_ordinal, const void* unique_id
         return 1;
     }
 }
+
+extern "C" int lbfgsb200_drv_p2p_export(int device_ordinal, void* handle64, char* err, int errlen)
+{
+    try
+    {
+        Device& dev = device(device_ordinal);
+        dev.check(lbfgs_b200_comm_p2p_export(dev.ctx(), handle64));
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        if (err && errlen > 0) { std::strncpy(err, e.what(), size_t(errlen) - 1); err[errlen - 1] = 0; }
+        return 1;
+    }
+}
+
+extern "C" int lbfgsb200_drv_p2p_attach(int device_ordinal, const void* handles, int rank, int nranks, long long index_offset,
+                                        char* err, int errlen)
+{
+    try
+    {
+        Device& dev = device(device_ordinal);
+        dev.check(lbfgs_b200_comm_p2p_attach(dev.ctx(), handles, rank, nranks));
+        dev.check(lbfgs_b200_set_index_offset(dev.ctx(), index_offset));
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        if (err && errlen > 0) { std::strncpy(err, e.what(), size_t(errlen) - 1); err[errlen - 1] = 0; }
+        return 1;
+    }
+}

@@ -45,6 +45,12 @@ struct lbfgs_b200_ctx
     int* h_flag = nullptr;         // pinned
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
+    // in-kernel exchange over peer memory (lbfgs_b200_comm_p2p_*): replaces the NCCL all-reduce when attached
+    XInbox* x_inbox = nullptr;          // this rank's inbox (cudaMalloc, exported through cudaIpc)
+    XComm* x_comm = nullptr;            // device copy of the peer table
+    void* x_peer[kXMaxRanks] = {};      // cudaIpcOpenMemHandle results (to close)
+    bool x_active = false;
+    unsigned long long x_epoch = 0;
     int64_t index_offset = 0;      // global index of this rank's element 0
     uint64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -138,10 +144,18 @@ static lbfgs_b200_status post_launch(lbfgs_b200_ctx* ctx, const char* what)
     return LBFGS_B200_OK;
 }
 
-// sum the first `count` result slots over all ranks (no-op on one GPU)
+// ReduceBuf for the next reducing launch: in p2p mode it carries the peer table and a fresh epoch
+static ReduceBuf next_rb(lbfgs_b200_ctx* ctx)
+{
+    ReduceBuf rb = ctx->rb;
+    if (ctx->x_active) { rb.xc = ctx->x_comm; rb.epoch = ++ctx->x_epoch; }
+    return rb;
+}
+
+// sum the first `count` result slots over all ranks (no-op on one GPU, and in p2p mode where the kernel did it)
 static lbfgs_b200_status allreduce_result(lbfgs_b200_ctx* ctx, int count)
 {
-    if (ctx->nranks > 1)
+    if (ctx->nranks > 1 && !ctx->x_active)
         NC(ctx, ncclAllReduce(ctx->rb.result, ctx->rb.result, count, ncclDouble, ncclSum, ctx->comm, ctx->stream));
     return LBFGS_B200_OK;
 }
@@ -529,6 +543,9 @@ void lbfgs_b200_ctx_destroy(lbfgs_b200_ctx* ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->comm) ncclCommDestroy(ctx->comm);
+    for (int r = 0; r < kXMaxRanks; r++) if (ctx->x_peer[r]) cudaIpcCloseMemHandle(ctx->x_peer[r]);
+    cudaFree(ctx->x_comm);
+    cudaFree(ctx->x_inbox);
     cudaFree(ctx->rb.partials);
     cudaFree(ctx->rb.ticket);
     cudaFree(ctx->rb.result);
@@ -676,6 +693,50 @@ lbfgs_b200_status lbfgs_b200_comm_init(lbfgs_b200_ctx* ctx, const void* unique_i
 }
 int lbfgs_b200_comm_size(const lbfgs_b200_ctx* ctx) { return ctx ? ctx->nranks : 0; }
 
+lbfgs_b200_status lbfgs_b200_comm_p2p_export(lbfgs_b200_ctx* ctx, void* ipc_handle_64)
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    REQUIRE(ctx, ctx && ipc_handle_64, "comm_p2p_export: NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->x_inbox)
+    {
+        CU(ctx, cudaMalloc(&ctx->x_inbox, sizeof(XInbox)));
+        CU(ctx, cudaMemset(ctx->x_inbox, 0, sizeof(XInbox)));
+        CU(ctx, cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t hnd;
+    CU(ctx, cudaIpcGetMemHandle(&hnd, ctx->x_inbox));
+    memcpy(ipc_handle_64, &hnd, sizeof(hnd));
+    return LBFGS_B200_OK;
+}
+
+lbfgs_b200_status lbfgs_b200_comm_p2p_attach(lbfgs_b200_ctx* ctx, const void* all_handles, int rank, int nranks)
+{
+    REQUIRE(ctx, ctx && all_handles && ctx->x_inbox, "comm_p2p_attach: export first");
+    REQUIRE(ctx, nranks >= 1 && nranks <= kXMaxRanks && rank >= 0 && rank < nranks, "comm_p2p_attach: 1 <= nranks <= %d", kXMaxRanks);
+    CU(ctx, cudaSetDevice(ctx->device));
+    XComm host{};
+    host.rank = rank;
+    host.nranks = nranks;
+    for (int r = 0; r < nranks; r++)
+    {
+        if (r == rank) { host.inbox[r] = ctx->x_inbox; continue; }
+        cudaIpcMemHandle_t hnd;
+        memcpy(&hnd, static_cast<const char*>(all_handles) + 64 * r, sizeof(hnd));
+        void* p = nullptr;
+        CU(ctx, cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+        ctx->x_peer[r] = p;
+        host.inbox[r] = static_cast<XInbox*>(p);
+    }
+    if (!ctx->x_comm) CU(ctx, cudaMalloc(&ctx->x_comm, sizeof(XComm)));
+    CU(ctx, cudaMemcpy(ctx->x_comm, &host, sizeof(XComm), cudaMemcpyHostToDevice));
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    ctx->x_epoch = 0;
+    ctx->x_active = nranks > 1;
+    return LBFGS_B200_OK;
+}
+
 }  // extern "C"
 
 // =====================================================================================================
@@ -693,8 +754,8 @@ static lbfgs_b200_status do_dot(lbfgs_b200_ctx* ctx, int64_t n, const T* a, cons
 {
     REQUIRE(ctx, ctx && a && b && out_host && n >= 0, "dot: bad arguments");
     const int grid = grid_for(ctx, n);
-    if (all_aligned<T>({a, b})) k_dots<T, 1, true><<<grid, kThreads, 0, ctx->stream>>>(n, a, b, nullptr, ctx->rb);
-    else k_dots<T, 1, false><<<grid, kThreads, 0, ctx->stream>>>(n, a, b, nullptr, ctx->rb);
+    if (all_aligned<T>({a, b})) k_dots<T, 1, true><<<grid, kThreads, 0, ctx->stream>>>(n, a, b, nullptr, next_rb(ctx));
+    else k_dots<T, 1, false><<<grid, kThreads, 0, ctx->stream>>>(n, a, b, nullptr, next_rb(ctx));
     if (auto st = post_launch(ctx, "k_dots<1>")) return st;
     if (auto st = allreduce_result(ctx, 1)) return st;
     if (auto st = fetch_result(ctx, 1)) return st;
@@ -707,8 +768,8 @@ static lbfgs_b200_status do_dot3(lbfgs_b200_ctx* ctx, int64_t n, const T* g, con
 {
     REQUIRE(ctx, ctx && g && d && x && out3 && n >= 0, "dot3: bad arguments");
     const int grid = grid_for(ctx, n);
-    if (all_aligned<T>({g, d, x})) k_dots<T, 3, true><<<grid, kThreads, 0, ctx->stream>>>(n, g, d, x, ctx->rb);
-    else k_dots<T, 3, false><<<grid, kThreads, 0, ctx->stream>>>(n, g, d, x, ctx->rb);
+    if (all_aligned<T>({g, d, x})) k_dots<T, 3, true><<<grid, kThreads, 0, ctx->stream>>>(n, g, d, x, next_rb(ctx));
+    else k_dots<T, 3, false><<<grid, kThreads, 0, ctx->stream>>>(n, g, d, x, next_rb(ctx));
     if (auto st = post_launch(ctx, "k_dots<3>")) return st;
     if (auto st = allreduce_result(ctx, 3)) return st;
     if (auto st = fetch_result(ctx, 3)) return st;
@@ -741,8 +802,9 @@ static lbfgs_b200_status launch_trial(lbfgs_b200_ctx* ctx, const OBJ& obj, int64
                                       T* x, T* g, bool vec)
 {
     const int grid = grid_for(ctx, n, 2);
-    if (vec) k_trial<T, OBJ, TRIAL, true><<<grid, kThreads, 0, ctx->stream>>>(obj, n, xp, d, step, x, g, ctx->rb);
-    else k_trial<T, OBJ, TRIAL, false><<<grid, kThreads, 0, ctx->stream>>>(obj, n, xp, d, step, x, g, ctx->rb);
+    const ReduceBuf rb = next_rb(ctx);
+    if (vec) k_trial<T, OBJ, TRIAL, true><<<grid, kThreads, 0, ctx->stream>>>(obj, n, xp, d, step, x, g, rb);
+    else k_trial<T, OBJ, TRIAL, false><<<grid, kThreads, 0, ctx->stream>>>(obj, n, xp, d, step, x, g, rb);
     return post_launch(ctx, "k_trial");
 }
 
@@ -844,10 +906,11 @@ static lbfgs_b200_status do_hist_update(lbfgs_b200_hist* h, const T* x, const T*
     T* y_out = h->y_col<T>(h->head);
     ProfSpan span(ctx, PH_UPDATE, double(sizeof(T)) * double(h->n) * 6.0);
     const int grid = grid_for(ctx, h->n, 2);
+    const ReduceBuf rb = next_rb(ctx);
     if (all_aligned<T>({x, xp, g, gp}))
-        k_update<T, true><<<grid, kThreads, 0, ctx->stream>>>(h->n, x, xp, g, gp, s_out, y_out, ctx->rb);
+        k_update<T, true><<<grid, kThreads, 0, ctx->stream>>>(h->n, x, xp, g, gp, s_out, y_out, rb);
     else
-        k_update<T, false><<<grid, kThreads, 0, ctx->stream>>>(h->n, x, xp, g, gp, s_out, y_out, ctx->rb);
+        k_update<T, false><<<grid, kThreads, 0, ctx->stream>>>(h->n, x, xp, g, gp, s_out, y_out, rb);
     if (auto st = post_launch(ctx, "k_update")) return st;
     span.stop();
     return commit_pair<T>(h, eps, 1, accepted_host, sy_yy_host);
@@ -859,10 +922,11 @@ template <class T> static lbfgs_b200_status do_hist_add(lbfgs_b200_hist* h, cons
     lbfgs_b200_ctx* ctx = h->ctx;
     REQUIRE(ctx, s && y, "hist_add: NULL vector");
     const int grid = grid_for(ctx, h->n, 2);
+    const ReduceBuf rb = next_rb(ctx);
     if (all_aligned<T>({s, y}))
-        k_add_pair<T, true><<<grid, kThreads, 0, ctx->stream>>>(h->n, s, y, h->s_col<T>(h->head), h->y_col<T>(h->head), ctx->rb);
+        k_add_pair<T, true><<<grid, kThreads, 0, ctx->stream>>>(h->n, s, y, h->s_col<T>(h->head), h->y_col<T>(h->head), rb);
     else
-        k_add_pair<T, false><<<grid, kThreads, 0, ctx->stream>>>(h->n, s, y, h->s_col<T>(h->head), h->y_col<T>(h->head), ctx->rb);
+        k_add_pair<T, false><<<grid, kThreads, 0, ctx->stream>>>(h->n, s, y, h->s_col<T>(h->head), h->y_col<T>(h->head), rb);
     if (auto st = post_launch(ctx, "k_add_pair")) return st;
     return commit_pair<T>(h, T(0), 0, nullptr, nullptr);
 }
@@ -871,8 +935,9 @@ template <class T, int KIND>
 static lbfgs_b200_status launch_stage(lbfgs_b200_ctx* ctx, const StageArgs<T>& s, bool vec)
 {
     const int grid = grid_for(ctx, s.n, 2);
-    if (vec) k_hv_stage<T, KIND, true><<<grid, kThreads, 0, ctx->stream>>>(s, ctx->rb);
-    else k_hv_stage<T, KIND, false><<<grid, kThreads, 0, ctx->stream>>>(s, ctx->rb);
+    const ReduceBuf rb = (s.B != nullptr) ? next_rb(ctx) : ctx->rb;
+    if (vec) k_hv_stage<T, KIND, true><<<grid, kThreads, 0, ctx->stream>>>(s, rb);
+    else k_hv_stage<T, KIND, false><<<grid, kThreads, 0, ctx->stream>>>(s, rb);
     if (auto st = post_launch(ctx, "k_hv_stage")) return st;
     if (s.B != nullptr) return allreduce_result(ctx, 1);
     return LBFGS_B200_OK;
@@ -956,6 +1021,8 @@ static lbfgs_b200_status gram_dots(lbfgs_b200_hist* h, const T* v)
     const int64_t ntiles = (h->n + kGramTE - 1) / kGramTE;
     const int grid = (int)(ntiles < ctx->sm_count ? ntiles : ctx->sm_count);
     const size_t smem = (size_t)kGramStages * 3 * kGramTE * sizeof(T);
+    const XComm* xc = ctx->x_active ? ctx->x_comm : nullptr;
+    const unsigned long long epoch = ctx->x_active ? ++ctx->x_epoch : 0ull;
 #define LAUNCH_GRAM(R)                                                                                       \
     do {                                                                                                     \
         static bool attr_set = false;                                                                        \
@@ -963,14 +1030,14 @@ static lbfgs_b200_status gram_dots(lbfgs_b200_hist* h, const T* v)
             CU(ctx, cudaFuncSetAttribute(k_gram_dots<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             attr_set = true;                                                                                 \
         }                                                                                                    \
-        k_gram_dots<T, R><<<grid, threads, smem, ctx->stream>>>(a, ctx->gram_partials, ctx->rb.ticket, ctx->gram_raw); \
+        k_gram_dots<T, R><<<grid, threads, smem, ctx->stream>>>(a, ctx->gram_partials, ctx->rb.ticket, ctx->gram_raw, xc, epoch); \
     } while (0)
     if (rounds <= 1) LAUNCH_GRAM(1);
     else if (rounds == 2) LAUNCH_GRAM(2);
     else LAUNCH_GRAM(3);
 #undef LAUNCH_GRAM
     if (auto st = post_launch(ctx, "k_gram_dots")) return st;
-    if (ctx->nranks > 1)
+    if (ctx->nranks > 1 && !ctx->x_active)
         NC(ctx, ncclAllReduce(ctx->gram_raw, ctx->gram_raw, c * kGramVals, ncclDouble, ncclSum, ctx->comm, ctx->stream));
     return LBFGS_B200_OK;
 }
@@ -1030,8 +1097,9 @@ static lbfgs_b200_status hv_gram(lbfgs_b200_hist* h, const T* v, T a, T* res, bo
         if (vec) CU(ctx, cudaFuncSetAttribute(k_gram_combine<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         else CU(ctx, cudaFuncSetAttribute(k_gram_combine<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    if (vec) k_gram_combine<T, true><<<grid, kThreads, smem, ctx->stream>>>(k, ctx->rb);
-    else k_gram_combine<T, false><<<grid, kThreads, smem, ctx->stream>>>(k, ctx->rb);
+    const ReduceBuf rb = want_vdot ? next_rb(ctx) : ctx->rb;
+    if (vec) k_gram_combine<T, true><<<grid, kThreads, smem, ctx->stream>>>(k, rb);
+    else k_gram_combine<T, false><<<grid, kThreads, smem, ctx->stream>>>(k, rb);
     if (auto st = post_launch(ctx, "k_gram_combine")) return st;
     gram_folded(h);
     if (want_vdot) return allreduce_result(ctx, 1);

@@ -99,7 +99,7 @@ __device__ __forceinline__ Pack<float> lds_pack(const float* p, int)
 }
 
 template <class T, int ROUNDS>
-__global__ void __launch_bounds__(kGramMaxThreads, 1) k_gram_dots(GramDotsArgs<T> a, double* partials, unsigned* ticket, double* result)
+__global__ void __launch_bounds__(kGramMaxThreads, 1) k_gram_dots(GramDotsArgs<T> a, double* partials, unsigned* ticket, double* result, const XComm* xc, unsigned long long epoch)
 {
     extern __shared__ __align__(128) unsigned char gram_smem[];
     T* tiles = reinterpret_cast<T*>(gram_smem);                  // [stage][3][TE]
@@ -292,6 +292,11 @@ __global__ void __launch_bounds__(kGramMaxThreads, 1) k_gram_dots(GramDotsArgs<T
         result[idx] = t;
     }
     if (tid == 0) *ticket = 0u;
+    if (xc != nullptr)
+    {
+        __threadfence();
+        xrank_allreduce(result, nvals, xc, epoch);
+    }
 }
 
 // ---- the O(c^2) recursion on coefficients ---------------------------------------------------------------------
