@@ -125,6 +125,13 @@ struct ReduceBuf
     double* result;      // [kMaxRed] device result slots of this launch
     const XComm* xc;     // nullptr on a single GPU (or when NCCL does the all-reduce)
     unsigned long long epoch;  // sequence number of this launch's exchange (identical on all ranks)
+    // host delivery: when mail_seq != 0 the last CTA also copies result[] into a mapped pinned-host mailbox and then
+    // publishes mail_seq there; the host spins on the sequence word instead of paying memcpy + stream synchronise
+    double* mail_vals;
+    unsigned long long* mail_word;
+    unsigned long long mail_seq;
+    const int* mail_flag_src;  // optional device int forwarded into the mailbox (e.g. the curvature-gate flag)
+    int* mail_flag_dst;
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
@@ -174,6 +181,17 @@ __device__ __forceinline__ void xrank_allreduce(double* result, int nv, const XC
     __threadfence();
     __syncthreads();
 }
+
+__device__ __forceinline__ void deliver_to_host(const ReduceBuf& rb, int nv)
+{
+    if (rb.mail_seq == 0ull) return;
+    for (int k = threadIdx.x; k < nv; k += blockDim.x) rb.mail_vals[k] = rb.result[k];
+    if (threadIdx.x == 0 && rb.mail_flag_src) *rb.mail_flag_dst = *rb.mail_flag_src;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_sys(rb.mail_word, rb.mail_seq);
+}
+
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -239,6 +257,7 @@ template <int NV> __device__ __forceinline__ bool grid_reduce(const double (&acc
     __threadfence();
     __syncthreads();
     if (rb.xc != nullptr) xrank_allreduce(rb.result, NV, rb.xc, rb.epoch);
+    deliver_to_host(rb, NV);
     return true;
 }
 

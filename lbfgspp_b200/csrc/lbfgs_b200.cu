@@ -18,6 +18,7 @@
 #include <cstring>
 #include <limits>
 #include <new>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -43,6 +44,11 @@ struct lbfgs_b200_ctx
     double* gram_raw = nullptr;    // [kMaxM*kGramVals] reduced dots
     int* d_flag = nullptr;         // device int flags (accepted, ...)
     int* h_flag = nullptr;         // pinned
+    // mapped pinned mailbox: kernels publish host-bound scalars here (see deliver_to_host)
+    struct Mail { volatile unsigned long long word; int flag; int pad; double vals[kXMaxVals]; };
+    Mail* h_mail = nullptr;        // host view
+    Mail* d_mail = nullptr;        // device view of the same memory
+    unsigned long long mail_seq = 0;
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
     // in-kernel exchange over peer memory (lbfgs_b200_comm_p2p_*): replaces the NCCL all-reduce when attached
@@ -145,11 +151,50 @@ static lbfgs_b200_status post_launch(lbfgs_b200_ctx* ctx, const char* what)
 }
 
 // ReduceBuf for the next reducing launch: in p2p mode it carries the peer table and a fresh epoch
-static ReduceBuf next_rb(lbfgs_b200_ctx* ctx)
+// to_host: the kernel's last CTA also publishes result[] in the mapped mailbox (not possible when a separate NCCL
+// all-reduce still has to run after the kernel)
+static bool mail_ok(const lbfgs_b200_ctx* ctx) { return ctx->nranks == 1 || ctx->x_active; }
+static ReduceBuf next_rb(lbfgs_b200_ctx* ctx, bool to_host = false)
 {
     ReduceBuf rb = ctx->rb;
     if (ctx->x_active) { rb.xc = ctx->x_comm; rb.epoch = ++ctx->x_epoch; }
+    if (to_host && mail_ok(ctx))
+    {
+        rb.mail_vals = ctx->d_mail->vals;
+        rb.mail_word = const_cast<unsigned long long*>(&ctx->d_mail->word);
+        rb.mail_seq = ++ctx->mail_seq;
+    }
     return rb;
+}
+
+// wait until the kernel that carries the current mail_seq has published; h_result mirrors the values afterwards
+static lbfgs_b200_status wait_mail(lbfgs_b200_ctx* ctx, int count)
+{
+    const unsigned long long want = ctx->mail_seq;
+    unsigned spins = 0;
+    while (ctx->h_mail->word != want)
+    {
+        if ((++spins & 0x3fff) == 0)
+        {
+            cudaError_t e = cudaStreamQuery(ctx->stream);
+            if (e != cudaSuccess && e != cudaErrorNotReady)
+                return fail(ctx, LBFGS_B200_ERR_CUDA, "stream failed while waiting for a result: %s", cudaGetErrorString(e));
+            if (e == cudaSuccess && ctx->h_mail->word != want)
+                return fail(ctx, LBFGS_B200_ERR_CUDA, "kernel finished without publishing its result (sequence %llu)", want);
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    for (int k = 0; k < count; k++) ctx->h_result[k] = ctx->h_mail->vals[k];
+    return LBFGS_B200_OK;
+}
+
+// host receives `count` result slots: mailbox when the kernel delivered there, else memcpy + synchronise
+static lbfgs_b200_status receive(lbfgs_b200_ctx* ctx, int count)
+{
+    if (mail_ok(ctx)) return wait_mail(ctx, count);
+    CU(ctx, cudaMemcpyAsync(ctx->h_result, ctx->rb.result, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return LBFGS_B200_OK;
 }
 
 // sum the first `count` result slots over all ranks (no-op on one GPU, and in p2p mode where the kernel did it)
@@ -385,7 +430,8 @@ __global__ void __launch_bounds__(kThreads) k_add_pair(int64_t n, const T* __res
 
 // gate + ys/theta bookkeeping from the reduced {s.y, y.y}: one thread (runs after the all-reduce)
 template <class T>
-__global__ void k_commit_pair(const double* result, T eps, int gate, T* ys_slot, T* theta, int* accepted)
+__global__ void k_commit_pair(const double* result, T eps, int gate, T* ys_slot, T* theta, int* accepted,
+                              double* mail_vals, int* mail_flag, unsigned long long* mail_word, unsigned long long mail_seq)
 {
     const T sy = (T)result[0], yy = (T)result[1];
     const bool ok = gate ? (sy > eps * yy) : true;
@@ -395,6 +441,14 @@ __global__ void k_commit_pair(const double* result, T eps, int gate, T* ys_slot,
         *theta = yy / sy;
     }
     *accepted = ok ? 1 : 0;
+    if (mail_seq != 0ull)
+    {
+        mail_vals[0] = result[0];
+        mail_vals[1] = result[1];
+        *mail_flag = ok ? 1 : 0;
+        __threadfence_system();
+        st_release_sys(mail_word, mail_seq);
+    }
 }
 
 // ----------------------------------------------------------------------------- literal two-loop stages
@@ -529,6 +583,9 @@ lbfgs_b200_status lbfgs_b200_ctx_create(lbfgs_b200_ctx** out, int device, void* 
     CUC(cudaMemsetAsync(ctx->rb.result, 0, sizeof(double) * 256, ctx->stream));
     CUC(cudaMallocHost(&ctx->h_result, sizeof(double) * 256));
     CUC(cudaMallocHost(&ctx->h_flag, sizeof(int) * 16));
+    CUC(cudaHostAlloc(&ctx->h_mail, sizeof(lbfgs_b200_ctx::Mail), cudaHostAllocMapped));
+    memset((void*)ctx->h_mail, 0, sizeof(lbfgs_b200_ctx::Mail));
+    CUC(cudaHostGetDevicePointer(&ctx->d_mail, ctx->h_mail, 0));
     CUC(cudaEventCreate(&ctx->ev0));
     CUC(cudaEventCreate(&ctx->ev1));
     CUC(cudaStreamSynchronize(ctx->stream));
@@ -554,6 +611,7 @@ void lbfgs_b200_ctx_destroy(lbfgs_b200_ctx* ctx)
     cudaFree(ctx->gram_raw);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+    if (ctx->h_mail) cudaFreeHost((void*)ctx->h_mail);
     for (int ph = 0; ph < 3; ph++) for (auto& sp : ctx->spans[ph]) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto& sp : ctx->free_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -754,11 +812,12 @@ static lbfgs_b200_status do_dot(lbfgs_b200_ctx* ctx, int64_t n, const T* a, cons
 {
     REQUIRE(ctx, ctx && a && b && out_host && n >= 0, "dot: bad arguments");
     const int grid = grid_for(ctx, n);
-    if (all_aligned<T>({a, b})) k_dots<T, 1, true><<<grid, kThreads, 0, ctx->stream>>>(n, a, b, nullptr, next_rb(ctx));
-    else k_dots<T, 1, false><<<grid, kThreads, 0, ctx->stream>>>(n, a, b, nullptr, next_rb(ctx));
+    const ReduceBuf rb = next_rb(ctx, true);
+    if (all_aligned<T>({a, b})) k_dots<T, 1, true><<<grid, kThreads, 0, ctx->stream>>>(n, a, b, nullptr, rb);
+    else k_dots<T, 1, false><<<grid, kThreads, 0, ctx->stream>>>(n, a, b, nullptr, rb);
     if (auto st = post_launch(ctx, "k_dots<1>")) return st;
     if (auto st = allreduce_result(ctx, 1)) return st;
-    if (auto st = fetch_result(ctx, 1)) return st;
+    if (auto st = receive(ctx, 1)) return st;
     *out_host = (T)ctx->h_result[0];
     return LBFGS_B200_OK;
 }
@@ -768,11 +827,12 @@ static lbfgs_b200_status do_dot3(lbfgs_b200_ctx* ctx, int64_t n, const T* g, con
 {
     REQUIRE(ctx, ctx && g && d && x && out3 && n >= 0, "dot3: bad arguments");
     const int grid = grid_for(ctx, n);
-    if (all_aligned<T>({g, d, x})) k_dots<T, 3, true><<<grid, kThreads, 0, ctx->stream>>>(n, g, d, x, next_rb(ctx));
-    else k_dots<T, 3, false><<<grid, kThreads, 0, ctx->stream>>>(n, g, d, x, next_rb(ctx));
+    const ReduceBuf rb = next_rb(ctx, true);
+    if (all_aligned<T>({g, d, x})) k_dots<T, 3, true><<<grid, kThreads, 0, ctx->stream>>>(n, g, d, x, rb);
+    else k_dots<T, 3, false><<<grid, kThreads, 0, ctx->stream>>>(n, g, d, x, rb);
     if (auto st = post_launch(ctx, "k_dots<3>")) return st;
     if (auto st = allreduce_result(ctx, 3)) return st;
-    if (auto st = fetch_result(ctx, 3)) return st;
+    if (auto st = receive(ctx, 3)) return st;
     for (int k = 0; k < 3; k++) out3[k] = (T)ctx->h_result[k];
     return LBFGS_B200_OK;
 }
@@ -802,7 +862,7 @@ static lbfgs_b200_status launch_trial(lbfgs_b200_ctx* ctx, const OBJ& obj, int64
                                       T* x, T* g, bool vec)
 {
     const int grid = grid_for(ctx, n, 2);
-    const ReduceBuf rb = next_rb(ctx);
+    const ReduceBuf rb = next_rb(ctx, true);
     if (vec) k_trial<T, OBJ, TRIAL, true><<<grid, kThreads, 0, ctx->stream>>>(obj, n, xp, d, step, x, g, rb);
     else k_trial<T, OBJ, TRIAL, false><<<grid, kThreads, 0, ctx->stream>>>(obj, n, xp, d, step, x, g, rb);
     return post_launch(ctx, "k_trial");
@@ -853,7 +913,7 @@ static lbfgs_b200_status do_trial(lbfgs_b200_ctx* ctx, int objective, const T* d
     if (st) return st;
     if (auto s2 = allreduce_result(ctx, 4)) return s2;
     span.stop();
-    if (auto s2 = fetch_result(ctx, 4)) return s2;
+    if (auto s2 = receive(ctx, 4)) return s2;
     for (int k = 0; k < 4; k++) out_host[k] = (T)ctx->h_result[k];
     if (!TRIAL) out_host[1] = T(0);
     return LBFGS_B200_OK;
@@ -875,11 +935,26 @@ static lbfgs_b200_status commit_pair(lbfgs_b200_hist* h, T eps, int gate, int* a
     lbfgs_b200_ctx* ctx = h->ctx;
     if (auto st = allreduce_result(ctx, 2)) return st;
     T* ys = static_cast<T*>(h->ys) + h->head;
-    k_commit_pair<T><<<1, 1, 0, ctx->stream>>>(ctx->rb.result, eps, gate, ys, static_cast<T*>(h->theta), ctx->d_flag);
-    if (auto st = post_launch(ctx, "k_commit_pair")) return st;
-    CU(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    if (auto st = fetch_result(ctx, 2)) return st;  // synchronises
-    const int ok = ctx->h_flag[0];
+    int ok = 0;
+    if (mail_ok(ctx))
+    {
+        const unsigned long long seq = ++ctx->mail_seq;
+        k_commit_pair<T><<<1, 1, 0, ctx->stream>>>(ctx->rb.result, eps, gate, ys, static_cast<T*>(h->theta), ctx->d_flag,
+                                                   ctx->d_mail->vals, &ctx->d_mail->flag,
+                                                   const_cast<unsigned long long*>(&ctx->d_mail->word), seq);
+        if (auto st = post_launch(ctx, "k_commit_pair")) return st;
+        if (auto st = wait_mail(ctx, 2)) return st;
+        ok = ctx->h_mail->flag;
+    }
+    else
+    {
+        k_commit_pair<T><<<1, 1, 0, ctx->stream>>>(ctx->rb.result, eps, gate, ys, static_cast<T*>(h->theta), ctx->d_flag,
+                                                   nullptr, nullptr, nullptr, 0ull);
+        if (auto st = post_launch(ctx, "k_commit_pair")) return st;
+        CU(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        if (auto st = fetch_result(ctx, 2)) return st;  // synchronises
+        ok = ctx->h_flag[0];
+    }
     if (ok)
     {
         // two pairs appended back to back: fold the earlier one while it is still the newest (age 0)
@@ -1097,7 +1172,7 @@ static lbfgs_b200_status hv_gram(lbfgs_b200_hist* h, const T* v, T a, T* res, bo
         if (vec) CU(ctx, cudaFuncSetAttribute(k_gram_combine<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         else CU(ctx, cudaFuncSetAttribute(k_gram_combine<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    const ReduceBuf rb = want_vdot ? next_rb(ctx) : ctx->rb;
+    const ReduceBuf rb = want_vdot ? next_rb(ctx, true) : ctx->rb;
     if (vec) k_gram_combine<T, true><<<grid, kThreads, smem, ctx->stream>>>(k, rb);
     else k_gram_combine<T, false><<<grid, kThreads, smem, ctx->stream>>>(k, rb);
     if (auto st = post_launch(ctx, "k_gram_combine")) return st;
@@ -1121,7 +1196,7 @@ static lbfgs_b200_status do_hist_apply_Hv(lbfgs_b200_hist* h, const T* v, T a, T
     if (st) return st;
     if (vdot_host)
     {
-        if (auto s2 = fetch_result(ctx, 1)) return s2;
+        if (auto s2 = (gram ? receive(ctx, 1) : fetch_result(ctx, 1))) return s2;
         *vdot_host = (T)ctx->h_result[0];
     }
     return LBFGS_B200_OK;
