@@ -10,7 +10,10 @@
 
 #include <limits>
 
+#include <vector>
+
 #include "DeviceVector.h"
+#include "SmallDense.h"
 
 namespace LBFGSpp {
 
@@ -29,8 +32,12 @@ class BFGSMat
     BFGSMat& operator=(const BFGSMat&);
 
 public:
-    BFGSMat() : m_dev(nullptr), m_hist(nullptr), m_n(0), m_m(0), m_algo(LBFGS_B200_HV_AUTO) {}
-    ~BFGSMat() { lbfgs_b200_hist_destroy(m_hist); }
+    BFGSMat() : m_dev(nullptr), m_hist(nullptr), m_n(0), m_m(0), m_algo(LBFGS_B200_HV_AUTO), m_theta_host(1), m_c_host(0), m_box(nullptr) {}
+    ~BFGSMat()
+    {
+        lbfgs_b200_box_destroy(m_box);
+        lbfgs_b200_hist_destroy(m_hist);
+    }
 
     // Which apply_Hv implementation to run (LBFGS_B200_HV_AUTO picks by problem size).
     void set_algorithm(int algo) { m_algo = algo; }
@@ -42,6 +49,8 @@ public:
     {
         if (m_hist && (m_dev != &dev || m_n != n || m_m != m))
         {
+            lbfgs_b200_box_destroy(m_box);
+            m_box = nullptr;
             lbfgs_b200_hist_destroy(m_hist);
             m_hist = nullptr;
         }
@@ -86,6 +95,162 @@ public:
         Scalar vr = Scalar(0);
         m_dev->check(detail::Abi<Scalar>::hist_apply_Hv(m_hist, v.data(), a, res.data(), m_algo, &vr));
         return vr;
+    }
+
+    //========== L-BFGS-B part (reference BFGSMat.h:99-146, 307-615) ==========//
+    // B = theta*I - W M W' with W = [Y, theta*S] (n x 2c, columns ordered newest pair first) and M = inv(Minv),
+    //   Minv = [ -D   L' ]   D = diag(s_a'y_a),  L(a,b) = s_a'y_b when pair a is newer than pair b, else 0.
+    //          [  L  theta*S'S ]
+    // The c x c Gram blocks are kept on the device (folded pair by pair by the same pass that serves apply_Hv) and
+    // downloaded here; the 2c x 2c algebra is host work like in the reference.  W itself is never formed: products with
+    // W are masked passes over the S/Y columns (Wt_dot, lincomb, masked_gram).
+private:
+    Scalar m_theta_host;
+    int m_c_host;
+    SmallMatrix<Scalar> m_Minv, m_M, m_SS, m_SY;
+    SmallSolver<Scalar> m_Msolver;
+    lbfgs_b200_box* m_box;
+
+public:
+    lbfgs_b200_hist* handle() const { return m_hist; }
+    Device& device() const { return *m_dev; }
+    Scalar theta() const { return m_theta_host; }
+    int ncorr() const { return m_c_host; }
+    const SmallMatrix<Scalar>& Minv() const { return m_Minv; }
+    const SmallMatrix<Scalar>& Mmat() const { return m_M; }
+
+    // Download the Gram blocks and rebuild Minv / M.  Call after reset() and after every accepted update().
+    void refresh_middle()
+    {
+        const int c = num_corrections();
+        m_c_host = c;
+        m_theta_host = Scalar(1);
+        if (c == 0)
+        {
+            m_dev->check(detail::BoxAbi<Scalar>::hist_gram(m_hist, nullptr, nullptr, nullptr, nullptr, &m_theta_host));
+            m_Minv = SmallMatrix<Scalar>();
+            m_M = SmallMatrix<Scalar>();
+            return;
+        }
+        m_SY = SmallMatrix<Scalar>(c, c);
+        m_SS = SmallMatrix<Scalar>(c, c);
+        m_dev->check(detail::BoxAbi<Scalar>::hist_gram(m_hist, m_SY.data(), m_SS.data(), nullptr, nullptr, &m_theta_host));
+        m_Minv = SmallMatrix<Scalar>(2 * c, 2 * c);
+        for (int a = 0; a < c; a++)
+        {
+            m_Minv(a, a) = -m_SY(a, a);
+            for (int b = 0; b < c; b++)
+            {
+                if (a < b)  // age a < age b: pair a is the newer one
+                {
+                    m_Minv(c + a, b) = m_SY(a, b);
+                    m_Minv(b, c + a) = m_SY(a, b);
+                }
+                m_Minv(c + a, c + b) = m_theta_host * m_SS(a, b);
+            }
+        }
+        m_Msolver.compute(m_Minv);
+        m_M = SmallMatrix<Scalar>(2 * c, 2 * c);
+        std::vector<Scalar> e(size_t(2 * c));
+        for (int j = 0; j < 2 * c; j++)
+        {
+            std::fill(e.begin(), e.end(), Scalar(0));
+            e[size_t(j)] = Scalar(1);
+            m_Msolver.solve_inplace(e);
+            for (int i = 0; i < 2 * c; i++) m_M(i, j) = e[size_t(i)];
+        }
+    }
+
+    // res = M v   (apply_Mv, BFGSMat.h:361-378)
+    std::vector<Scalar> apply_Mv(const std::vector<Scalar>& v) const
+    {
+        if (m_c_host < 1) return std::vector<Scalar>();
+        return m_Msolver.solve(v);
+    }
+
+    // W'v for a device vector v (already zero outside the index set of interest): [Y'v ; theta*S'v]
+    // (apply_Wtv / apply_WtPv, BFGSMat.h:315-320, 382-433)
+    std::vector<Scalar> Wt_dot(const Scalar* v_dev)
+    {
+        const int c = m_c_host;
+        std::vector<Scalar> raw(size_t(2 * c), Scalar(0));
+        if (c > 0)
+        {
+            m_dev->check(detail::BoxAbi<Scalar>::hist_wt_dot(m_hist, v_dev, raw.data()));
+            for (int a = 0; a < c; a++) raw[size_t(c + a)] *= m_theta_host;
+        }
+        return raw;
+    }
+
+    // out_i = a0*v0_i + sum_a cy_a*y_a[i] + cs_a*s_a[i] on rows whose class byte intersects `mask`
+    void lincomb(Scalar a0, const Scalar* v0_dev, const std::vector<Scalar>& coef, int mask, Scalar* out_dev)
+    {
+        m_dev->check(detail::BoxAbi<Scalar>::hist_lincomb(m_hist, box(), a0, v0_dev, coef.empty() ? nullptr : coef.data(),
+                                                          lbfgs_b200_box_classes(box()), mask, out_dev));
+    }
+
+    // inv(P'BP) v on the rows of `mask`; v_dev must be zero outside the mask  (solve_PtBP, BFGSMat.h:529-565)
+    void solve_PtBP(int mask, const Scalar* v_dev, Scalar* out_dev)
+    {
+        const int c = m_c_host;
+        const Scalar theta = m_theta_host;
+        if (c < 1)
+        {
+            lincomb(Scalar(1) / theta, v_dev, std::vector<Scalar>(), mask, out_dev);
+            return;
+        }
+        SmallMatrix<Scalar> G(2 * c, 2 * c);
+        m_dev->check(detail::BoxAbi<Scalar>::hist_masked_gram(m_hist, box(), lbfgs_b200_box_classes(box()), mask, G.data()));
+        SmallMatrix<Scalar> mid(2 * c, 2 * c);
+        for (int a = 0; a < c; a++)
+            for (int b = 0; b < c; b++)
+            {
+                mid(a, b) = m_Minv(a, b) - G(a, b) / theta;
+                mid(c + a, b) = m_Minv(c + a, b) - G(c + a, b);
+                mid(b, c + a) = mid(c + a, b);
+                mid(c + a, c + b) = theta * (m_SS(a, b) - G(c + a, c + b));
+            }
+        SmallSolver<Scalar> midsolver(mid);
+        std::vector<Scalar> z = Wt_dot(v_dev);      // [Y_P'v ; theta*S_P'v]
+        midsolver.solve_inplace(z);
+        std::vector<Scalar> coef(size_t(2 * c));
+        const Scalar t2 = theta * theta;
+        for (int a = 0; a < c; a++)
+        {
+            coef[size_t(a)] = z[size_t(a)] / t2;
+            coef[size_t(c + a)] = theta * z[size_t(c + a)] / t2;
+        }
+        lincomb(Scalar(1) / theta, v_dev, coef, mask, out_dev);
+    }
+
+    // out = -W_rows * (M u) on the rows of `mask`, u a host 2c-vector in W's [Y ; theta*S] convention
+    // (apply_PtWMv with scale -1 / apply_PtBQv, BFGSMat.h:435-478, 570-615)
+    void minus_W_M(const std::vector<Scalar>& u, int mask, Scalar* out_dev)
+    {
+        const int c = m_c_host;
+        std::vector<Scalar> coef(size_t(2 * c), Scalar(0));
+        if (c > 0)
+        {
+            const std::vector<Scalar> Mu = apply_Mv(u);
+            for (int a = 0; a < c; a++)
+            {
+                coef[size_t(a)] = -Mu[size_t(a)];
+                coef[size_t(c + a)] = -m_theta_host * Mu[size_t(c + a)];
+            }
+        }
+        lincomb(Scalar(0), nullptr, coef, mask, out_dev);
+    }
+
+    // the n-sized scratch of Cauchy / SubspaceMin, created on first use and tied to the history
+    lbfgs_b200_box* box()
+    {
+        if (!m_box) m_dev->check(lbfgs_b200_box_create(m_hist, &m_box));
+        return m_box;
+    }
+    void drop_box()
+    {
+        lbfgs_b200_box_destroy(m_box);
+        m_box = nullptr;
     }
 };
 

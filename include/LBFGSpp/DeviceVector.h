@@ -101,6 +101,27 @@ template <> struct Abi<float>
     static lbfgs_b200_status hist_apply_Hv(lbfgs_b200_hist* h, const float* v, float a, float* res, int algo, float* vdot) { return lbfgs_b200_hist_apply_Hv_f32(h, v, a, res, algo, vdot); }
 };
 
+// bound-constrained primitives
+template <class Scalar> struct BoxAbi;
+#define LBFGSPP_B200_BOXABI(T, SUF)                                                                                             \
+    template <> struct BoxAbi<T>                                                                                                \
+    {                                                                                                                           \
+        static lbfgs_b200_status clamp(lbfgs_b200_ctx* c, int64_t n, T* x, const T* lb, const T* ub) { return lbfgs_b200_box_clamp_##SUF(c, n, x, lb, ub); } \
+        static lbfgs_b200_status proj_grad_norm(lbfgs_b200_ctx* c, int64_t n, const T* x, const T* g, const T* lb, const T* ub, T* o) { return lbfgs_b200_box_proj_grad_norm_##SUF(c, n, x, g, lb, ub, o); } \
+        static lbfgs_b200_status dir_info(lbfgs_b200_ctx* c, int64_t n, const T* x, const T* d, const T* g, const T* lb, const T* ub, T* o) { return lbfgs_b200_box_dir_info_##SUF(c, n, x, d, g, lb, ub, o); } \
+        static lbfgs_b200_status hist_wt_dot(lbfgs_b200_hist* h, const T* v, T* raw) { return lbfgs_b200_hist_wt_dot_##SUF(h, v, raw); } \
+        static lbfgs_b200_status hist_gram(lbfgs_b200_hist* h, T* sy, T* ss, T* yy, T* ys, T* th) { return lbfgs_b200_hist_gram_##SUF(h, sy, ss, yy, ys, th); } \
+        static lbfgs_b200_status hist_lincomb(lbfgs_b200_hist* h, lbfgs_b200_box* b, T a0, const T* v0, const T* coef, const unsigned char* cls, int mask, T* out) { return lbfgs_b200_hist_lincomb_##SUF(h, b, a0, v0, coef, cls, mask, out); } \
+        static lbfgs_b200_status hist_masked_gram(lbfgs_b200_hist* h, lbfgs_b200_box* b, const unsigned char* cls, int mask, T* G) { return lbfgs_b200_hist_masked_gram_##SUF(h, b, cls, mask, G); } \
+        static lbfgs_b200_status cauchy_breaks(lbfgs_b200_box* b, const T* x, const T* g, const T* lb, const T* ub, T* o5) { return lbfgs_b200_box_cauchy_breaks_##SUF(b, x, g, lb, ub, o5); } \
+        static lbfgs_b200_status cauchy_sweep(lbfgs_b200_box* b, const T* g, const T* M, const T* p0, T theta, T gt, int64_t nord, int64_t ninf, T* out) { return lbfgs_b200_box_cauchy_sweep_##SUF(b, g, M, p0, theta, gt, nord, ninf, out); } \
+        static lbfgs_b200_status cauchy_build(lbfgs_b200_box* b, const T* x, const T* lb, const T* ub, T tc, T tf, T* cnt) { return lbfgs_b200_box_cauchy_build_##SUF(b, x, lb, ub, tc, tf, cnt); } \
+        static lbfgs_b200_status sub_step(lbfgs_b200_box* b, int op, int flag, const T* x0, const T* g, const T* lb, const T* ub, T* drt, T theta, T* o3) { return lbfgs_b200_box_sub_step_##SUF(b, op, flag, x0, g, lb, ub, drt, theta, o3); } \
+    };
+LBFGSPP_B200_BOXABI(double, f64)
+LBFGSPP_B200_BOXABI(float, f32)
+#undef LBFGSPP_B200_BOXABI
+
 }  // namespace detail
 
 // ----------------------------------------------------------------------------------------------------

@@ -136,6 +136,8 @@ def driver():
                                             C.c_int, fp, fp, dp, C.c_long, C.POINTER(_DrvResult)]
     lib.lbfgsb200_drv_ctx.restype = C.c_void_p
     lib.lbfgsb200_drv_ctx.argtypes = [C.c_int]
+    lib.lbfgsb200_drv_lbfgsb_f64.argtypes = [C.c_int, C.c_int, dp, dp, C.c_long, C.POINTER(_DrvParam), dp, dp, dp, dp, dp, C.c_long,
+                                             C.POINTER(_DrvResult)]
     lib.lbfgsb200_drv_session_create.restype = C.c_void_p
     lib.lbfgsb200_drv_session_create.argtypes = [C.c_int, C.c_int, dp, dp, C.c_long, C.c_int, C.POINTER(_DrvParam), C.c_int, dp,
                                                  C.c_char_p, C.c_int]
@@ -178,6 +180,32 @@ class LBFGSParam:
     def _c(self):
         return _DrvParam(self.m, self.epsilon, self.epsilon_rel, self.past, self.delta, self.max_iterations,
                          self.linesearch, 10, self.max_linesearch, self.min_step, self.max_step, self.ftol, self.wolfe)
+
+
+class LBFGSBParam:
+    """Same fields and defaults as LBFGSpp::LBFGSBParam<Scalar> (reference Param.h:330-341)."""
+
+    def __init__(self, **kw):
+        self.m = 6
+        self.epsilon = 1e-5
+        self.epsilon_rel = 1e-5
+        self.past = 1
+        self.delta = 1e-10
+        self.max_iterations = 0
+        self.max_submin = 10
+        self.max_linesearch = 20
+        self.min_step = 1e-20
+        self.max_step = 1e20
+        self.ftol = 1e-4
+        self.wolfe = 0.9
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise AttributeError("LBFGSBParam has no field %r" % k)
+            setattr(self, k, v)
+
+    def _c(self):
+        return _DrvParam(self.m, self.epsilon, self.epsilon_rel, self.past, self.delta, self.max_iterations, 3, self.max_submin,
+                         self.max_linesearch, self.min_step, self.max_step, self.ftol, self.wolfe)
 
 
 _EXC = {1: ValueError, 2: ArithmeticError, 3: RuntimeError, 4: RuntimeError}
@@ -223,6 +251,36 @@ class LBFGSSolver:
                     gnorm=res.gnorm, x=x, grad=grad, trace=trace[:res.trace_len].copy(), seconds=res.seconds,
                     seconds_e2e=res.seconds_e2e, launches=res.launches, h2d_bytes=res.h2d_bytes,
                     d2h_bytes=res.d2h_bytes)
+
+
+class LBFGSBSolver:
+    """LBFGSpp::LBFGSBSolver<double> (More-Thuente line search) on the GPU, host buffers in and out."""
+
+    def __init__(self, param=None, device=0):
+        self.param = param if param is not None else LBFGSBParam()
+        self.device = device
+
+    def minimize(self, objective, x0, lb, ub, data0=None, data1=None, trace_cap=100000, raise_errors=False):
+        drv = driver()
+        x = np.array(x0, dtype=np.float64, order="C").copy()
+        n = x.size
+        lbv = np.ascontiguousarray(np.broadcast_to(lb, n), dtype=np.float64)
+        ubv = np.ascontiguousarray(np.broadcast_to(ub, n), dtype=np.float64)
+        grad = np.zeros(n)
+        trace = np.zeros(trace_cap)
+        d0 = None if data0 is None else np.ascontiguousarray(data0, dtype=np.float64)
+        d1 = None if data1 is None else np.ascontiguousarray(data1, dtype=np.float64)
+        dp = C.POINTER(C.c_double)
+        ptr = lambda a: a.ctypes.data_as(dp) if a is not None else None
+        res = _DrvResult()
+        p = self.param._c()
+        drv.lbfgsb200_drv_lbfgsb_f64(self.device, objective, ptr(d0), ptr(d1), n, C.byref(p), ptr(x), ptr(lbv), ptr(ubv),
+                                     ptr(grad), ptr(trace), trace_cap, C.byref(res))
+        if res.status and raise_errors:
+            raise _EXC.get(res.status, RuntimeError)(res.msg.decode())
+        return dict(status=STATUS_NAMES[res.status], msg=res.msg.decode(), niter=res.niter, nfev=res.nfev, fx=res.fx,
+                    gnorm=res.gnorm, x=x, grad=grad, trace=trace[:res.trace_len].copy(), seconds=res.seconds,
+                    seconds_e2e=res.seconds_e2e, launches=res.launches)
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -362,6 +362,7 @@ struct lbfgs_b200_hist
     void *S = nullptr, *Y = nullptr, *ys = nullptr, *alpha = nullptr, *theta = nullptr;
     void* SY[2] = {nullptr, nullptr};  // Gram matrices [M][M] by physical slot, double-buffered (see k_gram_combine)
     void* YY[2] = {nullptr, nullptr};
+    void* SS[2] = {nullptr, nullptr};
     int gram_cur = 0;  // which buffer is current
     int pending = -1;  // physical slot of the newest pair whose Gram row/column has not been folded in yet
     int head = 0;   // physical slot the next pair is written to
@@ -1125,7 +1126,9 @@ template <class T> static GramSolveArgs<T> make_solve_args(lbfgs_b200_hist* h, T
     g.raw = ctx->gram_raw;
     const int in = h->gram_cur, out = (h->pending >= 0) ? 1 - h->gram_cur : h->gram_cur;
     g.SY_in = static_cast<const T*>(h->SY[in]); g.YY_in = static_cast<const T*>(h->YY[in]);
+    g.SS_in = static_cast<const T*>(h->SS[in]);
     g.SY_out = static_cast<T*>(h->SY[out]); g.YY_out = static_cast<T*>(h->YY[out]);
+    g.SS_out = static_cast<T*>(h->SS[out]);
     g.ys = static_cast<const T*>(h->ys); g.alpha = static_cast<T*>(h->alpha);
     g.theta = static_cast<const T*>(h->theta);
     fill_slots<T>(h, g.slots);
@@ -1267,6 +1270,7 @@ lbfgs_b200_status lbfgs_b200_hist_create(lbfgs_b200_ctx* ctx, lbfgs_b200_hist** 
     {
         if (e == cudaSuccess) e = cudaMalloc(&h->SY[b], (size_t)elem_bytes * h->M * h->M);
         if (e == cudaSuccess) e = cudaMalloc(&h->YY[b], (size_t)elem_bytes * h->M * h->M);
+        if (e == cudaSuccess) e = cudaMalloc(&h->SS[b], (size_t)elem_bytes * h->M * h->M);
     }
     if (e != cudaSuccess)
     {
@@ -1283,7 +1287,7 @@ void lbfgs_b200_hist_destroy(lbfgs_b200_hist* h)
     if (!h) return;
     if (h->ctx && h->ctx->stream) cudaStreamSynchronize(h->ctx->stream);
     cudaFree(h->S); cudaFree(h->Y); cudaFree(h->ys); cudaFree(h->alpha); cudaFree(h->theta);
-    for (int b = 0; b < 2; b++) { cudaFree(h->SY[b]); cudaFree(h->YY[b]); }
+    for (int b = 0; b < 2; b++) { cudaFree(h->SY[b]); cudaFree(h->YY[b]); cudaFree(h->SS[b]); }
     delete h;
 }
 
@@ -1299,6 +1303,7 @@ lbfgs_b200_status lbfgs_b200_hist_reset(lbfgs_b200_hist* h)
     {
         CU(ctx, cudaMemsetAsync(h->SY[b], 0, (size_t)h->elem * h->M * h->M, ctx->stream));
         CU(ctx, cudaMemsetAsync(h->YY[b], 0, (size_t)h->elem * h->M * h->M, ctx->stream));
+        CU(ctx, cudaMemsetAsync(h->SS[b], 0, (size_t)h->elem * h->M * h->M, ctx->stream));
     }
     CU(ctx, cudaMemsetAsync(h->ys, 0, (size_t)h->elem * h->M, ctx->stream));
     CU(ctx, cudaMemsetAsync(h->alpha, 0, (size_t)h->elem * h->M, ctx->stream));
@@ -1336,3 +1341,4 @@ DEFINE_HIST(double, f64)
 DEFINE_HIST(float, f32)
 
 }  // extern "C"
+#include "lbfgsb_impl.cuh"

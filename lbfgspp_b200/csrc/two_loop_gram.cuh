@@ -29,7 +29,7 @@ constexpr int kGramStages = 3;
 constexpr int kGramMaxWarps = 24;  // 768 threads, one CTA per SM (85 registers per thread available)
 constexpr int kGramMaxThreads = kGramMaxWarps * 32;
 constexpr int kMaxM = 64;
-constexpr int kGramVals = 5;       // per column pair: s.v, y.v, s.ynew, y.ynew, y.snew
+constexpr int kGramVals = 6;       // per column pair: s.v, y.v, s.ynew, y.ynew, y.snew, s.snew
 
 template <class T> struct GramDotsArgs
 {
@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(kGramMaxThreads, 1) k_gram_dots(GramDotsArgs<T
                                 acc[r][2] += ps[u].v[k] * pyn.v[k];
                                 acc[r][3] += py[u].v[k] * pyn.v[k];
                                 acc[r][4] += py[u].v[k] * psn.v[k];
+                                acc[r][5] += ps[u].v[k] * psn.v[k];
                             }
                         }
                     }
@@ -309,8 +310,10 @@ template <class T> struct GramSolveArgs
     const double* raw;       // [c][5] reduced dots (after the all-reduce)
     const T* SY_in;          // [M][M] by physical slot: SY[i*M+j] = s_i'y_j
     const T* YY_in;          // [M][M]
+    const T* SS_in;          // [M][M]  s_i's_j (not used by the recursion; kept for the L-BFGS-B middle matrix)
     T* SY_out;               // folded matrices (a second buffer: other CTAs may still be reading *_in)
     T* YY_out;
+    T* SS_out;
     const T* ys;             // [M]
     T* alpha;                // [M]
     const T* theta;
@@ -343,8 +346,12 @@ __device__ void gram_solve_in_smem(const GramSolveArgs<T>& g, T* sm, bool writer
         sYY[idx] = yy;
         if (writer && g.new_slot >= 0)
         {
+            T ss = g.SS_in[pi * M + pj];
+            if (j == 0) ss = (T)g.raw[i * kGramVals + 5];        // s_i's_new
+            else if (i == 0) ss = (T)g.raw[j * kGramVals + 5];   // s_new's_j
             g.SY_out[pi * M + pj] = sy;
             g.YY_out[pi * M + pj] = yy;
+            g.SS_out[pi * M + pj] = ss;
         }
     }
     __syncthreads();
