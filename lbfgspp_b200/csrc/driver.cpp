@@ -457,3 +457,45 @@ extern "C" int lbfgsb200_drv_lbfgsb_f64(int device_ordinal, int objective, const
         out->d2h_bytes = 8L * n * (grad_host ? 2 : 1);
     });
 }
+
+// Cauchy point on an explicit history (kernel-level test hook): pairs are appended with add_correction, then
+// Cauchy<double>::get_cauchy_point runs.  Outputs: xcp (n), classes (n), vecc (2c), counts {nact, nfree}.
+extern "C" int lbfgsb200_drv_cauchy_f64(int device_ordinal, long n, int m, int npairs, const double* S_host, const double* Y_host,
+                                        const double* x_host, const double* g_host, const double* lb_host, const double* ub_host,
+                                        double* xcp_host, unsigned char* cls_host, double* vecc_host, long* counts2, double* theta_out,
+                                        char* err, int errlen)
+{
+    try
+    {
+        Device& dev = device(device_ordinal);
+        typedef DeviceVector<double> Vector;
+        BFGSMat<double, true> mat;
+        mat.reset(dev, n, m);
+        Vector s(dev), y(dev);
+        for (int k = 0; k < npairs; k++)
+        {
+            s.copy_from_host(S_host + size_t(k) * n, n);
+            y.copy_from_host(Y_host + size_t(k) * n, n);
+            mat.add_correction(s, y);
+        }
+        mat.refresh_middle();
+        Vector x(dev), g(dev), lb(dev), ub(dev);
+        x.copy_from_host(x_host, n);
+        g.copy_from_host(g_host, n);
+        lb.copy_from_host(lb_host, n);
+        ub.copy_from_host(ub_host, n);
+        const CauchyResult<double> cp = Cauchy<double>::get_cauchy_point(mat, x, g, lb, ub);
+        dev.check(lbfgs_b200_memcpy_d2h(dev.ctx(), xcp_host, lbfgs_b200_box_xcp(mat.box()), sizeof(double) * size_t(n)));
+        dev.check(lbfgs_b200_memcpy_d2h(dev.ctx(), cls_host, lbfgs_b200_box_classes(mat.box()), size_t(n)));
+        for (size_t q = 0; q < cp.vecc.size(); q++) vecc_host[q] = cp.vecc[q];
+        counts2[0] = cp.nact;
+        counts2[1] = cp.nfree;
+        *theta_out = mat.theta();
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        if (err && errlen > 0) { std::strncpy(err, e.what(), size_t(errlen) - 1); err[errlen - 1] = 0; }
+        return 1;
+    }
+}
