@@ -117,6 +117,10 @@ class _DrvParam(C.Structure):
                 ("max_step", C.c_double), ("ftol", C.c_double), ("wolfe", C.c_double)]
 
 
+class _BatchItem(C.Structure):
+    _fields_ = [("status", C.c_int), ("niter", C.c_int), ("nfev", C.c_long), ("fx", C.c_double), ("gnorm", C.c_double)]
+
+
 class _DrvResult(C.Structure):
     _fields_ = [("status", C.c_int), ("msg", C.c_char * 200), ("niter", C.c_int), ("nfev", C.c_long),
                 ("fx", C.c_double), ("gnorm", C.c_double), ("trace_len", C.c_long), ("seconds", C.c_double),
@@ -484,6 +488,29 @@ class Session:
         if self.h:
             self.drv.lbfgsb200_drv_session_destroy(self.h)
             self.h = None
+
+
+def solve_batch(objective, X0, param=None, linesearch="MoreThuente", device=0, hv_algo=HV_AUTO, threads=4, sharded=False,
+                return_x=True):
+    """B independent problems (rows of X0) on one GPU: LBFGSSolver::minimize per problem, `threads` host threads each with
+    its own context/stream.  sharded=True: run on the driver's communicator-attached context (n-sharded over ranks), one
+    thread.  Returns (list of dicts, X, seconds)."""
+    drv = driver()
+    X0 = np.ascontiguousarray(X0, dtype=np.float64)
+    B, n = X0.shape
+    param = param if param is not None else LBFGSParam()
+    items = (_BatchItem * B)()
+    X = np.empty_like(X0) if return_x else None
+    secs = C.c_double(0)
+    dp = C.POINTER(C.c_double)
+    drv.lbfgsb200_drv_batch_f64.argtypes = [C.c_int, C.c_int, C.c_long, C.c_int, dp, C.c_int, C.POINTER(_DrvParam), C.c_int, C.c_int,
+                                            C.c_int, C.POINTER(_BatchItem), dp, dp]
+    p = param._c()
+    ls = LINE_SEARCHES[linesearch] if isinstance(linesearch, str) else int(linesearch)
+    drv.lbfgsb200_drv_batch_f64(device, objective, n, B, X0.ctypes.data_as(dp), ls, C.byref(p), hv_algo, threads, int(sharded), items,
+                                X.ctypes.data_as(dp) if return_x else None, C.byref(secs))
+    res = [dict(status=STATUS_NAMES[it.status], niter=it.niter, nfev=it.nfev, fx=it.fx, gnorm=it.gnorm) for it in items]
+    return res, X, secs.value
 
 
 def driver_ctx(device=0):

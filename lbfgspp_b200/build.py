@@ -51,7 +51,7 @@ def build_driver(force=False):
     if not force and _newer(DRV, srcs + [LIB]):
         return DRV
     cmd = [CXX, "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-o", DRV, os.path.join(CSRC, "driver.cpp"),
-           "-L", PKG, "-l:liblbfgs_b200.so", "-Wl,-rpath,$ORIGIN"]
+           "-L", PKG, "-l:liblbfgs_b200.so", "-Wl,-rpath,$ORIGIN", "-pthread"]
     subprocess.run(cmd, check=True)
     return DRV
 

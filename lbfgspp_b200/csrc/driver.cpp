@@ -499,3 +499,96 @@ extern "C" int lbfgsb200_drv_cauchy_f64(int device_ordinal, long n, int m, int n
         return 1;
     }
 }
+
+// ----------------------------------------------------------------------------------------------------------
+// Batches of independent problems (BASELINE config 5).  `nthreads` host threads, each with its own context
+// (stream, reduction scratch, mailbox) and its own solver object, take problems b = t, t + nthreads, ... ;
+// kernels of different problems interleave on the GPU and fill each other's launch/synchronisation gaps.
+// Every problem runs exactly the single-problem code path, so its result is bit-identical to a lone solve.
+// With a communicator attached to the device's driver context (n-sharded mode) use nthreads = 1.
+// ----------------------------------------------------------------------------------------------------------
+#include <thread>
+
+typedef struct
+{
+    int status;
+    int niter;
+    long nfev;
+    double fx;
+    double gnorm;
+} drv_batch_item;
+
+namespace {
+
+template <template <class> class LS>
+void batch_worker(int dev_ordinal, bool use_shared_device, int objective, long n, int B, int first, int stride, const double* x0s,
+                  const drv_param* q, int hv_algo, drv_batch_item* items, double* xs_out)
+{
+    typedef DeviceVector<double> Vector;
+    std::unique_ptr<Device> own;
+    Device* dev = nullptr;
+    try
+    {
+        if (use_shared_device) dev = &device(dev_ordinal);
+        else { own.reset(new Device(dev_ordinal)); dev = own.get(); }
+        const LBFGSParam<double> prm = to_param<double>(q);
+        LBFGSSolver<double, LS> solver(prm);
+        solver.set_hv_algorithm(hv_algo);
+        BuiltinObjective<double> obj(objective);
+        Vector x(*dev);
+        for (int b = first; b < B; b += stride)
+        {
+            drv_batch_item& it = items[b];
+            try
+            {
+                x.copy_from_host(x0s + size_t(b) * n, n);
+                double fx = 0;
+                it.niter = solver.minimize(obj, x, fx);
+                it.fx = fx;
+                it.gnorm = solver.final_grad_norm();
+                it.nfev = solver.num_evaluations();
+                it.status = 0;
+                if (xs_out) x.copy_to_host(xs_out + size_t(b) * n);
+            }
+            catch (const std::invalid_argument&) { it.status = 1; }
+            catch (const std::logic_error&) { it.status = 2; }
+            catch (const std::runtime_error&) { it.status = 3; }
+        }
+    }
+    catch (...)
+    {
+        for (int b = first; b < B; b += stride) items[b].status = 4;
+    }
+}
+
+}  // namespace
+
+extern "C" int lbfgsb200_drv_batch_f64(int device_ordinal, int objective, long n, int B, const double* x0s_host, int ls,
+                                       const drv_param* prm, int hv_algo, int nthreads, int shared_device, drv_batch_item* items,
+                                       double* xs_out_host, double* seconds_out)
+{
+    if (nthreads < 1) nthreads = 1;
+    if (shared_device) nthreads = 1;
+    for (int b = 0; b < B; b++) items[b] = drv_batch_item{4, 0, 0, 0.0, 0.0};
+    const double t0 = now();
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; t++)
+    {
+        auto fn = [=]() {
+            switch (ls)
+            {
+            case DRV_LS_BACKTRACKING: batch_worker<LineSearchBacktracking>(device_ordinal, shared_device != 0, objective, n, B, t, nthreads, x0s_host, prm, hv_algo, items, xs_out_host); break;
+            case DRV_LS_BRACKETING: batch_worker<LineSearchBracketing>(device_ordinal, shared_device != 0, objective, n, B, t, nthreads, x0s_host, prm, hv_algo, items, xs_out_host); break;
+            case DRV_LS_NOCEDAL_WRIGHT: batch_worker<LineSearchNocedalWright>(device_ordinal, shared_device != 0, objective, n, B, t, nthreads, x0s_host, prm, hv_algo, items, xs_out_host); break;
+            default: batch_worker<LineSearchMoreThuente>(device_ordinal, shared_device != 0, objective, n, B, t, nthreads, x0s_host, prm, hv_algo, items, xs_out_host); break;
+            }
+        };
+        if (nthreads == 1) fn();
+        else pool.emplace_back(fn);
+    }
+    for (auto& th : pool) th.join();
+    if (seconds_out) *seconds_out = now() - t0;
+    int bad = 0;
+    for (int b = 0; b < B; b++) bad += items[b].status != 0;
+    return bad;
+}
