@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <type_traits>
 #include <vector>
 
 #include "LBFGSpp/BFGSMat.h"
@@ -33,6 +34,44 @@
 #include "LBFGSpp/Param.h"
 
 namespace LBFGSpp {
+
+// A minimal host vector for code that has no Eigen: contiguous storage + the few members user functors rely on.
+template <typename Scalar>
+class HostVector
+{
+    std::vector<Scalar> m_v;
+
+public:
+    HostVector() {}
+    explicit HostVector(std::ptrdiff_t n, Scalar fill = Scalar(0)) : m_v(size_t(n), fill) {}
+    std::ptrdiff_t size() const { return std::ptrdiff_t(m_v.size()); }
+    void resize(std::ptrdiff_t n) { m_v.resize(size_t(n)); }
+    Scalar* data() { return m_v.data(); }
+    const Scalar* data() const { return m_v.data(); }
+    Scalar& operator[](std::ptrdiff_t i) { return m_v[size_t(i)]; }
+    const Scalar& operator[](std::ptrdiff_t i) const { return m_v[size_t(i)]; }
+    static HostVector Zero(std::ptrdiff_t n) { return HostVector(n, Scalar(0)); }
+    static HostVector Constant(std::ptrdiff_t n, Scalar v) { return HostVector(n, v); }
+};
+
+// Wraps a host functor `Scalar f(const HostVec& x, HostVec& grad)` as a device functor (see LBFGSSolver::minimize below).
+template <typename Foo, typename HostVec>
+class HostFunctorAdapter
+{
+    Foo& m_f;
+    HostVec m_x, m_g;
+
+public:
+    HostFunctorAdapter(Foo& f, std::ptrdiff_t n) : m_f(f), m_x(n), m_g(n) {}
+    template <typename Scalar>
+    Scalar operator()(const DeviceVector<Scalar>& x, DeviceVector<Scalar>& grad)
+    {
+        x.copy_to_host(m_x.data());
+        const Scalar fx = m_f(static_cast<const HostVec&>(m_x), m_g);
+        grad.copy_from_host(m_g.data(), x.size());
+        return fx;
+    }
+};
 
 template <typename Scalar, template <class> class LineSearch = LineSearchNocedalWright>
 class LBFGSSolver
@@ -123,8 +162,31 @@ public:
         return k;
     }
 
+    // ----- host-vector compatibility mode ---------------------------------------------------------------------------
+    // Existing LBFGSpp code passes host vectors (Eigen::VectorXd) and a functor over host vectors.  Any `HostVec` with
+    // data() / size() / resize() (Eigen::VectorXd, LBFGSpp::HostVector<Scalar>, ...) is accepted here: x is uploaded once, every
+    // objective evaluation copies x to the host, calls `f(x_host, grad_host)` and uploads grad (2n words over PCIe per call --
+    // meant for small problems and for porting; the vector work of the solver itself still runs on the GPU), and the
+    // solution is copied back into x.
+    template <typename Foo, typename HostVec>
+    typename std::enable_if<!std::is_same<HostVec, Vector>::value, int>::type minimize(Foo& f, HostVec& x, Scalar& fx)
+    {
+        Device& dev = Device::get_default();
+        const std::ptrdiff_t n = std::ptrdiff_t(x.size());
+        HostFunctorAdapter<Foo, HostVec> adapter(f, n);
+        Vector xd(dev);
+        xd.copy_from_host(x.data(), n);
+        const int niter = minimize(adapter, xd, fx);
+        xd.copy_to_host(x.data());
+        return niter;
+    }
+
     const Vector& final_grad() const { return m_grad; }
     Scalar final_grad_norm() const { return m_gnorm; }
+    // final_approx_hessian() / final_approx_inverse_hessian() of the reference (LBFGS.h:192-197 -> BFGSMat.h:150-271): explicit
+    // n x n matrices, only sensible for small n; returned row-major on the host.
+    SmallMatrix<Scalar> final_approx_hessian() { return m_bfgs.dense(false); }
+    SmallMatrix<Scalar> final_approx_inverse_hessian() { return m_bfgs.dense(true); }
     // number of objective evaluations of the last minimize() call (not in the reference; used by tests/bench)
     long num_evaluations() const { return m_nfev; }
 };

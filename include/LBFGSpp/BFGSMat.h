@@ -8,7 +8,9 @@
 #ifndef LBFGSPP_B200_BFGS_MAT_H
 #define LBFGSPP_B200_BFGS_MAT_H
 
+#include <algorithm>
 #include <limits>
+#include <stdexcept>
 
 #include <vector>
 
@@ -239,6 +241,57 @@ public:
             }
         }
         lincomb(Scalar(0), nullptr, coef, mask, out_dev);
+    }
+
+    // Explicit n x n approximations for small n (final_approx_hessian / final_approx_inverse_hessian of the reference,
+    // BFGSMat.h:150-271), through the compact representation:
+    //   B = theta*I - W M W'                with the Minv above,
+    //   H = I/theta + Z N Z',  Z = [Y/theta, S],  N = [ 0, -R^-1 ; -R^-T, R^-T (D + Y'Y/theta) R^-1 ],  R = triu(S'Y) in
+    //   chronological order.  H is formed as inv(B) here (same matrix; n is small by contract).
+    SmallMatrix<Scalar> dense(bool inverse)
+    {
+        refresh_middle();
+        const int n = int(m_n), c = m_c_host;
+        if (n > 4096) throw std::invalid_argument("dense Hessian approximations are only formed for n <= 4096");
+        SmallMatrix<Scalar> B(n, n);
+        for (int i = 0; i < n; i++) B(i, i) = m_theta_host;
+        if (c > 0)
+        {
+            // rows of W = [Y, theta*S] by age, downloaded column by column
+            SmallMatrix<Scalar> W(n, 2 * c);
+            std::vector<Scalar> col(static_cast<size_t>(n));
+            for (int a = 0; a < c; a++)
+            {
+                m_dev->check(lbfgs_b200_memcpy_d2h(m_dev->ctx(), col.data(), lbfgs_b200_hist_y_col(m_hist, a), sizeof(Scalar) * size_t(n)));
+                for (int i = 0; i < n; i++) W(i, a) = col[size_t(i)];
+                m_dev->check(lbfgs_b200_memcpy_d2h(m_dev->ctx(), col.data(), lbfgs_b200_hist_s_col(m_hist, a), sizeof(Scalar) * size_t(n)));
+                for (int i = 0; i < n; i++) W(i, c + a) = m_theta_host * col[size_t(i)];
+            }
+            for (int i = 0; i < n; i++)
+            {
+                std::vector<Scalar> wi(size_t(2 * c));
+                for (int q = 0; q < 2 * c; q++) wi[size_t(q)] = W(i, q);
+                const std::vector<Scalar> Mw = m_M.times(wi);
+                for (int j = 0; j < n; j++)
+                {
+                    Scalar acc = Scalar(0);
+                    for (int q = 0; q < 2 * c; q++) acc += W(j, q) * Mw[size_t(q)];
+                    B(j, i) -= acc;
+                }
+            }
+        }
+        if (!inverse) return B;
+        SmallSolver<Scalar> lu(B);
+        SmallMatrix<Scalar> H(n, n);
+        std::vector<Scalar> e(static_cast<size_t>(n));
+        for (int j = 0; j < n; j++)
+        {
+            std::fill(e.begin(), e.end(), Scalar(0));
+            e[size_t(j)] = Scalar(1);
+            lu.solve_inplace(e);
+            for (int i = 0; i < n; i++) H(i, j) = e[size_t(i)];
+        }
+        return H;
     }
 
     // the n-sized scratch of Cauchy / SubspaceMin, created on first use and tied to the history

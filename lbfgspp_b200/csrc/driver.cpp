@@ -592,3 +592,30 @@ extern "C" int lbfgsb200_drv_batch_f64(int device_ordinal, int objective, long n
     for (int b = 0; b < B; b++) bad += items[b].status != 0;
     return bad;
 }
+
+// dense B or H of an explicit history (test hook for final_approx_hessian / final_approx_inverse_hessian)
+extern "C" int lbfgsb200_drv_dense_f64(int device_ordinal, long n, int m, int npairs, const double* S_host, const double* Y_host,
+                                       int inverse, double* out_host /* n*n row-major */, char* err, int errlen)
+{
+    try
+    {
+        Device& dev = device(device_ordinal);
+        BFGSMat<double> mat;
+        mat.reset(dev, n, m);
+        DeviceVector<double> s(dev), y(dev);
+        for (int k = 0; k < npairs; k++)
+        {
+            s.copy_from_host(S_host + size_t(k) * n, n);
+            y.copy_from_host(Y_host + size_t(k) * n, n);
+            mat.add_correction(s, y);
+        }
+        const SmallMatrix<double> D = mat.dense(inverse != 0);
+        for (long i = 0; i < n * n; i++) out_host[i] = D.data()[i];
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        if (err && errlen > 0) { std::strncpy(err, e.what(), size_t(errlen) - 1); err[errlen - 1] = 0; }
+        return 1;
+    }
+}

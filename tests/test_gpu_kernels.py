@@ -190,3 +190,32 @@ def test_bad_arguments_are_reported(gpu_ctx):
     h32 = lb.History(gpu_ctx, 10, 3, np.float32)
     with pytest.raises(lb.LbfgsB200Error):
         gpu_ctx.check(gpu_ctx.lib.lbfgs_b200_hist_apply_Hv_f64(h32.h, v.ptr, -1.0, gpu_ctx.empty(10).ptr, 0, None))
+
+
+@pytest.mark.parametrize("n,m,npairs", [(6, 3, 0), (6, 3, 2), (12, 4, 4), (12, 4, 9), (40, 6, 6)])
+def test_dense_hessian_approximations(n, m, npairs):
+    """final_approx_hessian / final_approx_inverse_hessian (reference BFGSMat.h:150-271) against the textbook BFGS update applied
+    pair by pair to B0 = theta*I (independent of the compact representation used on both sides)."""
+    import ctypes as C
+    rng = np.random.default_rng(n + npairs)
+    S = rng.standard_normal((npairs, n))
+    A = rng.standard_normal((n, n))
+    A = A @ A.T / n + np.eye(n)                      # y = A s: consistent curvature
+    Y = S @ A
+    Sk, Yk = S[-m:], Y[-m:]
+    theta = float(Yk[-1] @ Yk[-1]) / float(Sk[-1] @ Yk[-1]) if npairs else 1.0
+    B = theta * np.eye(n)
+    for s, y in zip(Sk, Yk):
+        Bs = B @ s
+        B = B - np.outer(Bs, Bs) / (s @ Bs) + np.outer(y, y) / (y @ s)
+    drv = lb.driver()
+    dp = C.POINTER(C.c_double)
+    drv.lbfgsb200_drv_dense_f64.argtypes = [C.c_int, C.c_long, C.c_int, C.c_int, dp, dp, C.c_int, dp, C.c_char_p, C.c_int]
+    err = C.create_string_buffer(256)
+    for inverse, ref in ((0, B), (1, np.linalg.inv(B))):
+        out = np.zeros((n, n))
+        Sc, Yc = np.ascontiguousarray(S), np.ascontiguousarray(Y)
+        st = drv.lbfgsb200_drv_dense_f64(0, n, m, npairs, Sc.ctypes.data_as(dp) if npairs else None,
+                                         Yc.ctypes.data_as(dp) if npairs else None, inverse, out.ctypes.data_as(dp), err, 256)
+        assert st == 0, err.value
+        assert np.max(np.abs(out - ref)) <= 1e-9 * np.max(np.abs(ref))
