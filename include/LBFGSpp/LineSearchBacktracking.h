@@ -9,6 +9,7 @@
 
 #include <stdexcept>
 
+#include "LineSearchCore.h"
 #include "LineSearchDriver.h"
 #include "Param.h"
 
@@ -20,51 +21,13 @@ class LineSearchBacktracking
 public:
     typedef DeviceVector<Scalar> Vector;
 
-    class Machine
+    // The decisions live in BacktrackingCore<Scalar> (LineSearchCore.h, shared with the device-resident solve); this adapter gives
+    // them the reference's exceptions.
+    class Machine : public CoreMachine<Scalar, BacktrackingCore>
     {
-        const LBFGSParam<Scalar>& prm;
-        Scalar f0, slope0, armijo_slope;
-        int trials;
-
     public:
-        Scalar step;
-        Scalar best_fx, best_dg;  // unused: this search never falls back to a remembered point
-
-        Machine(const LBFGSParam<Scalar>& param, Scalar fx_init, Scalar dg_init, Scalar step0, Scalar /*step_max*/) :
-            prm(param), f0(fx_init), slope0(dg_init), armijo_slope(param.ftol * dg_init), trials(0), step(step0),
-            best_fx(fx_init), best_dg(dg_init)
-        {
-            if (step0 <= Scalar(0)) throw std::invalid_argument("'step' must be positive");
-            if (dg_init > 0) throw std::logic_error("the moving direction increases the objective function value");
-        }
-
-        int advance(Scalar fx, Scalar dg, bool& /*keep*/)
-        {
-            const Scalar shrink = Scalar(0.5), grow = Scalar(2.1);
-            Scalar factor;
-            const bool armijo_fails = (fx > f0 + step * armijo_slope) || (fx != fx);
-            if (armijo_fails)
-                factor = shrink;
-            else
-            {
-                if (prm.linesearch == LBFGS_LINESEARCH_BACKTRACKING_ARMIJO) return LS_ACCEPT;
-                if (dg < prm.wolfe * slope0)
-                    factor = grow;
-                else
-                {
-                    if (prm.linesearch == LBFGS_LINESEARCH_BACKTRACKING_WOLFE) return LS_ACCEPT;
-                    if (dg > -prm.wolfe * slope0)
-                        factor = shrink;
-                    else
-                        return LS_ACCEPT;
-                }
-            }
-            if (step < prm.min_step) throw std::runtime_error("the line search step became smaller than the minimum value allowed");
-            if (step > prm.max_step) throw std::runtime_error("the line search step became larger than the maximum value allowed");
-            step *= factor;
-            if (++trials >= prm.max_linesearch) throw std::runtime_error("the line search routine reached the maximum number of iterations");
-            return LS_EVALUATE;
-        }
+        Machine(const LBFGSParam<Scalar>& param, Scalar fx_init, Scalar dg_init, Scalar step0, Scalar step_max) :
+            CoreMachine<Scalar, BacktrackingCore>(CoreMachine<Scalar, BacktrackingCore>::options_of(param, param.linesearch), fx_init, dg_init, step0, step_max) {}
     };
 
     // Reference-compatible entry point.  `grad` holds the gradient at xp on entry and at x on return;

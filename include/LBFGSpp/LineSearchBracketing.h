@@ -11,6 +11,7 @@
 #include <limits>
 #include <stdexcept>
 
+#include "LineSearchCore.h"
 #include "LineSearchDriver.h"
 #include "Param.h"
 
@@ -22,49 +23,13 @@ class LineSearchBracketing
 public:
     typedef DeviceVector<Scalar> Vector;
 
-    class Machine
+    // The decisions live in BracketingCore<Scalar> (LineSearchCore.h, shared with the device-resident solve); this adapter gives
+    // them the reference's exceptions.
+    class Machine : public CoreMachine<Scalar, BracketingCore>
     {
-        const LBFGSParam<Scalar>& prm;
-        Scalar f0, slope0, armijo_slope, lo, hi;
-        int trials;
-
     public:
-        Scalar step;
-        Scalar best_fx, best_dg;  // unused
-
-        Machine(const LBFGSParam<Scalar>& param, Scalar fx_init, Scalar dg_init, Scalar step0, Scalar /*step_max*/) :
-            prm(param), f0(fx_init), slope0(dg_init), armijo_slope(param.ftol * dg_init), lo(0),
-            hi(std::numeric_limits<Scalar>::infinity()), trials(0), step(step0), best_fx(fx_init), best_dg(dg_init)
-        {
-            if (step0 <= Scalar(0)) throw std::invalid_argument("'step' must be positive");
-            if (dg_init > 0) throw std::logic_error("the moving direction increases the objective function value");
-        }
-
-        int advance(Scalar fx, Scalar dg, bool& /*keep*/)
-        {
-            if (fx > f0 + step * armijo_slope || !std::isfinite(fx))
-                hi = step;
-            else
-            {
-                if (prm.linesearch == LBFGS_LINESEARCH_BACKTRACKING_ARMIJO) return LS_ACCEPT;
-                if (dg < prm.wolfe * slope0)
-                    lo = step;
-                else
-                {
-                    if (prm.linesearch == LBFGS_LINESEARCH_BACKTRACKING_WOLFE) return LS_ACCEPT;
-                    if (dg > -prm.wolfe * slope0)
-                        hi = step;
-                    else
-                        return LS_ACCEPT;
-                }
-            }
-            if (lo > hi) throw std::runtime_error("the lower bound of the bracketing interval becomes larger than the upper bound");
-            if (step < prm.min_step) throw std::runtime_error("the line search step became smaller than the minimum value allowed");
-            if (step > prm.max_step) throw std::runtime_error("the line search step became larger than the maximum value allowed");
-            step = std::isinf(hi) ? 2 * step : lo / 2 + hi / 2;
-            if (++trials >= prm.max_linesearch) throw std::runtime_error("the line search routine reached the maximum number of iterations");
-            return LS_EVALUATE;
-        }
+        Machine(const LBFGSParam<Scalar>& param, Scalar fx_init, Scalar dg_init, Scalar step0, Scalar step_max) :
+            CoreMachine<Scalar, BracketingCore>(CoreMachine<Scalar, BracketingCore>::options_of(param, param.linesearch), fx_init, dg_init, step0, step_max) {}
     };
 
     // Reference-compatible entry point (`dg` is an output only, LineSearchBracketing.h:60).

@@ -49,6 +49,7 @@ struct lbfgs_b200_ctx
     Mail* h_mail = nullptr;        // host view
     Mail* d_mail = nullptr;        // device view of the same memory
     unsigned long long mail_seq = 0;
+    unsigned smem_optin = 0;       // which k_gram_dots instantiations already have their shared-memory opt-in on this device
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
     // in-kernel exchange over peer memory (lbfgs_b200_comm_p2p_*): replaces the NCCL all-reduce when attached
@@ -1101,10 +1102,11 @@ static lbfgs_b200_status gram_dots(lbfgs_b200_hist* h, const T* v)
     const unsigned long long epoch = ctx->x_active ? ++ctx->x_epoch : 0ull;
 #define LAUNCH_GRAM(R)                                                                                       \
     do {                                                                                                     \
-        static bool attr_set = false;                                                                        \
-        if (!attr_set) {                                                                                     \
+        /* the opt-in for > 48 KB of dynamic shared memory is per device: remember it per context */        \
+        const unsigned bit = 1u << ((sizeof(T) == 8 ? 0 : 4) + R);                                           \
+        if (!(ctx->smem_optin & bit)) {                                                                      \
             CU(ctx, cudaFuncSetAttribute(k_gram_dots<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            attr_set = true;                                                                                 \
+            ctx->smem_optin |= bit;                                                                          \
         }                                                                                                    \
         k_gram_dots<T, R><<<grid, threads, smem, ctx->stream>>>(a, ctx->gram_partials, ctx->rb.ticket, ctx->gram_raw, xc, epoch); \
     } while (0)

@@ -80,6 +80,11 @@ typedef struct {
 ORC_DECLARE(orc_)
 ORC_DECLARE(ref_)
 
+/* restatement only: ONE line search from (xp, fx0 = f(xp), grad0 = f'(xp)) along drt with initial `step`, by the restated
+ * ls_* function `ls`.  Outputs: accepted step, fx, dg, x (n), grad (n); returns ORC_* status; nfev / msg in `out`. */
+int orc_line_search_f64(int objective, const double* data0, const double* data1, long n, int ls, const orc_param* prm,
+                        const double* xp, const double* drt, double step_max, double* step_inout, double* fx_out, double* dg_out,
+                        double* x_out, double* grad_out, double* fx_trace, long trace_cap, orc_result* out);
 /* restatement only: repeated apply_Hv timing for the CPU baseline (returns seconds per call) */
 double orc_bfgs_apply_Hv_bench_f64(long n, int m, int reps, int sum_mode, int threads);
 /* restatement only: Gram-form (vector-free) two-loop used to study the fast GPU variant on CPU */

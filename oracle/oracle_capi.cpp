@@ -182,6 +182,47 @@ int orc_bfgs_apply_Hv_f64(long n, int m, int npairs, const double* S, const doub
     return 0;
 }
 
+int orc_line_search_f64(int objective, const double* d0, const double* d1, long n, int ls, const orc_param* prm, const double* xp,
+                        const double* drt, double step_max, double* step_inout, double* fx_out, double* dg_out, double* x_out,
+                        double* grad_out, double* trace, long cap, orc_result* out)
+{
+    return guarded(out, [&]() {
+        const orc::Blas1<double> la(ORC_SUM_SEQUENTIAL, 1);
+        Functor<double> f{objective, d0, d1, n, 1, 0, nullptr, 0};
+        std::vector<double> vxp(xp, xp + n), vd(drt, drt + n), x(n), grad(n);
+        double fx = f(vxp.data(), grad.data());
+        double dg = la.dot(grad.data(), vd.data(), n);
+        f.nfev = 0;
+        f.trace = trace;
+        f.cap = cap;
+        double step = *step_inout;
+        try
+        {
+            switch (ls)
+            {
+            case ORC_LS_BACKTRACKING: orc::ls_backtracking(f, *prm, la, vxp, vd, step_max, step, fx, grad, dg, x); break;
+            case ORC_LS_BRACKETING: orc::ls_bracketing(f, *prm, la, vxp, vd, step_max, step, fx, grad, dg, x); break;
+            case ORC_LS_NOCEDAL_WRIGHT: orc::ls_nocedal_wright(f, *prm, la, vxp, vd, step_max, step, fx, grad, dg, x); break;
+            default: orc::ls_more_thuente(f, *prm, la, vxp, vd, step_max, step, fx, grad, dg, x); break;
+            }
+        }
+        catch (...)
+        {
+            out->nfev = f.nfev;
+            out->trace_len = std::min(f.nfev, cap);
+            throw;
+        }
+        *step_inout = step;
+        *fx_out = fx;
+        *dg_out = dg;
+        std::copy(x.begin(), x.end(), x_out);
+        std::copy(grad.begin(), grad.end(), grad_out);
+        out->nfev = f.nfev;
+        out->trace_len = std::min(f.nfev, cap);
+        out->fx = fx;
+    });
+}
+
 double orc_objective_f64(int objective, const double* d0, const double* d1, long n, const double* x, double* grad)
 {
     return orc::evaluate<double>(objective, d0, d1, n, x, grad);

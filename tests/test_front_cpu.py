@@ -1,0 +1,88 @@
+"""CPU tests of the product's host logic: the line-search cores (include/LBFGSpp/LineSearchCore.h, the single source of the
+scalar decisions for both the header-only front and the device-resident solve) must behave bit-identically to the restated
+reference line searches, including every error path (exception kind + message)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import pyoracle as po
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, "tests", "cpp", "core_harness.so")
+
+
+@pytest.fixture(scope="module")
+def harness():
+    src = os.path.join(ROOT, "tests", "cpp", "core_harness.cpp")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-march=x86-64-v3", "-fPIC", "-shared", "-Wall",
+                    "-I", os.path.join(ROOT, "oracle"), "-o", SO, src], check=True)
+    lib = C.CDLL(SO)
+    dp = C.POINTER(C.c_double)
+    lib.core_line_search_f64.argtypes = [C.c_int, dp, dp, C.c_long, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                                         C.c_double, dp, dp, C.c_double, dp, dp, dp, dp, dp, dp, C.c_long, C.POINTER(C.c_long)]
+    lib.core_error_message.restype = C.c_char_p
+    return lib
+
+
+def oracle_ls(orc, objective, ls, prm, xp, drt, step, step_max):
+    n = xp.size
+    dp = C.POINTER(C.c_double)
+    P = lambda a: a.ctypes.data_as(dp)
+    x, g, trace = np.zeros(n), np.zeros(n), np.zeros(4096)
+    st, fx, dg = C.c_double(step), C.c_double(0), C.c_double(0)
+    res = po.Result()
+    orc.lib.orc_line_search_f64.argtypes = [C.c_int, dp, dp, C.c_long, C.c_int, C.POINTER(po.Param), dp, dp, C.c_double, dp, dp, dp, dp,
+                                            dp, dp, C.c_long, C.POINTER(po.Result)]
+    orc.lib.orc_line_search_f64(objective, None, None, n, ls, C.byref(prm), P(xp), P(drt), step_max, C.byref(st), C.byref(fx),
+                                C.byref(dg), P(x), P(g), P(trace), 4096, C.byref(res))
+    return dict(status=res.status, msg=res.msg.decode(), step=st.value, fx=fx.value, dg=dg.value, x=x, g=g,
+                trace=trace[:res.trace_len].copy(), nfev=res.nfev)
+
+
+def core_ls(lib, objective, ls, prm, xp, drt, step, step_max):
+    n = xp.size
+    dp = C.POINTER(C.c_double)
+    P = lambda a: a.ctypes.data_as(dp)
+    x, g, trace = np.zeros(n), np.zeros(n), np.zeros(4096)
+    st, fx, dg, nfev = C.c_double(step), C.c_double(0), C.c_double(0), C.c_long(0)
+    rc = lib.core_line_search_f64(objective, None, None, n, ls, prm.linesearch, prm.max_linesearch, prm.min_step, prm.max_step, prm.ftol,
+                                  prm.wolfe, P(xp), P(drt), step_max, C.byref(st), C.byref(fx), C.byref(dg), P(x), P(g), P(trace), 4096,
+                                  C.byref(nfev))
+    status = 0 if rc == 0 else lib.core_error_kind(rc)
+    msg = "" if rc == 0 else lib.core_error_message(rc).decode()
+    return dict(status=status, msg=msg, step=st.value, fx=fx.value, dg=dg.value, x=x, g=g, trace=trace[:min(nfev.value, 4096)].copy(),
+                nfev=nfev.value)
+
+
+@pytest.mark.parametrize("ls", [0, 1, 2, 3])
+def test_cores_match_restated_line_searches_bit_for_bit(harness, orc, ls):
+    rng = np.random.default_rng(40 + ls)
+    checked = errors = 0
+    for trial in range(300):
+        n = int(rng.choice([2, 4, 10, 50]))
+        xp = rng.uniform(-1.5, 1.5, n)
+        _, g = orc.objective(po.OBJ_ROSENBROCK_PAIRED, xp)
+        # mostly descent directions of wildly different scales; sometimes an ascent direction (error path)
+        drt = -g * 10.0 ** rng.uniform(-4, 1) + 0.05 * rng.standard_normal(n) * np.linalg.norm(g)
+        if trial % 17 == 0:
+            drt = g.copy()
+        step = float(10.0 ** rng.uniform(-3, 1))
+        prm = orc.default_param(linesearch=int(rng.choice([1, 2, 3])) if ls < 2 else 3,
+                                max_linesearch=int(rng.choice([1, 2, 5, 20, 64])), min_step=float(rng.choice([1e-20, 1e-3])),
+                                max_step=float(rng.choice([1e20, 2.0])))
+        step_max = float(rng.choice([1e20, 5.0, 0.5]))
+        a = oracle_ls(orc, po.OBJ_ROSENBROCK_PAIRED, ls, prm, xp, drt, step, step_max)
+        b = core_ls(harness, po.OBJ_ROSENBROCK_PAIRED, ls, prm, xp, drt, step, step_max)
+        assert a["status"] == b["status"], (trial, a["msg"], b["msg"])
+        assert a["msg"] == b["msg"]
+        assert a["nfev"] == b["nfev"] and np.array_equal(a["trace"], b["trace"])
+        if a["status"] == 0:
+            assert a["step"] == b["step"] and a["fx"] == b["fx"] and a["dg"] == b["dg"]
+            assert np.array_equal(a["x"], b["x"]) and np.array_equal(a["g"], b["g"])
+            checked += 1
+        else:
+            errors += 1
+    assert checked > 100 and errors > 5
