@@ -139,6 +139,7 @@ def main():
     ap.add_argument("--hv", default="auto", choices=["auto", "two_loop", "gram"])
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: in-kernel all-reduce over NVLink peer memory (default) or one ncclAllReduce per reduction")
+    ap.add_argument("--host-driven", action="store_true", help="host-driven solver loop instead of the device-resident CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-mode", action="store_true", help="timed region only (for runs under ncu; numbers are not bench values)")
     args = ap.parse_args()
@@ -193,7 +194,11 @@ def main():
 
     hv = {"auto": lb.HV_AUTO, "two_loop": lb.HV_TWO_LOOP, "gram": lb.HV_GRAM}[args.hv]
     prm = lb.LBFGSParam(m=M_HIST)
-    sess = lb.Session(lb.OBJ_ROSENBROCK_PAIRED, np.zeros(n_local), prm, "MoreThuente", device=local_rank, hv_algo=hv)
+    resident = (not args.host_driven) and (world == 1 or args.comm == "p2p") and args.hv != "two_loop"
+    sess = lb.Session(lb.OBJ_ROSENBROCK_PAIRED, np.zeros(n_local), prm, "MoreThuente", device=local_rank, hv_algo=hv, resident=resident)
+    # per-phase CUDA events exist only on the host-driven path: a second session supplies the phase / roofline numbers
+    prof_sess = sess if not resident else lb.Session(lb.OBJ_ROSENBROCK_PAIRED, np.zeros(n_local), prm, "MoreThuente",
+                                                     device=local_rank, hv_algo=hv, resident=False)
     ctx = lb.driver_ctx(local_rank)
     abi = lb.abi()
 
@@ -206,10 +211,6 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     import ctypes as C
-    abi.lbfgs_b200_profile_enable(ctx, 1)
-    for ph in range(3):
-        abi.lbfgs_b200_profile_read(ctx, ph, None, None, 1)
-        abi.lbfgs_b200_profile_bytes(ctx, ph, C.byref(C.c_double()), 1)
     barrier()
     abi.lbfgs_b200_timer_start(ctx)
     launches = 0
@@ -222,6 +223,19 @@ def main():
     abi.lbfgs_b200_timer_stop(ctx, C.byref(ms))
     barrier()
     dev_seconds = max_over_ranks(ms.value * 1e-3)
+    # ---- phase breakdown / roofline: the same kernels driven from the host with a CUDA-event pair around every call ----
+    prof_steps = max(2, min(args.steps, 5)) if not args.profile_mode else 1
+    if resident:
+        for _ in range(2):
+            prof_sess.solve()
+    abi.lbfgs_b200_profile_enable(ctx, 1)
+    for ph in range(3):
+        abi.lbfgs_b200_profile_read(ctx, ph, None, None, 1)
+        abi.lbfgs_b200_profile_bytes(ctx, ph, C.byref(C.c_double()), 1)
+    barrier()
+    for _ in range(prof_steps):
+        prof_sess.solve()
+    barrier()
     phases = {}
     for ph, name in enumerate(("apply_Hv", "trial", "update")):
         tms, calls, nbytes = C.c_double(0), C.c_uint64(0), C.c_double(0)
@@ -294,7 +308,9 @@ def main():
                      "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes": "8*n*(4c+2) per call, c = pairs in the history at that call (SURVEY.md 8d)",
                      "calls": hv_phase["calls"], "full_history": hv_full},
-        "phase_ms_per_step": {k: v["ms"] / args.steps for k, v in phases.items()},
+        "phase_ms_per_step": {k: v["ms"] / prof_steps for k, v in phases.items()},
+        "solver_loop": "device-resident (one CUDA graph launch per minimize; conditional WHILE/IF nodes)" if resident else "host-driven",
+        "phase_source": "CUDA-event pairs around every call of a host-driven pass of the same kernels (%d solves)" % prof_steps,
         "phase_gb_per_s": {k: (v["alg_bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None) for k, v in phases.items()},
     }
 

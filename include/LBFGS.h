@@ -73,6 +73,36 @@ public:
     }
 };
 
+namespace detail {
+// objectives that can be run by the device-resident solve: they describe themselves as one of the library's kernels
+template <class Foo>
+class is_builtin_objective
+{
+    template <class F> static auto probe(int) -> decltype(std::declval<F&>().builtin_kind(), std::true_type());
+    template <class> static std::false_type probe(...);
+public:
+    static const bool value = decltype(probe<Foo>(0))::value;
+};
+template <template <class> class LS> struct line_search_id;
+template <> struct line_search_id<LineSearchBacktracking> { static const int value = LBFGS_B200_LS_BACKTRACKING; };
+template <> struct line_search_id<LineSearchBracketing> { static const int value = LBFGS_B200_LS_BRACKETING; };
+template <> struct line_search_id<LineSearchNocedalWright> { static const int value = LBFGS_B200_LS_NOCEDAL_WRIGHT; };
+template <> struct line_search_id<LineSearchMoreThuente> { static const int value = LBFGS_B200_LS_MORE_THUENTE; };
+template <class S> struct resident_abi;
+template <> struct resident_abi<double>
+{
+    static lbfgs_b200_status minimize(lbfgs_b200_solver* s, int obj, const double* d0, const double* d1, const lbfgs_b200_param* p, int ls,
+                                      double* x, double* tr, long long cap, lbfgs_b200_outcome* o)
+    { return lbfgs_b200_solver_minimize_f64(s, obj, d0, d1, p, ls, x, tr, cap, o); }
+};
+template <> struct resident_abi<float>
+{
+    static lbfgs_b200_status minimize(lbfgs_b200_solver* s, int obj, const float* d0, const float* d1, const lbfgs_b200_param* p, int ls,
+                                      float* x, double* tr, long long cap, lbfgs_b200_outcome* o)
+    { return lbfgs_b200_solver_minimize_f32(s, obj, d0, d1, p, ls, x, tr, cap, o); }
+};
+}  // namespace detail
+
 template <typename Scalar, template <class> class LineSearch = LineSearchNocedalWright>
 class LBFGSSolver
 {
@@ -87,6 +117,55 @@ private:
     LineSearchWorkspace<Scalar> m_ws;
     Scalar m_gnorm;
     long m_nfev;
+    // device-resident solve (built-in objectives): the whole minimize() is one CUDA graph launch
+    bool m_resident;
+    lbfgs_b200_solver* m_rsolver;
+    Device* m_rdev;
+    std::ptrdiff_t m_rn;
+    int m_rm;
+    double* m_trace;
+    long m_trace_cap;
+
+    template <typename Foo>
+    int minimize_resident(Foo& f, Vector& x, Scalar& fx)
+    {
+        Device& dev = x.device();
+        const std::ptrdiff_t n = x.size();
+        if (m_rsolver && (m_rdev != &dev || m_rn != n || m_rm != m_param.m))
+        {
+            lbfgs_b200_solver_destroy(m_rsolver);
+            m_rsolver = nullptr;
+        }
+        if (!m_rsolver)
+        {
+            dev.check(lbfgs_b200_solver_create(dev.ctx(), n, m_param.m, int(sizeof(Scalar)), &m_rsolver));
+            m_rdev = &dev; m_rn = n; m_rm = m_param.m;
+        }
+        lbfgs_b200_param p;
+        p.m = m_param.m; p.epsilon = m_param.epsilon; p.epsilon_rel = m_param.epsilon_rel; p.past = m_param.past; p.delta = m_param.delta;
+        p.max_iterations = m_param.max_iterations; p.linesearch = m_param.linesearch; p.max_linesearch = m_param.max_linesearch;
+        p.min_step = m_param.min_step; p.max_step = m_param.max_step; p.ftol = m_param.ftol; p.wolfe = m_param.wolfe;
+        lbfgs_b200_outcome out;
+        dev.check(detail::resident_abi<Scalar>::minimize(m_rsolver, f.builtin_kind(), f.builtin_data0(), f.builtin_data1(), &p,
+                                                         detail::line_search_id<LineSearch>::value, x.data(), m_trace, m_trace_cap, &out));
+        f.add_calls(long(out.nfev));
+        m_nfev = long(out.nfev);
+        m_grad.resize(n);
+        dev.check(lbfgs_b200_memcpy_d2d(dev.ctx(), m_grad.data(), lbfgs_b200_solver_final_grad(m_rsolver), sizeof(Scalar) * size_t(n)));
+        if (out.status != 0) ls_throw(out.status);   // the exception the line search would have thrown on the host
+        fx = Scalar(out.fx);
+        m_gnorm = Scalar(out.gnorm);
+        return out.niter;
+    }
+    template <typename Foo>
+    typename std::enable_if<detail::is_builtin_objective<Foo>::value, bool>::type try_resident(Foo& f, Vector& x, Scalar& fx, int& niter)
+    {
+        if (!m_resident || m_param.past > 64) return false;
+        niter = minimize_resident(f, x, fx);
+        return true;
+    }
+    template <typename Foo>
+    typename std::enable_if<!detail::is_builtin_objective<Foo>::value, bool>::type try_resident(Foo&, Vector&, Scalar&, int&) { return false; }
 
     bool small_gradient(Scalar gg, Scalar xx)
     {
@@ -95,7 +174,19 @@ private:
     }
 
 public:
-    LBFGSSolver(const LBFGSParam<Scalar>& param) : m_param(param), m_gnorm(0), m_nfev(0) { m_param.check_param(); }
+    LBFGSSolver(const LBFGSParam<Scalar>& param) :
+        m_param(param), m_gnorm(0), m_nfev(0), m_resident(true), m_rsolver(nullptr), m_rdev(nullptr), m_rn(0), m_rm(0), m_trace(nullptr),
+        m_trace_cap(0)
+    {
+        m_param.check_param();
+    }
+    ~LBFGSSolver() { lbfgs_b200_solver_destroy(m_rsolver); }
+
+    // Built-in objectives are minimised by the device-resident solve by default (one CUDA graph launch, no host round trips,
+    // results bit-identical to the host-driven loop below); false selects the host-driven loop for them as well.
+    void set_device_resident(bool on) { m_resident = on; }
+    // resident solve only: record f of every evaluation into a host buffer (tests)
+    void set_trace_buffer(double* host, long cap) { m_trace = host; m_trace_cap = cap; }
 
     // apply_Hv implementation selector (LBFGS_B200_HV_*); not part of the reference API
     void set_hv_algorithm(int algo) { m_bfgs.set_algorithm(algo); }
@@ -109,6 +200,10 @@ public:
         Device& dev = x.device();
         const std::ptrdiff_t n = x.size();
         const int fpast = m_param.past;
+        {
+            int niter_resident = 0;
+            if (try_resident(f, x, fx, niter_resident)) return niter_resident;
+        }
 
         m_bfgs.reset(dev, n, m_param.m);
         for (Vector* v : {&m_xp, &m_grad, &m_gradp, &m_drt, &m_ws.x_lo, &m_ws.grad_lo})

@@ -31,6 +31,11 @@ public:
         m_kind(kind), m_data0(data0), m_data1(data1), m_ncalls(0) {}
 
     long ncalls() const { return m_ncalls; }
+    // descriptor used by the device-resident solve (LBFGSSolver picks it when these members exist)
+    int builtin_kind() const { return m_kind; }
+    const Scalar* builtin_data0() const { return m_data0; }
+    const Scalar* builtin_data1() const { return m_data1; }
+    void add_calls(long k) { m_ncalls += k; }
 
     Scalar operator()(const Vector& x, Vector& grad)
     {

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstddef>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <stdexcept>
 #include <string>
@@ -64,13 +65,23 @@ public:
         static std::shared_ptr<Device> dev;
         return dev;
     }
+    static std::mutex& default_mutex()
+    {
+        static std::mutex m;
+        return m;
+    }
     static Device& get_default()
     {
+        std::lock_guard<std::mutex> lock(default_mutex());   // solver objects may be constructed from several host threads
         std::shared_ptr<Device>& slot = default_slot();
         if (!slot) slot = std::make_shared<Device>(0);
         return *slot;
     }
-    static void set_default(const std::shared_ptr<Device>& dev) { default_slot() = dev; }
+    static void set_default(const std::shared_ptr<Device>& dev)
+    {
+        std::lock_guard<std::mutex> lock(default_mutex());
+        default_slot() = dev;
+    }
 };
 
 namespace detail {

@@ -226,6 +226,43 @@ void* lbfgs_b200_box_vector(lbfgs_b200_box* b, int which);               /* LBFG
 LBFGS_B200_DECLARE_BOX(double, f64)
 LBFGS_B200_DECLARE_BOX(float, f32)
 
+/* ---------------------------------------------------------------- device-resident solve (built-in objectives)
+ * LBFGSSolver<Scalar, LineSearch>::minimize() (reference LBFGS.h:78-173) as ONE CUDA graph launch: line-search state machine
+ * (the cores of include/LBFGSpp/LineSearchCore.h), convergence tests, curvature gate and buffer rotation all run on the
+ * device; conditional WHILE/IF graph nodes carry the control flow; the host is not involved between launch and completion.
+ * Same kernels bodies, grids and reduction orders as the host-driven entry points: results are bit-identical to them.
+ * When n is sharded the in-kernel NVLink exchange must be attached (lbfgs_b200_comm_p2p_*). */
+typedef struct lbfgs_b200_solver lbfgs_b200_solver;
+typedef struct {             /* LBFGSParam (reference Param.h:67-219); doubles for both precisions */
+    int m;
+    double epsilon, epsilon_rel;
+    int past;
+    double delta;
+    int max_iterations;
+    int linesearch;
+    int max_linesearch;
+    double min_step, max_step, ftol, wolfe;
+} lbfgs_b200_param;
+typedef struct {
+    int status;              /* 0, or a LBFGSpp::LineSearchError code (>= 16) = the exception the reference would throw */
+    int niter;               /* return value of minimize()                                                          */
+    long long nfev;          /* objective evaluations                                                               */
+    double fx, gnorm;
+} lbfgs_b200_outcome;
+enum { LBFGS_B200_LS_BACKTRACKING = 0, LBFGS_B200_LS_BRACKETING = 1, LBFGS_B200_LS_NOCEDAL_WRIGHT = 2, LBFGS_B200_LS_MORE_THUENTE = 3 };
+
+lbfgs_b200_status lbfgs_b200_solver_create(lbfgs_b200_ctx* ctx, int64_t n, int m, int elem_bytes, lbfgs_b200_solver** out);
+void lbfgs_b200_solver_destroy(lbfgs_b200_solver* s);
+const void* lbfgs_b200_solver_final_grad(const lbfgs_b200_solver* s);   /* device pointer, valid until the next minimize */
+lbfgs_b200_hist* lbfgs_b200_solver_history(lbfgs_b200_solver* s);       /* the S/Y ring the solver owns                  */
+/* x_inout: device vector (start point in, solution out).  trace_host (optional): f of every evaluation. */
+lbfgs_b200_status lbfgs_b200_solver_minimize_f64(lbfgs_b200_solver* s, int objective, const double* data0, const double* data1,
+                                                 const lbfgs_b200_param* prm, int line_search, double* x_inout,
+                                                 double* trace_host, long long trace_cap, lbfgs_b200_outcome* out);
+lbfgs_b200_status lbfgs_b200_solver_minimize_f32(lbfgs_b200_solver* s, int objective, const float* data0, const float* data1,
+                                                 const lbfgs_b200_param* prm, int line_search, float* x_inout,
+                                                 double* trace_host, long long trace_cap, lbfgs_b200_outcome* out);
+
 #ifdef __cplusplus
 }
 #endif

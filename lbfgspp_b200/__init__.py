@@ -144,7 +144,7 @@ def driver():
                                              C.POINTER(_DrvResult)]
     lib.lbfgsb200_drv_session_create.restype = C.c_void_p
     lib.lbfgsb200_drv_session_create.argtypes = [C.c_int, C.c_int, dp, dp, C.c_long, C.c_int, C.POINTER(_DrvParam), C.c_int, dp,
-                                                 C.c_char_p, C.c_int]
+                                                 C.c_char_p, C.c_int, C.c_int]
     lib.lbfgsb200_drv_session_destroy.argtypes = [C.c_void_p]
     lib.lbfgsb200_drv_session_destroy.restype = None
     lib.lbfgsb200_drv_session_solve.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(_DrvResult)]
@@ -225,13 +225,13 @@ class LBFGSSolver:
     """
 
     def __init__(self, param=None, linesearch="NocedalWright", dtype=np.float64, device=0, hv_algo=HV_AUTO,
-                 fused=True):
+                 fused=True, resident=False):
         self.param = param if param is not None else LBFGSParam()
         self.ls = LINE_SEARCHES[linesearch] if isinstance(linesearch, str) else int(linesearch)
         self.dtype = np.dtype(dtype)
         self.device = device
         self.hv_algo = hv_algo
-        self.fused = fused
+        self.fused = 2 if resident else fused   # 2: device-resident solve (one CUDA graph launch per minimize)
 
     def minimize(self, objective, x0, data0=None, data1=None, trace_cap=100000, raise_errors=False, want_grad=True):
         drv = driver()
@@ -456,7 +456,8 @@ class History:
 class Session:
     """A solver and its vectors kept resident on one GPU (bench.py): solve() repeats the same problem."""
 
-    def __init__(self, objective, x0, param, linesearch="MoreThuente", device=0, hv_algo=HV_AUTO, data0=None, data1=None):
+    def __init__(self, objective, x0, param, linesearch="MoreThuente", device=0, hv_algo=HV_AUTO, data0=None, data1=None,
+                 resident=True):
         self.drv = driver()
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
         self.n = x0.size
@@ -468,7 +469,7 @@ class Session:
         p = param._c()
         ls = LINE_SEARCHES[linesearch] if isinstance(linesearch, str) else int(linesearch)
         self.h = self.drv.lbfgsb200_drv_session_create(device, objective, ptr(d0), ptr(d1), self.n, ls, C.byref(p), hv_algo,
-                                                       ptr(x0), err, 256)
+                                                       ptr(x0), err, 256, int(resident))
         if not self.h:
             raise RuntimeError("session_create failed: " + err.value.decode())
 

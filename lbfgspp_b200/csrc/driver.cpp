@@ -193,6 +193,59 @@ void solve_ls(int ls, Device& dev, Objective& obj, const drv_param* q, int hv_al
     }
 }
 
+template <class Scalar, template <class> class LS>
+void solve_resident_with(Device& dev, BuiltinObjective<Scalar>& obj, const drv_param* q, long n, Scalar* x_host, Scalar* grad_host,
+                         double* trace, long cap, drv_result* out, double t_begin, long h2d_extra)
+{
+    typedef DeviceVector<Scalar> Vector;
+    const LBFGSParam<Scalar> prm = to_param<Scalar>(q);
+    LBFGSSolver<Scalar, LS> solver(prm);
+    solver.set_device_resident(true);
+    solver.set_trace_buffer(trace, cap);
+    Vector x(dev);
+    x.copy_from_host(x_host, n);
+    Scalar fx = Scalar(0);
+    const unsigned long long launches0 = lbfgs_b200_launch_count(dev.ctx());
+    const double t0 = now();
+    int niter = 0;
+    try { niter = solver.minimize(obj, x, fx); }
+    catch (...)
+    {
+        out->nfev = solver.num_evaluations();
+        out->trace_len = out->nfev < cap ? out->nfev : cap;
+        x.copy_to_host(x_host);
+        throw;
+    }
+    dev.synchronize();
+    const double t1 = now();
+    x.copy_to_host(x_host);
+    if (grad_host) solver.final_grad().copy_to_host(grad_host);
+    out->niter = niter;
+    out->fx = double(fx);
+    out->gnorm = double(solver.final_grad_norm());
+    out->nfev = solver.num_evaluations();
+    out->trace_len = out->nfev < cap ? out->nfev : cap;
+    out->seconds = t1 - t0;
+    out->seconds_e2e = now() - t_begin;
+    out->launches = lbfgs_b200_launch_count(dev.ctx()) - launches0;
+    out->h2d_bytes = long(sizeof(Scalar)) * n + h2d_extra;
+    out->d2h_bytes = long(sizeof(Scalar)) * n * (grad_host ? 2 : 1);
+}
+
+template <class Scalar>
+void solve_resident(int ls, Device& dev, BuiltinObjective<Scalar>& obj, const drv_param* q, long n, Scalar* x_host, Scalar* grad_host,
+                    double* trace, long cap, drv_result* out, double t_begin, long h2d_extra)
+{
+    switch (ls)
+    {
+    case DRV_LS_BACKTRACKING: solve_resident_with<Scalar, LineSearchBacktracking>(dev, obj, q, n, x_host, grad_host, trace, cap, out, t_begin, h2d_extra); break;
+    case DRV_LS_BRACKETING: solve_resident_with<Scalar, LineSearchBracketing>(dev, obj, q, n, x_host, grad_host, trace, cap, out, t_begin, h2d_extra); break;
+    case DRV_LS_NOCEDAL_WRIGHT: solve_resident_with<Scalar, LineSearchNocedalWright>(dev, obj, q, n, x_host, grad_host, trace, cap, out, t_begin, h2d_extra); break;
+    case DRV_LS_MORE_THUENTE: solve_resident_with<Scalar, LineSearchMoreThuente>(dev, obj, q, n, x_host, grad_host, trace, cap, out, t_begin, h2d_extra); break;
+    default: throw std::invalid_argument("unknown line search id");
+    }
+}
+
 template <class Scalar>
 int lbfgs_any(int dev_ordinal, int objective, const Scalar* data0_host, const Scalar* data1_host, long n, int ls,
               const drv_param* q, int hv_algo, int fused, Scalar* x_host, Scalar* grad_host, double* trace, long cap,
@@ -205,7 +258,12 @@ int lbfgs_any(int dev_ordinal, int objective, const Scalar* data0_host, const Sc
         long extra = 0;
         if (data0_host) { d0.copy_from_host(data0_host, n); extra += long(sizeof(Scalar)) * n; }
         if (data1_host) { d1.copy_from_host(data1_host, n); extra += long(sizeof(Scalar)) * n; }
-        if (fused)
+        if (fused == 2)   // device-resident solve: the objective must stay visible as a built-in (no tracing wrapper)
+        {
+            BuiltinObjective<Scalar> obj(objective, d0.data(), d1.data());
+            solve_resident<Scalar>(ls, dev, obj, q, n, x_host, grad_host, trace, cap, out, t_begin, extra);
+        }
+        else if (fused)
         {
             BuiltinObjective<Scalar> obj(objective, d0.data(), d1.data());
             solve_ls<Scalar, BuiltinObjective<Scalar>, true>(ls, dev, obj, q, hv_algo, n, x_host, grad_host, trace, cap, out, t_begin, extra);
@@ -280,7 +338,8 @@ extern "C" {
 
 // x0_host (n) is uploaded once and kept on the device; data0/data1 (n each, optional) likewise.
 void* lbfgsb200_drv_session_create(int device_ordinal, int objective, const double* data0_host, const double* data1_host,
-                                   long n, int ls, const drv_param* prm, int hv_algo, const double* x0_host, char* err, int errlen)
+                                   long n, int ls, const drv_param* prm, int hv_algo, const double* x0_host, char* err, int errlen,
+                                   int resident)
 {
     try
     {
@@ -301,6 +360,10 @@ void* lbfgsb200_drv_session_create(int device_ordinal, int objective, const doub
         s->s_br.set_hv_algorithm(hv_algo);
         s->s_nw.set_hv_algorithm(hv_algo);
         s->s_mt.set_hv_algorithm(hv_algo);
+        s->s_bt.set_device_resident(resident != 0);
+        s->s_br.set_device_resident(resident != 0);
+        s->s_nw.set_device_resident(resident != 0);
+        s->s_mt.set_device_resident(resident != 0);
         return s.release();
     }
     catch (const std::exception& e)

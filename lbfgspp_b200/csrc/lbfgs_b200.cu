@@ -286,9 +286,10 @@ __global__ void __launch_bounds__(kThreads) k_dots(int64_t n, const T* __restric
 // fused line-search trial  (x = xp + step*d ; g = grad f(x) ; {f, g.d, g.g, x.x})
 //   TRIAL = false: plain objective evaluation at x (no xp/d, no x store), reduces {f, -, g.g, x.x}
 // =====================================================================================================
+// body shared by the stand-alone kernel and the device-resident solve; returns true in the last CTA once result[0..4) is final
 template <class T, class OBJ, bool TRIAL, bool VEC>
-__global__ void __launch_bounds__(kThreads) k_trial(OBJ obj, int64_t n, const T* __restrict__ xp, const T* __restrict__ d,
-                                                    T step, T* __restrict__ x, T* __restrict__ g, ReduceBuf rb)
+__device__ __forceinline__ bool trial_body(const OBJ& obj, int64_t n, const T* __restrict__ xp, const T* __restrict__ d,
+                                           T step, T* __restrict__ x, T* __restrict__ g, const ReduceBuf& rb)
 {
     T acc[4] = {T(0), T(0), T(0), T(0)};
     const int64_t packs = (n + 3) >> 2, stride = (int64_t)gridDim.x * kThreads;
@@ -336,7 +337,14 @@ __global__ void __launch_bounds__(kThreads) k_trial(OBJ obj, int64_t n, const T*
         store4<T, Hint::Plain, VEC>(g, i0, cnt, pg);
     }
     double dacc[4] = {(double)acc[0], (double)acc[1], (double)acc[2], (double)acc[3]};
-    grid_reduce<4>(dacc, rb);
+    return grid_reduce<4>(dacc, rb);
+}
+
+template <class T, class OBJ, bool TRIAL, bool VEC>
+__global__ void __launch_bounds__(kThreads) k_trial(OBJ obj, int64_t n, const T* __restrict__ xp, const T* __restrict__ d,
+                                                    T step, T* __restrict__ x, T* __restrict__ g, ReduceBuf rb)
+{
+    trial_body<T, OBJ, TRIAL, VEC>(obj, n, xp, d, step, x, g, rb);
 }
 
 // =====================================================================================================
@@ -376,9 +384,9 @@ struct lbfgs_b200_hist
 
 // s = x - xp ; y = g - gp -> slot ; {s.y, y.y}
 template <class T, bool VEC>
-__global__ void __launch_bounds__(kThreads) k_update(int64_t n, const T* __restrict__ x, const T* __restrict__ xp,
-                                                     const T* __restrict__ g, const T* __restrict__ gp,
-                                                     T* __restrict__ s_out, T* __restrict__ y_out, ReduceBuf rb)
+__device__ __forceinline__ bool update_body(int64_t n, const T* __restrict__ x, const T* __restrict__ xp,
+                                            const T* __restrict__ g, const T* __restrict__ gp,
+                                            T* __restrict__ s_out, T* __restrict__ y_out, const ReduceBuf& rb)
 {
     T acc[2] = {T(0), T(0)};
     const int64_t packs = (n + 3) >> 2, stride = (int64_t)gridDim.x * kThreads;
@@ -402,7 +410,15 @@ __global__ void __launch_bounds__(kThreads) k_update(int64_t n, const T* __restr
         store4<T, Hint::Plain, VEC>(y_out, i0, cnt, y);
     }
     double dacc[2] = {(double)acc[0], (double)acc[1]};
-    grid_reduce<2>(dacc, rb);
+    return grid_reduce<2>(dacc, rb);
+}
+
+template <class T, bool VEC>
+__global__ void __launch_bounds__(kThreads) k_update(int64_t n, const T* __restrict__ x, const T* __restrict__ xp,
+                                                     const T* __restrict__ g, const T* __restrict__ gp,
+                                                     T* __restrict__ s_out, T* __restrict__ y_out, ReduceBuf rb)
+{
+    update_body<T, VEC>(n, x, xp, g, gp, s_out, y_out, rb);
 }
 
 // {s.y, y.y} of an explicitly given pair while copying it into the slot (BFGSMat::add_correction)
@@ -1133,6 +1149,8 @@ template <class T> static GramSolveArgs<T> make_solve_args(lbfgs_b200_hist* h, T
     g.SS_out = static_cast<T*>(h->SS[out]);
     g.ys = static_cast<const T*>(h->ys); g.alpha = static_cast<T*>(h->alpha);
     g.theta = static_cast<const T*>(h->theta);
+    g.ov_slot = -1;
+    g.ov_theta_on = 0;
     fill_slots<T>(h, g.slots);
     return g;
 }
@@ -1344,3 +1362,4 @@ DEFINE_HIST(float, f32)
 
 }  // extern "C"
 #include "lbfgsb_impl.cuh"
+#include "resident.cuh"

@@ -99,7 +99,7 @@ __device__ __forceinline__ Pack<float> lds_pack(const float* p, int)
 }
 
 template <class T, int ROUNDS>
-__global__ void __launch_bounds__(kGramMaxThreads, 1) k_gram_dots(GramDotsArgs<T> a, double* partials, unsigned* ticket, double* result, const XComm* xc, unsigned long long epoch)
+__device__ __forceinline__ void gram_dots_body(const GramDotsArgs<T>& a, double* partials, unsigned* ticket, double* result, const XComm* xc, unsigned long long epoch)
 {
     extern __shared__ __align__(128) unsigned char gram_smem[];
     T* tiles = reinterpret_cast<T*>(gram_smem);                  // [stage][3][TE]
@@ -300,6 +300,12 @@ __global__ void __launch_bounds__(kGramMaxThreads, 1) k_gram_dots(GramDotsArgs<T
     }
 }
 
+template <class T, int ROUNDS>
+__global__ void __launch_bounds__(kGramMaxThreads, 1) k_gram_dots(GramDotsArgs<T> a, double* partials, unsigned* ticket, double* result, const XComm* xc, unsigned long long epoch)
+{
+    gram_dots_body<T, ROUNDS>(a, partials, ticket, result, xc, epoch);
+}
+
 // ---- the O(c^2) recursion on coefficients ---------------------------------------------------------------------
 // Runs in shared memory in the prologue of EVERY CTA of the combine kernel (identical arithmetic everywhere, ~2 us,
 // no extra launch); CTA 0 also writes the folded Gram matrices and the alphas back for the next call.
@@ -317,6 +323,11 @@ template <class T> struct GramSolveArgs
     const T* ys;             // [M]
     T* alpha;                // [M]
     const T* theta;
+    // overrides used by the device-resident solve, where the newest pair's ys / theta are committed only after this kernel:
+    int ov_slot;             // physical slot whose ys is `ov_ys` (-1: none)
+    T ov_ys;
+    int ov_theta_on;
+    T ov_theta;
     unsigned char slots[kMaxM];
 };
 
@@ -357,13 +368,14 @@ __device__ void gram_solve_in_smem(const GramSolveArgs<T>& g, T* sm, bool writer
     __syncthreads();
     if (tid == 0 && g.with_v)
     {
-        const T theta = *g.theta;
+        const T theta = g.ov_theta_on ? g.ov_theta : *g.theta;
+        auto ys_of = [&](int i) { return (g.slots[i] == g.ov_slot) ? g.ov_ys : g.ys[g.slots[i]]; };
         // backward sweep (BFGSMat.h:285-290): alpha_i = s_i'q / ys_i with q = a*v - sum_{newer t} alpha_t y_t
         for (int i = 0; i < c; i++)
         {
             T sq = g.a * (T)g.raw[i * kGramVals + 0];
             for (int t = 0; t < i; t++) sq -= al[t] * sSY[i * c + t];
-            al[i] = sq / g.ys[g.slots[i]];
+            al[i] = sq / ys_of(i);
         }
         // forward sweep (BFGSMat.h:293-301): r = q/theta + sum_{older t} (alpha_t - beta_t) s_t ; beta_i = y_i'r / ys_i
         T* cs = coef + 1 + c;
@@ -373,7 +385,7 @@ __device__ void gram_solve_in_smem(const GramSolveArgs<T>& g, T* sm, bool writer
             for (int t = 0; t < c; t++) yq -= al[t] * sYY[i * c + t];
             T yr = yq / theta;
             for (int t = c - 1; t > i; t--) yr += cs[t] * sSY[t * c + i];
-            const T beta = yr / g.ys[g.slots[i]];
+            const T beta = yr / ys_of(i);
             cs[i] = al[i] - beta;
         }
         coef[0] = g.a / theta;
@@ -403,8 +415,9 @@ template <class T> struct GramCombineArgs
     GramSolveArgs<T> solve;
 };
 
+// returns true in the last CTA (after the optional v.res reduction); the stand-alone kernel ignores it
 template <class T, bool VEC>
-__global__ void __launch_bounds__(kThreads) k_gram_combine(GramCombineArgs<T> a, ReduceBuf rb)
+__device__ __forceinline__ bool gram_combine_body(const GramCombineArgs<T>& a, const ReduceBuf& rb)
 {
     extern __shared__ __align__(16) unsigned char comb_smem[];
     T* sm = reinterpret_cast<T*>(comb_smem);
@@ -459,8 +472,15 @@ __global__ void __launch_bounds__(kThreads) k_gram_combine(GramCombineArgs<T> a,
     if (a.want_dot)
     {
         double dacc[1] = {(double)dot};
-        grid_reduce<1>(dacc, rb);
+        return grid_reduce<1>(dacc, rb);
     }
+    return false;
+}
+
+template <class T, bool VEC>
+__global__ void __launch_bounds__(kThreads) k_gram_combine(GramCombineArgs<T> a, ReduceBuf rb)
+{
+    gram_combine_body<T, VEC>(a, rb);
 }
 
 }  // namespace lb
