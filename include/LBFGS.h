@@ -150,6 +150,7 @@ private:
                                                          detail::line_search_id<LineSearch>::value, x.data(), m_trace, m_trace_cap, &out));
         f.add_calls(long(out.nfev));
         m_nfev = long(out.nfev);
+        if (!m_grad.is_bound_to(dev)) m_grad = Vector(dev);
         m_grad.resize(n);
         dev.check(lbfgs_b200_memcpy_d2d(dev.ctx(), m_grad.data(), lbfgs_b200_solver_final_grad(m_rsolver), sizeof(Scalar) * size_t(n)));
         if (out.status != 0) ls_throw(out.status);   // the exception the line search would have thrown on the host
@@ -208,7 +209,7 @@ public:
         m_bfgs.reset(dev, n, m_param.m);
         for (Vector* v : {&m_xp, &m_grad, &m_gradp, &m_drt, &m_ws.x_lo, &m_ws.grad_lo})
         {
-            if (&v->device() != &dev) *v = Vector(dev);
+            if (!v->is_bound_to(dev)) *v = Vector(dev);
             v->resize(n);
         }
         if (fpast > 0) m_fx.assign(size_t(fpast), Scalar(0));

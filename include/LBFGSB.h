@@ -73,7 +73,7 @@ public:
         m_bfgs.refresh_middle();
         for (Vector* v : {&m_xp, &m_grad, &m_gradp, &m_drt, &m_ws.x_lo, &m_ws.grad_lo})
         {
-            if (&v->device() != &dev) *v = Vector(dev);
+            if (!v->is_bound_to(dev)) *v = Vector(dev);
             v->resize(n);
         }
         if (fpast > 0) m_fx.assign(size_t(fpast), Scalar(0));

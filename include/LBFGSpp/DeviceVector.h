@@ -148,9 +148,14 @@ class DeviceVector
     std::ptrdiff_t m_size;
     std::ptrdiff_t m_capacity;
 
+    Device& bound()
+    {
+        if (!m_dev) m_dev = &Device::get_default();
+        return *m_dev;
+    }
     void release()
     {
-        if (m_ptr) lbfgs_b200_free(m_dev->ctx(), m_ptr);
+        if (m_ptr && m_dev) lbfgs_b200_free(m_dev->ctx(), m_ptr);
         m_ptr = nullptr;
         m_size = m_capacity = 0;
     }
@@ -159,7 +164,9 @@ public:
     typedef Scalar value_type;
     typedef std::ptrdiff_t Index;
 
-    DeviceVector() : m_dev(&Device::get_default()), m_ptr(nullptr), m_size(0), m_capacity(0) {}
+    // A default-constructed vector is not bound to a device yet: it binds to the process-wide default device on first use
+    // (or to another vector's device on assignment), so that solver objects can be created without touching a GPU.
+    DeviceVector() : m_dev(nullptr), m_ptr(nullptr), m_size(0), m_capacity(0) {}
     explicit DeviceVector(Index n) : m_dev(&Device::get_default()), m_ptr(nullptr), m_size(0), m_capacity(0) { resize(n); }
     DeviceVector(Device& dev, Index n) : m_dev(&dev), m_ptr(nullptr), m_size(0), m_capacity(0) { resize(n); }
     explicit DeviceVector(Device& dev) : m_dev(&dev), m_ptr(nullptr), m_size(0), m_capacity(0) {}
@@ -186,7 +193,8 @@ public:
         return *this;
     }
 
-    Device& device() const { return *m_dev; }
+    Device& device() const { return m_dev ? *m_dev : Device::get_default(); }
+    bool is_bound_to(const Device& dev) const { return m_dev == &dev; }
     Index size() const { return m_size; }
     Scalar* data() { return m_ptr; }
     const Scalar* data() const { return m_ptr; }
@@ -199,7 +207,7 @@ public:
         {
             release();
             void* p = nullptr;
-            m_dev->check(lbfgs_b200_malloc(m_dev->ctx(), &p, sizeof(Scalar) * size_t(n)));
+            bound().check(lbfgs_b200_malloc(m_dev->ctx(), &p, sizeof(Scalar) * size_t(n)));
             m_ptr = static_cast<Scalar*>(p);
             m_capacity = n;
         }

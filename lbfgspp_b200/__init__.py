@@ -47,7 +47,7 @@ def _load(name):
         if not os.path.exists(path):
             raise NativeLibraryMissing(
                 "%s is not built; run `python -m lbfgspp_b200.build` (there is no CPU fallback)" % path)
-        _libs[name] = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        _libs[name] = C.CDLL(path)   # RTLD_LOCAL: nothing here may interpose with other loaded libraries
     return _libs[name]
 
 

@@ -53,7 +53,8 @@ def build_driver(force=False):
     srcs = _sources(CSRC, os.path.join(ROOT, "include"))
     if not force and _newer(DRV, srcs + [LIB]):
         return DRV
-    cmd = [CXX, "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-o", DRV, os.path.join(CSRC, "driver.cpp"),
+    cmd = [CXX, "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-fvisibility=hidden", "-fvisibility-inlines-hidden",
+           "-Wl,-Bsymbolic", "-o", DRV, os.path.join(CSRC, "driver.cpp"),
            "-L", PKG, "-l:liblbfgs_b200.so", "-Wl,-rpath,$ORIGIN", "-pthread"]
     subprocess.run(cmd, check=True)
     return DRV

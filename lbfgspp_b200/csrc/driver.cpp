@@ -16,6 +16,7 @@
 
 using namespace LBFGSpp;
 
+#pragma GCC visibility push(default)
 extern "C" {
 
 typedef struct
@@ -682,3 +683,5 @@ extern "C" int lbfgsb200_drv_dense_f64(int device_ordinal, long n, int m, int np
         return 1;
     }
 }
+
+#pragma GCC visibility pop

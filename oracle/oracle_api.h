@@ -11,6 +11,11 @@
 #ifndef LBFGS_ORACLE_API_H
 #define LBFGS_ORACLE_API_H
 
+/* Both checker libraries are built with -fvisibility=hidden -Wl,-Bsymbolic: only this C API is exported, and their internal
+ * C++ symbols (namespace LBFGSpp of the reference, namespace orc) can never interpose with, or be interposed by, the product's
+ * libraries when a test process loads several of them. */
+#define ORC_API __attribute__((visibility("default")))
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -57,24 +62,24 @@ typedef struct {
 } orc_result;
 
 #define ORC_DECLARE(P)                                                                                         \
-    void P##default_param(orc_param* p, int lbfgsb);                                                           \
+    ORC_API void P##default_param(orc_param* p, int lbfgsb);                                                           \
     /* LBFGSSolver<double, LS>::minimize; x in/out (n), grad_out (n) = final_grad() or NULL */                 \
-    int P##lbfgs_f64(int objective, const double* data0, const double* data1, long n, int ls,                  \
+    ORC_API int P##lbfgs_f64(int objective, const double* data0, const double* data1, long n, int ls,                  \
                      const orc_param* prm, int sum_mode, double* x, double* grad_out, double* fx_trace,        \
                      long trace_cap, orc_result* out);                                                         \
-    int P##lbfgs_f32(int objective, const float* data0, const float* data1, long n, int ls,                    \
+    ORC_API int P##lbfgs_f32(int objective, const float* data0, const float* data1, long n, int ls,                    \
                      const orc_param* prm, int sum_mode, float* x, float* grad_out, double* fx_trace,          \
                      long trace_cap, orc_result* out);                                                         \
     /* LBFGSBSolver<double>::minimize (MoreThuente) */                                                         \
-    int P##lbfgsb_f64(int objective, const double* data0, const double* data1, long n, const orc_param* prm,   \
+    ORC_API int P##lbfgsb_f64(int objective, const double* data0, const double* data1, long n, const orc_param* prm,   \
                       int sum_mode, double* x, const double* lb, const double* ub, double* grad_out,           \
                       double* fx_trace, long trace_cap, orc_result* out);                                      \
     /* BFGSMat<double>: reset(n,m); add_correction(S[:,k], Y[:,k]) for k < npairs (column-major, ld = n);     \
        then res = a*H*v.  ys_out/theta_out optional (m values / 1 value). */                                   \
-    int P##bfgs_apply_Hv_f64(long n, int m, int npairs, const double* S, const double* Y, const double* v,     \
+    ORC_API int P##bfgs_apply_Hv_f64(long n, int m, int npairs, const double* S, const double* Y, const double* v,     \
                              double a, int sum_mode, double* res, double* ys_out, double* theta_out);          \
     /* evaluate an objective once: returns fx, writes grad */                                                  \
-    double P##objective_f64(int objective, const double* data0, const double* data1, long n, const double* x,  \
+    ORC_API double P##objective_f64(int objective, const double* data0, const double* data1, long n, const double* x,  \
                             double* grad);
 
 ORC_DECLARE(orc_)
@@ -82,13 +87,13 @@ ORC_DECLARE(ref_)
 
 /* restatement only: ONE line search from (xp, fx0 = f(xp), grad0 = f'(xp)) along drt with initial `step`, by the restated
  * ls_* function `ls`.  Outputs: accepted step, fx, dg, x (n), grad (n); returns ORC_* status; nfev / msg in `out`. */
-int orc_line_search_f64(int objective, const double* data0, const double* data1, long n, int ls, const orc_param* prm,
+ORC_API int orc_line_search_f64(int objective, const double* data0, const double* data1, long n, int ls, const orc_param* prm,
                         const double* xp, const double* drt, double step_max, double* step_inout, double* fx_out, double* dg_out,
                         double* x_out, double* grad_out, double* fx_trace, long trace_cap, orc_result* out);
 /* restatement only: repeated apply_Hv timing for the CPU baseline (returns seconds per call) */
-double orc_bfgs_apply_Hv_bench_f64(long n, int m, int reps, int sum_mode, int threads);
+ORC_API double orc_bfgs_apply_Hv_bench_f64(long n, int m, int reps, int sum_mode, int threads);
 /* restatement only: Gram-form (vector-free) two-loop used to study the fast GPU variant on CPU */
-int orc_lbfgs_gram_f64(int objective, const double* data0, const double* data1, long n, int ls,
+ORC_API int orc_lbfgs_gram_f64(int objective, const double* data0, const double* data1, long n, int ls,
                        const orc_param* prm, int sum_mode, double* x, double* grad_out, double* fx_trace,
                        long trace_cap, orc_result* out);
 

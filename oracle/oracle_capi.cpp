@@ -254,6 +254,6 @@ double orc_bfgs_apply_Hv_bench_f64(long n, int m, int reps, int sum_mode, int th
     return dt / reps;
 }
 
-int orc_hw_threads() { return hw_threads(); }
+ORC_API int orc_hw_threads() { return hw_threads(); }
 
 }  // extern "C"

@@ -17,7 +17,7 @@ SO = os.path.join(ROOT, "tests", "cpp", "core_harness.so")
 @pytest.fixture(scope="module")
 def harness():
     src = os.path.join(ROOT, "tests", "cpp", "core_harness.cpp")
-    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-march=x86-64-v3", "-fPIC", "-shared", "-Wall",
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-march=x86-64-v3", "-fPIC", "-shared", "-Wall", "-Wl,-Bsymbolic",
                     "-I", os.path.join(ROOT, "oracle"), "-o", SO, src], check=True)
     lib = C.CDLL(SO)
     dp = C.POINTER(C.c_double)
