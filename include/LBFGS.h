@@ -118,7 +118,7 @@ private:
     Scalar m_gnorm;
     long m_nfev;
     // device-resident solve (built-in objectives): the whole minimize() is one CUDA graph launch
-    bool m_resident;
+    int m_resident;   // -1 automatic, 0 host-driven loop, 1 device-resident solve
     lbfgs_b200_solver* m_rsolver;
     Device* m_rdev;
     std::ptrdiff_t m_rn;
@@ -161,7 +161,10 @@ private:
     template <typename Foo>
     typename std::enable_if<detail::is_builtin_objective<Foo>::value, bool>::type try_resident(Foo& f, Vector& x, Scalar& fx, int& niter)
     {
-        if (!m_resident || m_param.past > 64) return false;
+        // automatic: the graph's per-node latency (~3 us) beats host round trips for small and medium shards; for very long
+        // vectors both are noise next to the HBM time and the host-driven loop keeps the per-phase profiling hooks
+        const bool want = (m_resident == 1) || (m_resident == -1 && x.size() <= 4000000);
+        if (!want || m_param.past > 64) return false;
         niter = minimize_resident(f, x, fx);
         return true;
     }
@@ -176,16 +179,17 @@ private:
 
 public:
     LBFGSSolver(const LBFGSParam<Scalar>& param) :
-        m_param(param), m_gnorm(0), m_nfev(0), m_resident(true), m_rsolver(nullptr), m_rdev(nullptr), m_rn(0), m_rm(0), m_trace(nullptr),
+        m_param(param), m_gnorm(0), m_nfev(0), m_resident(-1), m_rsolver(nullptr), m_rdev(nullptr), m_rn(0), m_rm(0), m_trace(nullptr),
         m_trace_cap(0)
     {
         m_param.check_param();
     }
     ~LBFGSSolver() { lbfgs_b200_solver_destroy(m_rsolver); }
 
-    // Built-in objectives are minimised by the device-resident solve by default (one CUDA graph launch, no host round trips,
-    // results bit-identical to the host-driven loop below); false selects the host-driven loop for them as well.
-    void set_device_resident(bool on) { m_resident = on; }
+    // Built-in objectives can be minimised by the device-resident solve (one CUDA graph launch, no host round trips, results
+    // bit-identical to the host-driven loop below).  Default: automatic (resident up to n = 4e6 per GPU).
+    void set_device_resident(bool on) { m_resident = on ? 1 : 0; }
+    void set_device_resident_auto() { m_resident = -1; }
     // resident solve only: record f of every evaluation into a host buffer (tests)
     void set_trace_buffer(double* host, long cap) { m_trace = host; m_trace_cap = cap; }
 

@@ -8,7 +8,7 @@
 //   * convergence tests of LBFGS.h:137-154, the curvature gate of :161, the ring bookkeeping of BFGSMat.h:81-97
 //   * buffer rotation (x <-> xp, grad <-> gradp, x <-> x_lo ...) = pointer swaps inside the device state
 // and control flow is a CUDA graph with conditional nodes (CUDA 12.4+):
-//   first_eval -> begin -> WHILE(!finished){ iter_begin -> WHILE(line search){ trial } -> after_ls -> IF(continue){ update -> gram_dots -> gram_combine } }
+//   first_eval -> begin -> WHILE(!finished){ iter_begin -> WHILE(line search){ trial } -> after_ls(+update) -> gram_dots -> gram_combine }
 // Every conditional handle is set either by a kernel upstream of its node in the same graph or by a kernel of its own body.
 // Kernels take their operands from the device state (pointers rotate), so the instantiated graph is reused for every solve
 // of the same shape.  Arithmetic is the host-driven path's, kernel for kernel (same bodies, same grids, same split of the
@@ -102,7 +102,7 @@ template <class T> struct ResidentEnv
     DevSolve<T>* st;
     ReduceBuf rb;            // partials / ticket / result ; xc ; (epoch filled per launch from st->epoch)
     unsigned* aux_ticket;    // for kernels that do not reduce but need a "last CTA"
-    cudaGraphConditionalHandle h_outer, h_inner, h_cont;
+    cudaGraphConditionalHandle h_outer, h_inner;
     // history storage (fixed)
     T *S, *Y, *ys, *alpha, *theta;
     T *SY[2], *YY[2], *SS[2];
@@ -286,12 +286,15 @@ __global__ void __launch_bounds__(kThreads) kg_trial(ResidentEnv<T> env)
 }
 
 // ------------------------------------------------------------------------------------------------ after the line search
-// (optional restore of the start point) + convergence tests of LBFGS.h:130-154
+// One kernel: (optional restore of the start point) + the pair update s = x - xp, y = g - gp written speculatively into the free
+// ring slot with {s.y, y.y} -> st->gate (LBFGS.h:159-160, BFGSMat.h:85-92) + the convergence tests of LBFGS.h:130-154 in the
+// last CTA.  When the solve is over the pair is simply never committed.
 template <class T>
 __global__ void __launch_bounds__(kThreads) kg_after_ls(ResidentEnv<T> env)
 {
     DevSolve<T>* st = env.st;
-    if (st->need_restore)
+    const bool restore = st->need_restore != 0;
+    if (restore)
     {
         const T* xp = st->xp; const T* gp = st->gp;
         T* x = st->x; T* g = st->g;
@@ -301,7 +304,15 @@ __global__ void __launch_bounds__(kThreads) kg_after_ls(ResidentEnv<T> env)
             g[i] = gp[i];
         }
     }
-    if (!last_cta_arrives(env.aux_ticket) || threadIdx.x != 0) return;
+    const ReduceBuf rb = resident_rb(env, st->gate);
+    T* s_out = env.S + (int64_t)st->head * env.ld;
+    T* y_out = env.Y + (int64_t)st->head * env.ld;
+    // after a restore x == xp and g == gp: read the sources so that s = y = 0 without depending on the copy above
+    const T* xs = restore ? st->xp : st->x;
+    const T* gs = restore ? st->gp : st->g;
+    if (!update_body<T, true>(st->n, xs, st->xp, gs, st->gp, s_out, y_out, rb)) return;
+    if (threadIdx.x != 0) return;
+    if (rb.xc) st->epoch++;
     st->need_restore = 0;
     if (!st->finished)
     {
@@ -321,24 +332,10 @@ __global__ void __launch_bounds__(kThreads) kg_after_ls(ResidentEnv<T> env)
         }
         if (!st->finished && st->max_iterations != 0 && k >= st->max_iterations) { st->finished = 1; st->niter = k; }
     }
-    const unsigned cont = st->finished ? 0u : 1u;
-    cudaGraphSetConditional(env.h_cont, cont);
-    if (!cont) cudaGraphSetConditional(env.h_outer, 0u);
+    if (st->finished) cudaGraphSetConditional(env.h_outer, 0u);
 }
 
-// ------------------------------------------------------------------------------------------------ update + apply_Hv
-// s = x - xp, y = g - gp into the free slot; {s.y, y.y} -> st->gate  (LBFGS.h:159-160, BFGSMat.h:85-92)
-template <class T>
-__global__ void __launch_bounds__(kThreads) kg_update(ResidentEnv<T> env)
-{
-    DevSolve<T>* st = env.st;
-    const ReduceBuf rb = resident_rb(env, st->gate);
-    T* s_out = env.S + (int64_t)st->head * env.ld;
-    T* y_out = env.Y + (int64_t)st->head * env.ld;
-    if (!update_body<T, true>(st->n, st->x, st->xp, st->g, st->gp, s_out, y_out, rb)) return;
-    if (threadIdx.x == 0 && rb.xc) st->epoch++;
-}
-
+// ------------------------------------------------------------------------------------------------ apply_Hv
 // ring geometry after the curvature gate (LBFGS.h:161): every thread derives it from the state and {s.y, y.y}
 template <class T> struct Geometry
 {
@@ -362,6 +359,7 @@ template <class T, int ROUNDS>
 __global__ void __launch_bounds__(kGramMaxThreads, 1) kg_gram_dots(ResidentEnv<T> env)
 {
     DevSolve<T>* st = env.st;
+    if (st->finished) return;   // the solve ended in kg_after_ls: nothing to prepare
     const Geometry<T> q = gate_geometry(st);
     GramDotsArgs<T> a;
     a.n = st->n; a.ld = env.ld; a.v = st->g; a.S = env.S; a.Y = env.Y;
@@ -381,6 +379,7 @@ template <class T>
 __global__ void __launch_bounds__(kThreads) kg_gram_combine(ResidentEnv<T> env)
 {
     DevSolve<T>* st = env.st;
+    if (st->finished) return;
     const Geometry<T> q = gate_geometry(st);
     GramCombineArgs<T> a;
     a.n = st->n; a.ld = env.ld; a.v = st->g; a.S = env.S; a.Y = env.Y; a.res = st->drt; a.want_dot = 1;
@@ -449,10 +448,9 @@ static lbfgs_b200_status build_graph(lbfgs_b200_solver* s, const lb::ResidentEnv
     ResidentEnv<T> env = env_in;
     CU(ctx, cudaGraphConditionalHandleCreate(&env.h_outer, s->graph, 0, cudaGraphCondAssignDefault));
     CU(ctx, cudaGraphConditionalHandleCreate(&env.h_inner, s->graph, 0, cudaGraphCondAssignDefault));
-    CU(ctx, cudaGraphConditionalHandleCreate(&env.h_cont, s->graph, 0, cudaGraphCondAssignDefault));
 
     const int64_t n = s->n;
-    const int g_stream2 = grid_for(ctx, n, 2), g_stream1 = grid_for(ctx, n, 1), g_elem = grid_for(ctx, n * 4, 4);
+    const int g_stream2 = grid_for(ctx, n, 2), g_stream1 = grid_for(ctx, n, 1);
     void* args[] = {&env};
     auto kernel_node = [&](cudaGraph_t g, cudaGraphNode_t* node, const cudaGraphNode_t* deps, size_t ndeps, void* fn, int grid, int block,
                            size_t smem) -> cudaError_t {
@@ -470,17 +468,15 @@ static lbfgs_b200_status build_graph(lbfgs_b200_solver* s, const lb::ResidentEnv
         return e;
     };
 
-    cudaGraphNode_t n_first, n_begin, n_outer, n_iter, n_inner, n_trial, n_after, n_if, n_update, n_dots, n_combine;
-    cudaGraph_t g_outer, g_inner, g_if;
+    cudaGraphNode_t n_first, n_begin, n_outer, n_iter, n_inner, n_trial, n_after, n_dots, n_combine;
+    cudaGraph_t g_outer, g_inner;
     CU(ctx, kernel_node(s->graph, &n_first, nullptr, 0, (void*)kg_first_eval<T, OBJ>, g_stream2, kThreads, 0));
     CU(ctx, kernel_node(s->graph, &n_begin, &n_first, 1, (void*)kg_begin<T>, g_stream2, kThreads, 0));
     CU(ctx, cond_node(s->graph, &n_outer, &n_begin, 1, env.h_outer, cudaGraphCondTypeWhile, &g_outer));
     CU(ctx, kernel_node(g_outer, &n_iter, nullptr, 0, (void*)kg_iter_begin<T>, 1, 32, 0));
     CU(ctx, cond_node(g_outer, &n_inner, &n_iter, 1, env.h_inner, cudaGraphCondTypeWhile, &g_inner));
     CU(ctx, kernel_node(g_inner, &n_trial, nullptr, 0, (void*)kg_trial<T, OBJ>, g_stream2, kThreads, 0));
-    CU(ctx, kernel_node(g_outer, &n_after, &n_inner, 1, (void*)kg_after_ls<T>, g_elem, kThreads, 0));
-    CU(ctx, cond_node(g_outer, &n_if, &n_after, 1, env.h_cont, cudaGraphCondTypeIf, &g_if));
-    CU(ctx, kernel_node(g_if, &n_update, nullptr, 0, (void*)kg_update<T>, g_stream2, kThreads, 0));
+    CU(ctx, kernel_node(g_outer, &n_after, &n_inner, 1, (void*)kg_after_ls<T>, g_stream2, kThreads, 0));
     // Gram pass: launch geometry for the largest history (the kernel derives the actual one from the state)
     int split = 8;
     while (split > 1 && s->m * split > kGramMaxWarps) split >>= 1;
@@ -491,11 +487,11 @@ static lbfgs_b200_status build_graph(lbfgs_b200_solver* s, const lb::ResidentEnv
     const size_t smem_dots = (size_t)kGramStages * 3 * kGramTE * sizeof(T);
     void* dots_fn = rounds <= 1 ? (void*)kg_gram_dots<T, 1> : rounds == 2 ? (void*)kg_gram_dots<T, 2> : (void*)kg_gram_dots<T, 3>;
     CU(ctx, cudaFuncSetAttribute(dots_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dots));
-    CU(ctx, kernel_node(g_if, &n_dots, &n_update, 1, dots_fn, g_dots, kGramMaxThreads, smem_dots));
+    CU(ctx, kernel_node(g_outer, &n_dots, &n_after, 1, dots_fn, g_dots, kGramMaxThreads, smem_dots));
     const size_t smem_comb = gram_solve_smem_elems(s->m) * sizeof(T);
     if (smem_comb > 40 * 1024)
         CU(ctx, cudaFuncSetAttribute((void*)kg_gram_combine<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_comb));
-    CU(ctx, kernel_node(g_if, &n_combine, &n_dots, 1, (void*)kg_gram_combine<T>, g_stream1, kThreads, smem_comb));
+    CU(ctx, kernel_node(g_outer, &n_combine, &n_dots, 1, (void*)kg_gram_combine<T>, g_stream1, kThreads, smem_comb));
     CU(ctx, cudaGraphInstantiate(&s->exec, s->graph, 0));
     return LBFGS_B200_OK;
 }
