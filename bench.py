@@ -140,7 +140,7 @@ def main():
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: in-kernel all-reduce over NVLink peer memory (default) or one ncclAllReduce per reduction")
     ap.add_argument("--solver-loop", default="auto", choices=["auto", "resident", "host"],
-                    help="device-resident CUDA graph or host-driven loop (auto: resident for N >= 4, see DESIGN.md section 10)")
+                    help="device-resident CUDA graph or host-driven loop (auto = host-driven: at n = 1e7 the two are within noise, see DESIGN.md section 10)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-mode", action="store_true", help="timed region only (for runs under ncu; numbers are not bench values)")
     args = ap.parse_args()
@@ -195,7 +195,7 @@ def main():
 
     hv = {"auto": lb.HV_AUTO, "two_loop": lb.HV_TWO_LOOP, "gram": lb.HV_GRAM}[args.hv]
     prm = lb.LBFGSParam(m=M_HIST)
-    resident = (args.solver_loop == "resident" or (args.solver_loop == "auto" and world >= 4)) \
+    resident = (args.solver_loop == "resident") \
         and (world == 1 or args.comm == "p2p") and args.hv != "two_loop"
     sess = lb.Session(lb.OBJ_ROSENBROCK_PAIRED, np.zeros(n_local), prm, "MoreThuente", device=local_rank, hv_algo=hv, resident=resident)
     # per-phase CUDA events exist only on the host-driven path: a second session supplies the phase / roofline numbers
