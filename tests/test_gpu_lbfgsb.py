@@ -1,6 +1,6 @@
 """GPU parity tests for the bound-constrained solver (BASELINE config 4) against the reference headers' outputs:
-the frozen golden vectors (tests/golden/lbfgs_ref.json, kind "lbfgsb") everywhere, and live runs of oracle/_ref where
-that build travelled with the repo.  Parity: same iteration count, evaluation count within +-1 on the short runs (the
+the frozen golden vectors (tests/golden/lbfgs_ref.json, kind "lbfgsb"), and live runs of the restatement
+(oracle/lbfgsb_oracle.hpp, pinned bit for bit to oracle/_ref by tests/test_oracle_cpu.py).  Parity: same iteration count, evaluation count within +-1 on the short runs (the
 Cauchy sweep and the BOXCQP solves re-associate sums), |fx - fx_ref| <= 1e-9 max(1,|fx_ref|), |x - x_ref|_inf <= 1e-6."""
 import numpy as np
 import pytest
@@ -32,15 +32,15 @@ def test_lbfgsb_golden_vectors(case):
 
 @pytest.mark.parametrize("kind,n", [(lb.OBJ_ROSENBROCK_PAIRED, 1000), (lb.OBJ_ROSENBROCK_CHAINED, 1000),
                                     (lb.OBJ_ROSENBROCK_PAIRED, 100000), (lb.OBJ_ROSENBROCK_CHAINED, 100000)])
-def test_config4_shape_box_2_4(ref, kind, n):
+def test_config4_shape_box_2_4(orc, kind, n):
     """BASELINE config 4 (both readings of 'Rosenbrock-box'): lb = 2, ub = 4, x0 = 3."""
     x0 = np.full(n, 3.0)
     g = lb.LBFGSBSolver(lb.LBFGSBParam()).minimize(kind, x0, 2.0, 4.0)
-    c = ref.lbfgsb(kind, x0, 2.0, 4.0, ref.default_param(lbfgsb=True))
+    c = orc.lbfgsb(kind, x0, 2.0, 4.0, orc.default_param(lbfgsb=True))
     check(g, c["status"], c["niter"], c["nfev"], c["fx"], c["x"])
 
 
-def test_box_random_interior_and_loose_bounds(ref):
+def test_box_random_interior_and_loose_bounds(orc):
     rng = np.random.default_rng(4)
     n = 5000
     x0 = rng.uniform(-1, 1, n)
@@ -49,7 +49,7 @@ def test_box_random_interior_and_loose_bounds(ref):
     lbv[::7] = -np.inf
     ubv[::11] = np.inf
     g = lb.LBFGSBSolver(lb.LBFGSBParam()).minimize(lb.OBJ_ROSENBROCK_PAIRED, x0, lbv, ubv)
-    c = ref.lbfgsb(po.OBJ_ROSENBROCK_PAIRED, x0, lbv, ubv, ref.default_param(lbfgsb=True))
+    c = orc.lbfgsb(po.OBJ_ROSENBROCK_PAIRED, x0, lbv, ubv, orc.default_param(lbfgsb=True))
     assert g["status"] == c["status"] == "ok"
     assert abs(g["fx"] - c["fx"]) <= 1e-6 * max(1.0, abs(c["fx"]))
     assert np.all(g["x"] >= lbv) and np.all(g["x"] <= ubv)

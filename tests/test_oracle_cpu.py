@@ -36,6 +36,17 @@ def test_restatement_matches_golden_apply_Hv(orc, case):
     assert float(theta).hex() == case["theta"]
 
 
+@pytest.mark.parametrize("case", golden_cases("lbfgsb"), ids=lambda c: c["name"])
+def test_restatement_matches_golden_lbfgsb(orc, case):
+    p = orc.default_param(lbfgsb=True, **case["param"])
+    r = orc.lbfgsb(case["objective"], unhex(case["x0"]), unhex(case["lb"]), unhex(case["ub"]), p)
+    assert r["status"] == case["status"] and r["msg"] == case["msg"]
+    assert (r["niter"], r["nfev"]) == (case["niter"], case["nfev"])
+    assert np.array_equal(r["trace"], unhex(case["trace"]))
+    assert np.array_equal(r["x"], unhex(case["x"])) and np.array_equal(r["grad"], unhex(case["grad"]))
+    assert float(r["fx"]).hex() == case["fx"] and float(r["gnorm"]).hex() == case["gnorm"]
+
+
 def test_survey_probe_values(orc):
     """BASELINE.md section 4 (independent numpy transliteration): iteration / evaluation counts must agree."""
     expect = {"NocedalWright": (22, 36), "MoreThuente": (21, 28), "Bracketing": (22, 31), "Backtracking": (22, 31)}
@@ -113,3 +124,48 @@ def test_pin_apply_Hv_against_reference_headers(orc, ref):
         ra, _, ta = ref.apply_Hv(S, Y, v, -1.0, m)
         rb, _, tb = orc.apply_Hv(S, Y, v, -1.0, m)
         assert np.array_equal(ra, rb) and ta == tb
+
+
+def test_pin_lbfgsb_against_reference_headers(orc, ref):
+    """Cauchy point, subspace minimisation, Bunch-Kaufman LDL' and the L-BFGS-B driver, bit for bit: mixed finite /
+    infinite / degenerate (l == u) bounds, history sizes 1..10, 0..10 BOXCQP sweeps, delta-based stopping."""
+    rng = np.random.default_rng(3)
+    for obj in (po.OBJ_ROSENBROCK_CHAINED, po.OBJ_ROSENBROCK_PAIRED, po.OBJ_QUAD_SHIFT, po.OBJ_QUAD_TRIDIAG):
+        for n in (2, 4, 10, 25, 26, 100):
+            if obj == po.OBJ_ROSENBROCK_PAIRED and n % 2:
+                continue
+            for trial in range(6):
+                lo = rng.uniform(-2, 1, n)
+                hi = lo + rng.uniform(0, 3, n)
+                if trial == 0:
+                    lo[:], hi[:] = 2.0, 4.0
+                elif trial == 1:
+                    lo[:], hi[:] = -np.inf, np.inf
+                elif trial == 2:
+                    hi[::3] = lo[::3]
+                elif trial == 3:
+                    lo[::2], hi[1::3] = -np.inf, np.inf
+                x0 = rng.uniform(-3, 5, n)
+                d0, d1 = po.quad_tridiag_data(n, seed=trial)[:2] if obj == po.OBJ_QUAD_TRIDIAG else (None, None)
+                kw = dict(m=int(rng.choice([1, 2, 3, 6, 10])), max_iterations=int(rng.choice([0, 5, 50])),
+                          max_submin=int(rng.choice([0, 1, 10])), past=int(rng.choice([0, 0, 2])))
+                if kw["past"]:
+                    kw["delta"] = 1e-8
+                a = orc.lbfgsb(obj, x0, lo, hi, orc.default_param(lbfgsb=True, **kw), data0=d0, data1=d1)
+                b = ref.lbfgsb(obj, x0, lo, hi, ref.default_param(lbfgsb=True, **kw), data0=d0, data1=d1)
+                assert same_run(a, b), (obj, n, trial, kw)
+
+
+def test_pin_lbfgsb_larger_against_reference_headers(orc, ref):
+    for n, obj in ((2000, po.OBJ_ROSENBROCK_CHAINED), (5000, po.OBJ_ROSENBROCK_PAIRED)):
+        a = orc.lbfgsb(obj, np.full(n, 3.0), 2.0, 4.0, orc.default_param(lbfgsb=True))
+        b = ref.lbfgsb(obj, np.full(n, 3.0), 2.0, 4.0, ref.default_param(lbfgsb=True))
+        assert same_run(a, b) and a["status"] == "ok"
+
+
+def test_lbfgsb_parameter_and_bound_errors(orc):
+    """LBFGSB.h:132-133 (size check) and Param.h:351-376 (check_param) surface as invalid_argument."""
+    r = orc.lbfgsb(po.OBJ_QUAD_SHIFT, np.zeros(4), 0.0, 1.0, orc.default_param(lbfgsb=True, m=0))
+    assert r["status"] == "invalid_argument" and "'m' must be positive" in r["msg"]
+    r = orc.lbfgsb(po.OBJ_QUAD_SHIFT, np.zeros(4), 0.0, 1.0, orc.default_param(lbfgsb=True, max_submin=-1))
+    assert r["status"] == "invalid_argument" and "max_submin" in r["msg"]
