@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "DeviceVector.h"
+#include "BKLDLT.h"
 #include "SmallDense.h"
 
 namespace LBFGSpp {
@@ -110,7 +111,7 @@ private:
     Scalar m_theta_host;
     int m_c_host;
     SmallMatrix<Scalar> m_Minv, m_M, m_SS, m_SY;
-    SmallSolver<Scalar> m_Msolver;
+    BKLDLT<Scalar> m_Msolver;  // Minv is symmetric indefinite (reference BFGSMat.h:47,134-146)
     lbfgs_b200_box* m_box;
 
 public:
@@ -212,7 +213,7 @@ public:
                 mid(b, c + a) = mid(c + a, b);
                 mid(c + a, c + b) = theta * (m_SS(a, b) - G(c + a, c + b));
             }
-        SmallSolver<Scalar> midsolver(mid);
+        BKLDLT<Scalar> midsolver(mid);  // reference BFGSMat.h:551
         std::vector<Scalar> z = Wt_dot(v_dev);      // [Y_P'v ; theta*S_P'v]
         midsolver.solve_inplace(z);
         std::vector<Scalar> coef(size_t(2 * c));

@@ -1,9 +1,8 @@
 // LBFGSpp/SmallDense.h -- host-side dense algebra for the 2m x 2m "middle" matrices of L-BFGS-B.
 //
-// The reference factorises these matrices (at most 40 x 40) with its BKLDLT class (reference include/LBFGSpp/BKLDLT.h)
-// on the CPU; SURVEY.md section 2 keeps that work on the host.  This is an independent, much smaller implementation:
-// a row-major dense matrix and an LU factorisation with partial pivoting, which solves the same symmetric indefinite
-// systems (results agree with Bunch-Kaufman to rounding; info() reports a singular pivot the same way).
+// SmallMatrix: row-major dense storage shared by the host-side solvers.  SmallSolver: LU with partial pivoting for general
+// square systems -- the stand-in for Eigen's PartialPivLU that the reference uses when it inverts the dense approximate
+// Hessian (reference BFGSMat.h:205).  The symmetric indefinite middle matrices are factorised by BKLDLT.h.
 #ifndef LBFGSPP_B200_SMALL_DENSE_H
 #define LBFGSPP_B200_SMALL_DENSE_H
 
@@ -44,7 +43,7 @@ public:
     }
 };
 
-// Solver for the small symmetric (indefinite) systems; interface mirrors the reference's BKLDLT: compute / solve_inplace / info.
+// General square solver; interface: compute / solve_inplace / solve / info.
 template <typename Scalar>
 class SmallSolver
 {

@@ -75,3 +75,27 @@ extern "C" int core_line_search_f64(int objective, const double* d0, const doubl
 
 extern "C" const char* core_error_message(int code) { return ls_error_message(code); }
 extern "C" int core_error_kind(int code) { return ls_error_kind(code); }
+
+// ---- host dense algebra of the L-BFGS-B middle matrices (include/LBFGSpp/BKLDLT.h, SmallDense.h) ----------------------------
+#include "../../include/LBFGSpp/BKLDLT.h"
+
+// a: n x n row-major (only the `uplo` triangle is read: 0 lower, 1 upper); b in, x out.  Returns info(), or -1 / -2 for the
+// invalid_argument / logic_error paths (probe < 0: -1 = non-square input, -2 = solve before compute).
+extern "C" int bkldlt_solve_f64(int n, const double* a, int uplo, const double* b, double* x, int probe)
+{
+    try
+    {
+        if (probe == -1) { BKLDLT<double> f(SmallMatrix<double>(2, 3)); return 0; }
+        if (probe == -2) { BKLDLT<double> f; std::vector<double> v(2); f.solve_inplace(v); return 0; }
+        SmallMatrix<double> m(n, n);
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) m(i, j) = a[size_t(i) * n + j];
+        BKLDLT<double> f(m, uplo);
+        std::vector<double> v(b, b + n);
+        f.solve_inplace(v);
+        std::copy(v.begin(), v.end(), x);
+        return f.info();
+    }
+    catch (const std::invalid_argument&) { return -1; }
+    catch (const std::logic_error&) { return -2; }
+}

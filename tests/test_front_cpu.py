@@ -86,3 +86,50 @@ def test_cores_match_restated_line_searches_bit_for_bit(harness, orc, ls):
         else:
             errors += 1
     assert checked > 100 and errors > 5
+
+
+# ---- host dense algebra of L-BFGS-B (include/LBFGSpp/BKLDLT.h) --------------------------------------------------------------
+def bk_solve(lib, a, b, uplo=0, probe=0):
+    dp = C.POINTER(C.c_double)
+    lib.bkldlt_solve_f64.argtypes = [C.c_int, dp, C.c_int, dp, dp, C.c_int]
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.zeros_like(b)
+    info = lib.bkldlt_solve_f64(a.shape[0], a.ctypes.data_as(dp), uplo, b.ctypes.data_as(dp), x.ctypes.data_as(dp), probe)
+    return info, x
+
+
+def test_bunch_kaufman_solves_symmetric_indefinite_systems(harness):
+    rng = np.random.default_rng(11)
+    for n in (1, 2, 3, 5, 12, 20, 40):
+        for kind in range(5):
+            a = rng.standard_normal((n, n))
+            a = a + a.T
+            if kind == 1 and n > 1:
+                np.fill_diagonal(a, 0.0)              # every pivot must be 2x2 or swapped
+            elif kind == 2:
+                a = a @ a.T + n * np.eye(n)           # SPD: all 1x1, no swaps needed
+            elif kind == 3:
+                a[np.abs(a) < 0.8] = 0.0              # sparse pattern, many exact zeros
+                a += np.diag(rng.choice([-3.0, 3.0], n))
+            elif kind == 4 and n % 2 == 0:            # shape of the L-BFGS-B middle matrix [-D L'; L theta*S'S]
+                c = n // 2
+                s, y = rng.standard_normal((c, 50)), rng.standard_normal((c, 50))
+                sy = s @ y.T
+                a = np.block([[-np.diag(np.abs(np.diag(sy)) + 0.1), np.tril(sy, -1).T], [np.tril(sy, -1), 1.7 * (s @ s.T)]])
+            b = rng.standard_normal(n)
+            expect = np.linalg.solve(a, b)
+            scale = np.linalg.cond(a) * np.finfo(float).eps * 50
+            for uplo in (0, 1):
+                tri = np.tril(a) if uplo == 0 else np.triu(a)  # the other triangle must not be read
+                info, x = bk_solve(harness, tri + 7.0 * (np.triu(np.ones((n, n)), 1) if uplo == 0 else np.tril(np.ones((n, n)), -1)), b, uplo)
+                assert info == 0
+                assert np.max(np.abs(x - expect)) <= scale * max(1.0, np.max(np.abs(expect))), (n, kind, uplo)
+
+
+def test_bunch_kaufman_error_paths(harness):
+    """Non-square -> invalid_argument (reference BKLDLT.h:395-396); solve before compute -> logic_error (:446-447);
+    a singular pivot block -> info() == NUMERICAL_ISSUE (2)."""
+    assert bk_solve(harness, np.eye(2), np.ones(2), probe=-1)[0] == -1
+    assert bk_solve(harness, np.eye(2), np.ones(2), probe=-2)[0] == -2
+    assert bk_solve(harness, np.zeros((3, 3)), np.ones(3))[0] == 2
