@@ -86,6 +86,10 @@ lbfgs_b200_status lbfgs_b200_profile_read(lbfgs_b200_ctx* ctx, int phase, double
 lbfgs_b200_status lbfgs_b200_profile_bytes(lbfgs_b200_ctx* ctx, int phase, double* alg_bytes_host, int reset);
 /* n-sharding: global index of this rank's element 0 (used by objectives that depend on the coordinate index) */
 lbfgs_b200_status lbfgs_b200_set_index_offset(lbfgs_b200_ctx* ctx, int64_t offset);
+/* n-sharding: offset as above plus the global vector length.  Required before a neighbour-coupled built-in objective
+ * (chained Rosenbrock, tridiagonal quadratic) is evaluated on a sharded vector: those exchange one boundary coordinate per
+ * side with the neighbouring ranks before every evaluation (every block but the last must hold a multiple of 4 coordinates). */
+lbfgs_b200_status lbfgs_b200_set_global_extent(lbfgs_b200_ctx* ctx, int64_t offset, int64_t n_global);
 
 /* n-sharding over GPUs: rank r owns a contiguous block of every vector; all scalars replicated.
  * unique_id is NCCL's 128-byte ncclUniqueId, created on one rank and shipped to the others by the caller. */

@@ -298,14 +298,23 @@ class Context:
         if st:
             raise LbfgsB200Error(st, self.lib.lbfgs_b200_last_error(None).decode())
 
+    @classmethod
+    def borrow(cls, handle):
+        """Non-owning wrapper around an existing lbfgs_b200_ctx* (e.g. driver_ctx(device), which may carry a communicator)."""
+        self = cls.__new__(cls)
+        self.lib = abi()
+        self.h = handle if isinstance(handle, C.c_void_p) else C.c_void_p(handle)
+        self.owned = False
+        return self
+
     def check(self, st):
         if st:
             raise LbfgsB200Error(st, self.lib.lbfgs_b200_last_error(self.h).decode())
 
     def close(self):
-        if self.h:
+        if self.h and getattr(self, "owned", True):
             self.lib.lbfgs_b200_ctx_destroy(self.h)
-            self.h = C.c_void_p()
+        self.h = C.c_void_p()
 
     def __del__(self):
         try:
@@ -543,6 +552,14 @@ def p2p_attach(device, all_handles, rank, nranks, index_offset=0):
     buf = C.create_string_buffer(bytes(all_handles), 64 * nranks)
     if driver().lbfgsb200_drv_p2p_attach(device, buf, rank, nranks, index_offset, err, 256):
         raise RuntimeError("p2p_attach failed: " + err.value.decode())
+
+
+def set_global_extent(device, index_offset, n_global):
+    """Declare this rank's block of the global vector (needed by the chained-Rosenbrock / tridiagonal objectives when sharded:
+    they exchange one boundary coordinate per side with the neighbouring ranks before every evaluation)."""
+    err = C.create_string_buffer(256)
+    if driver().lbfgsb200_drv_set_global_extent(device, C.c_longlong(index_offset), C.c_longlong(n_global), err, 256):
+        raise RuntimeError("set_global_extent failed: " + err.value.decode())
 
 
 def comm_unique_id():

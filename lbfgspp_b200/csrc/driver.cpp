@@ -471,6 +471,23 @@ extern "C" int lbfgsb200_drv_p2p_attach(int device_ordinal, const void* handles,
     }
 }
 
+// n-sharding: declare this rank's block [index_offset, index_offset + n_local) of a global vector of n_global coordinates
+// (needed by the neighbour-coupled built-in objectives, which exchange halos; see lbfgs_b200_set_global_extent)
+extern "C" int lbfgsb200_drv_set_global_extent(int device_ordinal, long long index_offset, long long n_global, char* err, int errlen)
+{
+    try
+    {
+        Device& dev = device(device_ordinal);
+        dev.check(lbfgs_b200_set_global_extent(dev.ctx(), index_offset, n_global));
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        if (err && errlen > 0) { std::strncpy(err, e.what(), size_t(errlen) - 1); err[errlen - 1] = 0; }
+        return 1;
+    }
+}
+
 
 // LBFGSBSolver<double>::minimize with host buffers (More-Thuente line search, built-in objective, fused trials)
 extern "C" int lbfgsb200_drv_lbfgsb_f64(int device_ordinal, int objective, const double* data0_host, const double* data1_host, long n,

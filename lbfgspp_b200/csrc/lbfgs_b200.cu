@@ -59,6 +59,8 @@ struct lbfgs_b200_ctx
     bool x_active = false;
     unsigned long long x_epoch = 0;
     int64_t index_offset = 0;      // global index of this rank's element 0
+    int64_t n_global = 0;          // global vector length (0 = not declared; needed only by neighbour-coupled objectives)
+    double* d_halo = nullptr;      // kHaloDoubles: boundary coordinates of this rank and of its two neighbours (objectives.cuh)
     uint64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // optional per-phase device timing (lbfgs_b200_profile_*): event pairs recorded around each call
@@ -283,6 +285,47 @@ __global__ void __launch_bounds__(kThreads) k_dots(int64_t n, const T* __restric
 }
 
 // =====================================================================================================
+// halo exchange for neighbour-coupled objectives under n-sharding (one element per side per evaluation)
+//   a = xp (or x), b = d (or nullptr): every rank publishes {a[0], b[0], a[n-1], b[n-1]} and receives its neighbours' four.
+// =====================================================================================================
+template <class T>
+__global__ void k_halo_pack(int64_t n, const T* __restrict__ a, const T* __restrict__ b, double* __restrict__ halo)
+{
+    if (threadIdx.x == 0)
+    {
+        halo[0] = (double)a[0];
+        halo[1] = b ? (double)b[0] : 0.0;
+        halo[2] = (double)a[n - 1];
+        halo[3] = b ? (double)b[n - 1] : 0.0;
+    }
+}
+
+// peer-memory variant: one warp; lane 0 talks to the left neighbour, lane 1 to the right one.  Uses the inbox slot of this
+// launch's epoch exactly like xrank_allreduce (every rank issues the same sequence of exchanges, so epochs agree).
+template <class T>
+__global__ void k_halo_exchange(int64_t n, const T* __restrict__ a, const T* __restrict__ b, double* __restrict__ halo,
+                                const XComm* __restrict__ xc, unsigned long long epoch)
+{
+    const int lane = threadIdx.x;
+    if (lane > 1) return;
+    const int me = xc->rank, R = xc->nranks, slot = (int)(epoch % kXRing);
+    const int nb = (lane == 0) ? me - 1 : me + 1;
+    double* mine = halo + 4 + 4 * lane;   // [4..7] from the left, [8..11] from the right
+    if (nb < 0 || nb >= R)
+    {
+        for (int k = 0; k < 4; k++) mine[k] = 0.0;
+        return;
+    }
+    const double v[4] = {(double)a[0], b ? (double)b[0] : 0.0, (double)a[n - 1], b ? (double)b[n - 1] : 0.0};
+    for (int k = 0; k < 4; k++) xc->inbox[nb]->vals[slot][me][k] = v[k];
+    __threadfence_system();
+    st_release_sys(&xc->inbox[nb]->flag[slot][me], epoch);
+    const unsigned long long* f = &xc->inbox[me]->flag[slot][nb];
+    while (ld_acquire_sys(f) != epoch) {}
+    for (int k = 0; k < 4; k++) mine[k] = ld_volatile_f64(&xc->inbox[me]->vals[slot][nb][k]);
+}
+
+// =====================================================================================================
 // fused line-search trial  (x = xp + step*d ; g = grad f(x) ; {f, g.d, g.g, x.x})
 //   TRIAL = false: plain objective evaluation at x (no xp/d, no x store), reduces {f, -, g.g, x.x}
 // =====================================================================================================
@@ -305,10 +348,12 @@ __device__ __forceinline__ bool trial_body(const OBJ& obj, int64_t n, const T* _
             const Pack<T> px = load4<T, Hint::Stream, VEC>(xp, i0, cnt), pd = load4<T, Hint::Stream, VEC>(d, i0, cnt);
 #pragma unroll
             for (int k = 0; k < 4; k++) { dv[k] = pd.v[k]; xv[k] = px.v[k] + step * pd.v[k]; }
-            if (OBJ::kHalo)
+            if constexpr (OBJ::kHalo)
             {
                 if (i0 > 0) xl = xp[i0 - 1] + step * d[i0 - 1];
+                else if (obj.halo && obj.gofs > 0) xl = T(obj.halo[kHaloLeftA]) + step * T(obj.halo[kHaloLeftB]);
                 if (i0 + 4 < n) xr = xp[i0 + 4] + step * d[i0 + 4];
+                else if (obj.halo && i0 + 4 == n && obj.gofs + n < obj.n_glob) xr = T(obj.halo[kHaloRightA]) + step * T(obj.halo[kHaloRightB]);
             }
         }
         else
@@ -316,10 +361,12 @@ __device__ __forceinline__ bool trial_body(const OBJ& obj, int64_t n, const T* _
             const Pack<T> px = load4<T, Hint::Stream, VEC>(x, i0, cnt);
 #pragma unroll
             for (int k = 0; k < 4; k++) xv[k] = px.v[k];
-            if (OBJ::kHalo)
+            if constexpr (OBJ::kHalo)
             {
                 if (i0 > 0) xl = x[i0 - 1];
+                else if (obj.halo && obj.gofs > 0) xl = T(obj.halo[kHaloLeftA]);
                 if (i0 + 4 < n) xr = x[i0 + 4];
+                else if (obj.halo && i0 + 4 == n && obj.gofs + n < obj.n_glob) xr = T(obj.halo[kHaloRightA]);
             }
         }
         acc[0] += obj.eval(i0, cnt, xv, xl, xr, gv);
@@ -597,6 +644,8 @@ lbfgs_b200_status lbfgs_b200_ctx_create(lbfgs_b200_ctx** out, int device, void* 
     CUC(cudaMalloc(&ctx->d_flag, sizeof(int) * 16));
     CUC(cudaMalloc(&ctx->gram_partials, sizeof(double) * (size_t)ctx->sm_count * kMaxM * kGramVals));
     CUC(cudaMalloc(&ctx->gram_raw, sizeof(double) * kMaxM * kGramVals));
+    CUC(cudaMalloc(&ctx->d_halo, sizeof(double) * kHaloDoubles));
+    CUC(cudaMemsetAsync(ctx->d_halo, 0, sizeof(double) * kHaloDoubles, ctx->stream));
     CUC(cudaMemsetAsync(ctx->rb.ticket, 0, sizeof(unsigned), ctx->stream));
     CUC(cudaMemsetAsync(ctx->rb.result, 0, sizeof(double) * 256, ctx->stream));
     CUC(cudaMallocHost(&ctx->h_result, sizeof(double) * 256));
@@ -627,6 +676,7 @@ void lbfgs_b200_ctx_destroy(lbfgs_b200_ctx* ctx)
     cudaFree(ctx->d_flag);
     cudaFree(ctx->gram_partials);
     cudaFree(ctx->gram_raw);
+    cudaFree(ctx->d_halo);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
     if (ctx->h_mail) cudaFreeHost((void*)ctx->h_mail);
@@ -744,6 +794,14 @@ lbfgs_b200_status lbfgs_b200_set_index_offset(lbfgs_b200_ctx* ctx, int64_t offse
 {
     REQUIRE(ctx, ctx != nullptr, "set_index_offset: NULL context");
     ctx->index_offset = offset;
+    return LBFGS_B200_OK;
+}
+
+lbfgs_b200_status lbfgs_b200_set_global_extent(lbfgs_b200_ctx* ctx, int64_t offset, int64_t n_global)
+{
+    REQUIRE(ctx, ctx != nullptr && offset >= 0 && n_global >= offset, "set_global_extent: need 0 <= offset <= n_global");
+    ctx->index_offset = offset;
+    ctx->n_global = n_global;
     return LBFGS_B200_OK;
 }
 
@@ -875,6 +933,39 @@ static lbfgs_b200_status do_scale_out(lbfgs_b200_ctx* ctx, int64_t n, T s, const
     return post_launch(ctx, "k_scale_out");
 }
 
+// Boundary coordinates of the evaluation point to and from the neighbouring ranks (objectives.cuh: halo record).  Stream-ordered;
+// in peer-memory mode it consumes one exchange epoch, with NCCL it is a grouped send/recv pair per neighbour.
+template <class T>
+static lbfgs_b200_status exchange_halo(lbfgs_b200_ctx* ctx, int64_t n, const T* a, const T* b)
+{
+    REQUIRE(ctx, ctx->n_global > 0, "a neighbour-coupled objective under n-sharding needs lbfgs_b200_set_global_extent()");
+    REQUIRE(ctx, n >= 1 && ctx->index_offset + n <= ctx->n_global, "halo exchange: local block [%lld, %lld) exceeds the global extent %lld",
+            (long long)ctx->index_offset, (long long)(ctx->index_offset + n), (long long)ctx->n_global);
+    REQUIRE(ctx, ctx->rank == ctx->nranks - 1 || n % 4 == 0, "halo exchange: every block but the last must hold a multiple of 4 coordinates (got %lld)", (long long)n);
+    if (ctx->x_active)
+    {
+        k_halo_exchange<T><<<1, 32, 0, ctx->stream>>>(n, a, b, ctx->d_halo, ctx->x_comm, ++ctx->x_epoch);
+        return post_launch(ctx, "k_halo_exchange");
+    }
+    REQUIRE(ctx, ctx->comm != nullptr, "halo exchange: no communicator attached");
+    k_halo_pack<T><<<1, 32, 0, ctx->stream>>>(n, a, b, ctx->d_halo);
+    if (auto st = post_launch(ctx, "k_halo_pack")) return st;
+    CU(ctx, cudaMemsetAsync(ctx->d_halo + 4, 0, sizeof(double) * 8, ctx->stream));
+    NC(ctx, ncclGroupStart());
+    if (ctx->rank > 0)
+    {
+        NC(ctx, ncclSend(ctx->d_halo, 4, ncclDouble, ctx->rank - 1, ctx->comm, ctx->stream));
+        NC(ctx, ncclRecv(ctx->d_halo + 4, 4, ncclDouble, ctx->rank - 1, ctx->comm, ctx->stream));
+    }
+    if (ctx->rank < ctx->nranks - 1)
+    {
+        NC(ctx, ncclSend(ctx->d_halo, 4, ncclDouble, ctx->rank + 1, ctx->comm, ctx->stream));
+        NC(ctx, ncclRecv(ctx->d_halo + 8, 4, ncclDouble, ctx->rank + 1, ctx->comm, ctx->stream));
+    }
+    NC(ctx, ncclGroupEnd());
+    return LBFGS_B200_OK;
+}
+
 template <class T, class OBJ, bool TRIAL>
 static lbfgs_b200_status launch_trial(lbfgs_b200_ctx* ctx, const OBJ& obj, int64_t n, const T* xp, const T* d, T step,
                                       T* x, T* g, bool vec)
@@ -892,8 +983,16 @@ static lbfgs_b200_status do_trial(lbfgs_b200_ctx* ctx, int objective, const T* d
 {
     REQUIRE(ctx, ctx && x && g && out_host && n >= 1, "trial/objective: bad arguments");
     if (TRIAL) REQUIRE(ctx, xp && d, "trial: xp/d are NULL");
-    REQUIRE(ctx, ctx->nranks == 1 || objective == LBFGS_B200_OBJ_ROSENBROCK_PAIRED || objective == LBFGS_B200_OBJ_QUAD_SHIFT,
-            "objective %d couples neighbouring coordinates: n-sharding needs a halo exchange (not implemented)", objective);
+    const bool coupled = objective == LBFGS_B200_OBJ_ROSENBROCK_CHAINED || objective == LBFGS_B200_OBJ_QUAD_TRIDIAG;
+    const double* halo = nullptr;
+    int64_t gofs = 0, n_glob = n;
+    if (coupled && ctx->nranks > 1)
+    {
+        if (auto sh = exchange_halo<T>(ctx, n, TRIAL ? xp : x, TRIAL ? d : nullptr)) return sh;
+        halo = ctx->d_halo;
+        gofs = ctx->index_offset;
+        n_glob = ctx->n_global;
+    }
     const bool vec = all_aligned<T>({xp, d, x, g});
     lbfgs_b200_status st = LBFGS_B200_OK;
     ProfSpan span(ctx, PH_TRIAL, double(sizeof(T)) * double(n) * ((TRIAL ? 4.0 : 2.0) + (objective == LBFGS_B200_OBJ_QUAD_TRIDIAG ? 2.0 : 0.0)));
@@ -914,15 +1013,15 @@ static lbfgs_b200_status do_trial(lbfgs_b200_ctx* ctx, int objective, const T* d
     }
     case LBFGS_B200_OBJ_ROSENBROCK_CHAINED:
     {
-        REQUIRE(ctx, n >= 2, "chained Rosenbrock needs n >= 2");
-        RosenbrockChained<T> o{n};
+        REQUIRE(ctx, n_glob >= 2, "chained Rosenbrock needs n >= 2");
+        RosenbrockChained<T> o{n, gofs, n_glob, halo};
         st = launch_trial<T, RosenbrockChained<T>, TRIAL>(ctx, o, n, xp, d, step, x, g, vec);
         break;
     }
     case LBFGS_B200_OBJ_QUAD_TRIDIAG:
     {
         REQUIRE(ctx, data0 && data1, "quad_tridiag needs data0 = diag, data1 = rhs");
-        QuadTridiag<T> o{n, data0, data1};
+        QuadTridiag<T> o{n, data0, data1, gofs, n_glob, halo};
         st = launch_trial<T, QuadTridiag<T>, TRIAL>(ctx, o, n, xp, d, step, x, g, vec);
         break;
     }

@@ -148,8 +148,8 @@ template <class T> __device__ __forceinline__ void record_eval(DevSolve<T>* st, 
 template <class T, class OBJ> struct ObjMaker;
 template <class T> struct ObjMaker<T, RosenbrockPaired<T> > { static __device__ RosenbrockPaired<T> make(const ResidentEnv<T>&, int64_t n) { return RosenbrockPaired<T>{n}; } };
 template <class T> struct ObjMaker<T, QuadShift<T> > { static __device__ QuadShift<T> make(const ResidentEnv<T>& e, int64_t n) { return QuadShift<T>{n, e.index_offset}; } };
-template <class T> struct ObjMaker<T, RosenbrockChained<T> > { static __device__ RosenbrockChained<T> make(const ResidentEnv<T>&, int64_t n) { return RosenbrockChained<T>{n}; } };
-template <class T> struct ObjMaker<T, QuadTridiag<T> > { static __device__ QuadTridiag<T> make(const ResidentEnv<T>& e, int64_t n) { return QuadTridiag<T>{n, e.data0, e.data1}; } };
+template <class T> struct ObjMaker<T, RosenbrockChained<T> > { static __device__ RosenbrockChained<T> make(const ResidentEnv<T>&, int64_t n) { return RosenbrockChained<T>{n, 0, n, nullptr}; } };
+template <class T> struct ObjMaker<T, QuadTridiag<T> > { static __device__ QuadTridiag<T> make(const ResidentEnv<T>& e, int64_t n) { return QuadTridiag<T>{n, e.data0, e.data1, 0, n, nullptr}; } };
 
 // fx = f(x, grad), norms, early exit (LBFGS.h:91-103), first step 1/||g|| and dg = -g.g (:106-108,123)
 template <class T, class OBJ>
@@ -509,7 +509,7 @@ static lbfgs_b200_status solver_minimize(lbfgs_b200_solver* s, int objective, co
     REQUIRE(ctx, prm->past <= kMaxPast, "past > %d is not supported by the device-resident solve", kMaxPast);
     REQUIRE(ctx, ctx->nranks == 1 || ctx->x_active, "the device-resident solve needs the in-kernel exchange (comm_p2p) when sharded");
     REQUIRE(ctx, ctx->nranks == 1 || objective == LBFGS_B200_OBJ_ROSENBROCK_PAIRED || objective == LBFGS_B200_OBJ_QUAD_SHIFT,
-            "objective %d couples neighbouring coordinates: n-sharding needs a halo exchange (not implemented)", objective);
+            "objective %d couples neighbouring coordinates: under n-sharding use the host-driven loop (the device-resident graph has no halo exchange)", objective);
     if (objective == LBFGS_B200_OBJ_ROSENBROCK_PAIRED) REQUIRE(ctx, s->n % 2 == 0, "paired Rosenbrock needs an even n");
     if (objective == LBFGS_B200_OBJ_QUAD_TRIDIAG) REQUIRE(ctx, data0 && data1, "quad_tridiag needs data0 = diag, data1 = rhs");
     lbfgs_b200_hist* h = s->hist;
