@@ -38,6 +38,7 @@ struct lbfgs_b200_ctx
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int sm_count = 148;
+    int ctas_per_sm_cap = 8;       // streaming grids: at most this many CTAs per SM (tuning knob LBFGS_B200_CTAS_PER_SM, 1..8)
     ReduceBuf rb{};                // device scratch for grid_reduce
     double* h_result = nullptr;    // pinned mirror of rb.result (+ extra slots)
     double* gram_partials = nullptr;  // [sm_count][kMaxM*kGramVals] block partials of k_gram_dots
@@ -137,7 +138,7 @@ static int grid_for(const lbfgs_b200_ctx* ctx, int64_t n, int packs_per_thread =
 {
     const int64_t packs = (n + 3) / 4;
     const int64_t want = (packs + (int64_t)kThreads * packs_per_thread - 1) / ((int64_t)kThreads * packs_per_thread);
-    const int64_t cap = (int64_t)ctx->sm_count * 8;
+    const int64_t cap = (int64_t)ctx->sm_count * ctx->ctas_per_sm_cap;
     int64_t g = want < 1 ? 1 : want;
     if (g > cap) g = cap;
     if (g > ctx->sm_count) g = (g / ctx->sm_count) * ctx->sm_count;  // whole waves
@@ -636,6 +637,11 @@ lbfgs_b200_status lbfgs_b200_ctx_create(lbfgs_b200_ctx** out, int device, void* 
         return LBFGS_B200_ERR_CUDA;
     }
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char* e = getenv("LBFGS_B200_CTAS_PER_SM"))
+    {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 8) ctx->ctas_per_sm_cap = v;
+    }
     if (stream) ctx->stream = static_cast<cudaStream_t>(stream);
     else { CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
     CUC(cudaMalloc(&ctx->rb.partials, sizeof(double) * kMaxBlocks * kMaxRed));
