@@ -254,8 +254,8 @@ public:
             }
             if (m_param.max_iterations != 0 && k >= m_param.max_iterations) return k;  // LBFGS.h:151-154
 
-            m_bfgs.update(x, m_xp, m_grad, m_gradp);                         // LBFGS.h:159-162
-            dg = m_bfgs.apply_Hv_dot(m_grad, -Scalar(1), m_drt);             // LBFGS.h:165 (+ :123 of the next pass)
+            // LBFGS.h:159-162 (s, y, curvature gate, add_correction) + :165 (apply_Hv) + :123 of the next pass (dg), fused
+            dg = m_bfgs.update_apply_Hv_dot(x, m_xp, m_grad, m_gradp, -Scalar(1), m_drt);
             step = Scalar(1);
             k++;
         }

@@ -100,6 +100,20 @@ public:
         return vr;
     }
 
+    // update(x, xp, g, gp) followed by apply_Hv_dot(g, a, res) as ONE device pass over x, xp, g, gp (LBFGS.h:159-165): the
+    // correction pair is formed inside the Gram-dots kernel.  Returns g.res; `accepted` tells whether the pair passed the gate.
+    Scalar update_apply_Hv_dot(const Vector& x, const Vector& xp, const Vector& g, const Vector& gp, const Scalar& a, Vector& res,
+                               bool* accepted = nullptr)
+    {
+        res.resize(g.size());
+        int acc = 0;
+        Scalar vr = Scalar(0);
+        m_dev->check(detail::Abi<Scalar>::hist_update_apply_Hv(m_hist, x.data(), xp.data(), g.data(), gp.data(),
+                                                               std::numeric_limits<Scalar>::epsilon(), a, res.data(), m_algo, &acc, &vr));
+        if (accepted) *accepted = acc != 0;
+        return vr;
+    }
+
     //========== L-BFGS-B part (reference BFGSMat.h:99-146, 307-615) ==========//
     // B = theta*I - W M W' with W = [Y, theta*S] (n x 2c, columns ordered newest pair first) and M = inv(Minv),
     //   Minv = [ -D   L' ]   D = diag(s_a'y_a),  L(a,b) = s_a'y_b when pair a is newer than pair b, else 0.

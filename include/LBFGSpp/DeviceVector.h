@@ -98,6 +98,7 @@ template <> struct Abi<double>
     static lbfgs_b200_status hist_update(lbfgs_b200_hist* h, const double* x, const double* xp, const double* g, const double* gp, double eps, int* acc, double* sy_yy) { return lbfgs_b200_hist_update_f64(h, x, xp, g, gp, eps, acc, sy_yy); }
     static lbfgs_b200_status hist_add(lbfgs_b200_hist* h, const double* s, const double* y) { return lbfgs_b200_hist_add_f64(h, s, y); }
     static lbfgs_b200_status hist_apply_Hv(lbfgs_b200_hist* h, const double* v, double a, double* res, int algo, double* vdot) { return lbfgs_b200_hist_apply_Hv_f64(h, v, a, res, algo, vdot); }
+    static lbfgs_b200_status hist_update_apply_Hv(lbfgs_b200_hist* h, const double* x, const double* xp, const double* g, const double* gp, double eps, double a, double* res, int algo, int* acc, double* vdot) { return lbfgs_b200_hist_update_apply_Hv_f64(h, x, xp, g, gp, eps, a, res, algo, acc, vdot); }
 };
 template <> struct Abi<float>
 {
@@ -110,6 +111,7 @@ template <> struct Abi<float>
     static lbfgs_b200_status hist_update(lbfgs_b200_hist* h, const float* x, const float* xp, const float* g, const float* gp, float eps, int* acc, float* sy_yy) { return lbfgs_b200_hist_update_f32(h, x, xp, g, gp, eps, acc, sy_yy); }
     static lbfgs_b200_status hist_add(lbfgs_b200_hist* h, const float* s, const float* y) { return lbfgs_b200_hist_add_f32(h, s, y); }
     static lbfgs_b200_status hist_apply_Hv(lbfgs_b200_hist* h, const float* v, float a, float* res, int algo, float* vdot) { return lbfgs_b200_hist_apply_Hv_f32(h, v, a, res, algo, vdot); }
+    static lbfgs_b200_status hist_update_apply_Hv(lbfgs_b200_hist* h, const float* x, const float* xp, const float* g, const float* gp, float eps, float a, float* res, int algo, int* acc, float* vdot) { return lbfgs_b200_hist_update_apply_Hv_f32(h, x, xp, g, gp, eps, a, res, algo, acc, vdot); }
 };
 
 // bound-constrained primitives

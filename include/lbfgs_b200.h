@@ -155,6 +155,12 @@ const void* lbfgs_b200_hist_y_col(const lbfgs_b200_hist* h, int age);
      * res must not alias v. */                                                                                \
     lbfgs_b200_status lbfgs_b200_hist_apply_Hv_##SUF(lbfgs_b200_hist* h, const T* v, T a, T* res, int algo,    \
                                                      T* vdotres_host);                                        \
+    /* LBFGS.h:159-165 in one call: hist_update(x, xp, g, gp) followed by apply_Hv(v = g, a, res) (+ g.res).   \
+     * With the Gram form the pair is formed inside the dots pass, so x, xp, g, gp are read once and no         \
+     * separate update kernel runs; otherwise equivalent to the two calls.  res must not alias an input. */    \
+    lbfgs_b200_status lbfgs_b200_hist_update_apply_Hv_##SUF(lbfgs_b200_hist* h, const T* x, const T* xp,       \
+                                                            const T* g, const T* gp, T eps, T a, T* res,       \
+                                                            int algo, int* accepted_host, T* gdotres_host);    \
     /* host copies of theta and of ys/alpha by age (newest first), for tests */                                \
     lbfgs_b200_status lbfgs_b200_hist_scalars_##SUF(lbfgs_b200_hist* h, T* theta_host, T* ys_host,             \
                                                     T* alpha_host);

@@ -105,6 +105,7 @@ def abi():
         getattr(lib, "lbfgs_b200_hist_update_" + suf).argtypes = [vp, vp, vp, vp, vp, ct, C.POINTER(ci), pt]
         getattr(lib, "lbfgs_b200_hist_add_" + suf).argtypes = [vp, vp, vp]
         getattr(lib, "lbfgs_b200_hist_apply_Hv_" + suf).argtypes = [vp, vp, ct, vp, ci, pt]
+        getattr(lib, "lbfgs_b200_hist_update_apply_Hv_" + suf).argtypes = [vp, vp, vp, vp, vp, ct, ct, vp, ci, C.POINTER(ci), pt]
         getattr(lib, "lbfgs_b200_hist_scalars_" + suf).argtypes = [vp, pt, pt, pt]
     lib._typed = True
     return lib
@@ -439,6 +440,15 @@ class History:
         self.ctx.check(getattr(self.ctx.lib, "lbfgs_b200_hist_update_" + self.suf)(self.h, x.ptr, xp.ptr, g.ptr, gp.ptr,
                                                                                   eps, C.byref(acc), sy))
         return bool(acc.value), sy[0], sy[1]
+
+    def update_apply_Hv(self, x, xp, g, gp, a, res, algo=HV_AUTO, eps=None):
+        """hist_update(x, xp, g, gp) + apply_Hv(g, a, res) as one call (pair formed inside the dots pass); -> (accepted, g.res)"""
+        eps = np.finfo(self.dtype).eps if eps is None else eps
+        acc = C.c_int(0)
+        out = (self.ct * 1)()
+        self.ctx.check(getattr(self.ctx.lib, "lbfgs_b200_hist_update_apply_Hv_" + self.suf)(
+            self.h, x.ptr, xp.ptr, g.ptr, gp.ptr, eps, a, res.ptr, algo, C.byref(acc), out))
+        return bool(acc.value), out[0]
 
     def apply_Hv(self, v, a, res, algo=HV_AUTO, want_dot=False):
         out = (self.ct * 1)()

@@ -1052,17 +1052,23 @@ template <class T> static lbfgs_b200_status hist_check(lbfgs_b200_hist* h)
 
 template <class T> static lbfgs_b200_status gram_refresh(lbfgs_b200_hist* h);
 
+// src: device doubles {s'y, y'y} of the pair sitting in slot h->head; nullptr = the reduction slots of the kernel just launched
+// (still to be all-reduced), otherwise already global sums.
 template <class T>
-static lbfgs_b200_status commit_pair(lbfgs_b200_hist* h, T eps, int gate, int* accepted_host, T* sy_yy_host)
+static lbfgs_b200_status commit_pair(lbfgs_b200_hist* h, T eps, int gate, int* accepted_host, T* sy_yy_host, const double* src = nullptr)
 {
     lbfgs_b200_ctx* ctx = h->ctx;
-    if (auto st = allreduce_result(ctx, 2)) return st;
+    if (!src)
+    {
+        if (auto st = allreduce_result(ctx, 2)) return st;
+        src = ctx->rb.result;
+    }
     T* ys = static_cast<T*>(h->ys) + h->head;
     int ok = 0;
     if (mail_ok(ctx))
     {
         const unsigned long long seq = ++ctx->mail_seq;
-        k_commit_pair<T><<<1, 1, 0, ctx->stream>>>(ctx->rb.result, eps, gate, ys, static_cast<T*>(h->theta), ctx->d_flag,
+        k_commit_pair<T><<<1, 1, 0, ctx->stream>>>(src, eps, gate, ys, static_cast<T*>(h->theta), ctx->d_flag,
                                                    ctx->d_mail->vals, &ctx->d_mail->flag,
                                                    const_cast<unsigned long long*>(&ctx->d_mail->word), seq);
         if (auto st = post_launch(ctx, "k_commit_pair")) return st;
@@ -1071,11 +1077,12 @@ static lbfgs_b200_status commit_pair(lbfgs_b200_hist* h, T eps, int gate, int* a
     }
     else
     {
-        k_commit_pair<T><<<1, 1, 0, ctx->stream>>>(ctx->rb.result, eps, gate, ys, static_cast<T*>(h->theta), ctx->d_flag,
+        k_commit_pair<T><<<1, 1, 0, ctx->stream>>>(src, eps, gate, ys, static_cast<T*>(h->theta), ctx->d_flag,
                                                    nullptr, nullptr, nullptr, 0ull);
         if (auto st = post_launch(ctx, "k_commit_pair")) return st;
         CU(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        if (auto st = fetch_result(ctx, 2)) return st;  // synchronises
+        CU(ctx, cudaMemcpyAsync(ctx->h_result, src, sizeof(double) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
         ok = ctx->h_flag[0];
     }
     if (ok)
@@ -1198,44 +1205,68 @@ template <class T> static void fill_slots(const lbfgs_b200_hist* h, unsigned cha
 }
 
 // [S Y]'[v s_new y_new] (+ all-reduce).  v == nullptr: only the new pair's Gram row/column ("refresh").
+// Speculative "update + dots" (form != nullptr): the pair (s, y) = (x - xp, v - gp) is formed on the fly into the spare slot
+// h->head and takes part as the newest column, exactly as if it had been appended already; the caller commits or discards it.
+template <class T> struct PairForm { const T* x; const T* xp; const T* gp; };
+
 template <class T>
-static lbfgs_b200_status gram_dots(lbfgs_b200_hist* h, const T* v)
+static lbfgs_b200_status gram_dots(lbfgs_b200_hist* h, const T* v, const PairForm<T>* form = nullptr)
 {
     lbfgs_b200_ctx* ctx = h->ctx;
-    const int c = h->ncorr;
+    const int c = form ? (h->ncorr < h->m ? h->ncorr + 1 : h->m) : h->ncorr;
     GramDotsArgs<T> a{};
     a.n = h->n; a.ld = h->ld; a.v = v;
     a.S = static_cast<const T*>(h->S); a.Y = static_cast<const T*>(h->Y);
-    a.c = c; a.new_slot = h->pending;
+    a.c = c; a.new_slot = form ? h->head : h->pending;
+    if (form)
+    {
+        a.fx = form->x; a.fxp = form->xp; a.fgp = form->gp;
+        a.s_out = h->s_col<T>(h->head); a.y_out = h->y_col<T>(h->head);
+    }
     // warps = (column pairs in flight) x (warps per column pair); as many of the 24 warp slots as divide evenly
     int split = 8;
     while (split > 1 && c * split > kGramMaxWarps) split >>= 1;
     a.split = split;
     a.cols_per_round = c < kGramMaxWarps / split ? c : kGramMaxWarps / split;
     a.use_tma = (v == nullptr || (reinterpret_cast<uintptr_t>(v) & 15) == 0) ? 1 : 0;
-    fill_slots<T>(h, a.slots);
+    if (form)
+    {
+        a.slots[0] = (unsigned char)h->head;                      // ages as they will be once the pair is committed
+        for (int age = 1; age < c; age++) a.slots[age] = (unsigned char)h->slot(age - 1);
+    }
+    else
+        fill_slots<T>(h, a.slots);
     const int rounds = (c + a.cols_per_round - 1) / a.cols_per_round;
     const int threads = a.cols_per_round * split * 32;
     const int64_t ntiles = (h->n + kGramTE - 1) / kGramTE;
     const int grid = (int)(ntiles < ctx->sm_count ? ntiles : ctx->sm_count);
-    const size_t smem = (size_t)kGramStages * 3 * kGramTE * sizeof(T);
+    const size_t smem = (size_t)kGramStages * (form ? 4 : 3) * kGramTE * sizeof(T);
     const XComm* xc = ctx->x_active ? ctx->x_comm : nullptr;
     const unsigned long long epoch = ctx->x_active ? ++ctx->x_epoch : 0ull;
-#define LAUNCH_GRAM(R)                                                                                       \
+#define LAUNCH_GRAM(KERNEL, R, BASE)                                                                         \
     do {                                                                                                     \
         /* the opt-in for > 48 KB of dynamic shared memory is per device: remember it per context */        \
-        const unsigned bit = 1u << ((sizeof(T) == 8 ? 0 : 4) + R);                                           \
+        const unsigned bit = 1u << (BASE + (sizeof(T) == 8 ? 0 : 4) + R);                                    \
         if (!(ctx->smem_optin & bit)) {                                                                      \
-            CU(ctx, cudaFuncSetAttribute(k_gram_dots<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            CU(ctx, cudaFuncSetAttribute(KERNEL<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             ctx->smem_optin |= bit;                                                                          \
         }                                                                                                    \
-        k_gram_dots<T, R><<<grid, threads, smem, ctx->stream>>>(a, ctx->gram_partials, ctx->rb.ticket, ctx->gram_raw, xc, epoch); \
+        KERNEL<T, R><<<grid, threads, smem, ctx->stream>>>(a, ctx->gram_partials, ctx->rb.ticket, ctx->gram_raw, xc, epoch); \
     } while (0)
-    if (rounds <= 1) LAUNCH_GRAM(1);
-    else if (rounds == 2) LAUNCH_GRAM(2);
-    else LAUNCH_GRAM(3);
+    if (form)
+    {
+        if (rounds <= 1) LAUNCH_GRAM(k_pair_dots, 1, 8);
+        else if (rounds == 2) LAUNCH_GRAM(k_pair_dots, 2, 8);
+        else LAUNCH_GRAM(k_pair_dots, 3, 8);
+    }
+    else
+    {
+        if (rounds <= 1) LAUNCH_GRAM(k_gram_dots, 1, 0);
+        else if (rounds == 2) LAUNCH_GRAM(k_gram_dots, 2, 0);
+        else LAUNCH_GRAM(k_gram_dots, 3, 0);
+    }
 #undef LAUNCH_GRAM
-    if (auto st = post_launch(ctx, "k_gram_dots")) return st;
+    if (auto st = post_launch(ctx, form ? "k_pair_dots" : "k_gram_dots")) return st;
     if (ctx->nranks > 1 && !ctx->x_active)
         NC(ctx, ncclAllReduce(ctx->gram_raw, ctx->gram_raw, c * kGramVals, ncclDouble, ncclSum, ctx->comm, ctx->stream));
     return LBFGS_B200_OK;
@@ -1282,11 +1313,20 @@ template <class T> static lbfgs_b200_status gram_refresh(lbfgs_b200_hist* h)
     return LBFGS_B200_OK;
 }
 
+template <class T> static lbfgs_b200_status hv_gram_combine(lbfgs_b200_hist* h, const T* v, T a, T* res, bool want_vdot);
+
 template <class T>
 static lbfgs_b200_status hv_gram(lbfgs_b200_hist* h, const T* v, T a, T* res, bool want_vdot)
 {
-    lbfgs_b200_ctx* ctx = h->ctx;
     if (auto st = gram_dots<T>(h, v)) return st;
+    return hv_gram_combine<T>(h, v, a, res, want_vdot);
+}
+
+// second half of the Gram-form apply_Hv: ctx->gram_raw holds the (all-reduced) dots of the current history against v
+template <class T>
+static lbfgs_b200_status hv_gram_combine(lbfgs_b200_hist* h, const T* v, T a, T* res, bool want_vdot)
+{
+    lbfgs_b200_ctx* ctx = h->ctx;
     GramCombineArgs<T> k{};
     k.n = h->n; k.ld = h->ld; k.v = v;
     k.S = static_cast<const T*>(h->S); k.Y = static_cast<const T*>(h->Y);
@@ -1320,6 +1360,49 @@ static lbfgs_b200_status do_hist_apply_Hv(lbfgs_b200_hist* h, const T* v, T a, T
     ProfSpan span(ctx, PH_APPLY_HV, double(sizeof(T)) * double(h->n) * (4.0 * h->ncorr + 2.0));
     lbfgs_b200_status st = gram ? hv_gram<T>(h, v, a, res, vdot_host != nullptr)
                                 : hv_two_loop<T>(h, v, a, res, vdot_host != nullptr);
+    span.stop();
+    if (st) return st;
+    if (vdot_host)
+    {
+        if (auto s2 = (gram ? receive(ctx, 1) : fetch_result(ctx, 1))) return s2;
+        *vdot_host = (T)ctx->h_result[0];
+    }
+    return LBFGS_B200_OK;
+}
+
+// LBFGS.h:159-165 as one call: { s = x - xp; y = g - gp; if (s'y > eps*y'y) add_correction(s, y); res = a*H*g } (+ g.res).
+// With the Gram form the pair is formed inside the dots pass (k_pair_dots): no separate update kernel, x/xp/g/gp are read
+// once, s and y are written once.  The pair is committed only after the gate has seen s'y, y'y (its own dots); a rejected
+// pair leaves the history untouched and the old history answers, as in the reference.
+template <class T>
+static lbfgs_b200_status do_hist_update_apply_Hv(lbfgs_b200_hist* h, const T* x, const T* xp, const T* g, const T* gp, T eps,
+                                                 T a, T* res, int algo, int* accepted_host, T* vdot_host)
+{
+    if (auto st = hist_check<T>(h)) return st;
+    lbfgs_b200_ctx* ctx = h->ctx;
+    REQUIRE(ctx, x && xp && g && gp && res, "update_apply_Hv: NULL vector");
+    REQUIRE(ctx, res != g && res != x && res != xp && res != gp, "update_apply_Hv: res aliases an input");
+    REQUIRE(ctx, algo >= LBFGS_B200_HV_AUTO && algo <= LBFGS_B200_HV_GRAM, "update_apply_Hv: unknown algorithm %d", algo);
+    if (algo == LBFGS_B200_HV_TWO_LOOP || !all_aligned<T>({x, xp, g, gp}))
+    {
+        if (auto st = do_hist_update<T>(h, x, xp, g, gp, eps, accepted_host, nullptr)) return st;
+        return do_hist_apply_Hv<T>(h, g, a, res, algo, vdot_host);
+    }
+    if (h->pending >= 0)
+        if (auto st = gram_refresh<T>(h)) return st;
+    const int c_new = h->ncorr < h->m ? h->ncorr + 1 : h->m;
+    ProfSpan span(ctx, PH_APPLY_HV, double(sizeof(T)) * double(h->n) * (4.0 * c_new + 2.0 + 6.0));
+    const PairForm<T> form{x, xp, gp};
+    if (auto st = gram_dots<T>(h, g, &form)) return st;
+    int ok = 0;
+    if (auto st = commit_pair<T>(h, eps, 1, &ok, nullptr, ctx->gram_raw + 2)) return st;  // age-0 column: [2] = s'y, [3] = y'y
+    if (accepted_host) *accepted_host = ok;
+    const bool want = vdot_host != nullptr;
+    bool gram = true;
+    lbfgs_b200_status st;
+    if (ok) st = hv_gram_combine<T>(h, g, a, res, want);
+    else if (h->ncorr > 0) st = hv_gram<T>(h, g, a, res, want);
+    else { gram = false; st = hv_two_loop<T>(h, g, a, res, want); }
     span.stop();
     if (st) return st;
     if (vdot_host)
@@ -1459,6 +1542,9 @@ const void* lbfgs_b200_hist_y_col(const lbfgs_b200_hist* h, int age)
     { return do_hist_add<T>(h, s, y); }                                                                        \
     lbfgs_b200_status lbfgs_b200_hist_apply_Hv_##SUF(lbfgs_b200_hist* h, const T* v, T a, T* res, int algo,    \
                                                      T* vdot) { return do_hist_apply_Hv<T>(h, v, a, res, algo, vdot); } \
+    lbfgs_b200_status lbfgs_b200_hist_update_apply_Hv_##SUF(lbfgs_b200_hist* h, const T* x, const T* xp, const T* g, \
+                                                            const T* gp, T eps, T a, T* res, int algo, int* acc, T* vdot) \
+    { return do_hist_update_apply_Hv<T>(h, x, xp, g, gp, eps, a, res, algo, acc, vdot); }                      \
     lbfgs_b200_status lbfgs_b200_hist_scalars_##SUF(lbfgs_b200_hist* h, T* th, T* ys, T* al)                   \
     { return do_hist_scalars<T>(h, th, ys, al); }
 

@@ -43,6 +43,14 @@ template <class T> struct GramDotsArgs
     int cols_per_round;  // column pairs processed concurrently by one CTA (warps = cols_per_round * split)
     int use_tma;       // v 16-byte aligned
     unsigned char slots[kMaxM];  // physical slot by age (0 = newest)
+    // FORM variant ("update + dots" in one pass, LBFGS.h:159-165): the newest pair is not in the ring yet; it is formed tile by
+    // tile as s = fx - fxp, y = v - fgp (v = the new gradient), written to columns `new_slot` of S and Y, and used from shared
+    // memory for its own dots.  All five pointers 32-byte aligned.
+    const T* fx;
+    const T* fxp;
+    const T* fgp;
+    T* s_out;
+    T* y_out;
 };
 
 // ---- mbarrier / TMA helpers (sm_90+ PTX, assembled for sm_100a) -------------------------------------
@@ -98,11 +106,12 @@ __device__ __forceinline__ Pack<float> lds_pack(const float* p, int)
     return r;
 }
 
-template <class T, int ROUNDS>
+template <class T, int ROUNDS, bool FORM = false>
 __device__ __forceinline__ void gram_dots_body(const GramDotsArgs<T>& a, double* partials, unsigned* ticket, double* result, const XComm* xc, unsigned long long epoch)
 {
+    constexpr int NT = FORM ? 4 : 3;                             // staged vectors per tile: v, s_new, y_new (+ xp while forming)
     extern __shared__ __align__(128) unsigned char gram_smem[];
-    T* tiles = reinterpret_cast<T*>(gram_smem);                  // [stage][3][TE]
+    T* tiles = reinterpret_cast<T*>(gram_smem);                  // [stage][NT][TE]
     __shared__ __align__(8) uint64_t full_bar[kGramStages];
     __shared__ double s_red[kGramMaxWarps][ROUNDS * kGramVals];
     __shared__ unsigned char s_slots[kMaxM];
@@ -110,8 +119,8 @@ __device__ __forceinline__ void gram_dots_body(const GramDotsArgs<T>& a, double*
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
     const bool with_v = a.v != nullptr, with_new = a.new_slot >= 0;
-    const T* snew = with_new ? a.S + (int64_t)a.new_slot * a.ld : nullptr;
-    const T* ynew = with_new ? a.Y + (int64_t)a.new_slot * a.ld : nullptr;
+    const T* snew = (with_new && !FORM) ? a.S + (int64_t)a.new_slot * a.ld : nullptr;
+    const T* ynew = (with_new && !FORM) ? a.Y + (int64_t)a.new_slot * a.ld : nullptr;
     const int64_t ntiles = (a.n + kGramTE - 1) / kGramTE;
     const int my_col = warp / a.split, my_part = warp % a.split;
     const int part_len = kGramTE / a.split;                        // elements of a tile handled by this warp
@@ -126,7 +135,7 @@ __device__ __forceinline__ void gram_dots_body(const GramDotsArgs<T>& a, double*
 
     // stage a tile of the right-hand vectors: TMA for full aligned tiles, guarded element loads for the tail
     auto stage_tile = [&](int64_t tile, int stage) {
-        T* dst = tiles + (size_t)stage * 3 * kGramTE;
+        T* dst = tiles + (size_t)stage * NT * kGramTE;
         const int64_t e0 = tile * kGramTE;
         const int64_t len = (a.n - e0 < kGramTE) ? (a.n - e0) : kGramTE;
         if (a.use_tma && len == kGramTE)
@@ -134,12 +143,23 @@ __device__ __forceinline__ void gram_dots_body(const GramDotsArgs<T>& a, double*
             if (tid == 0)
             {
                 const unsigned bytes = kGramTE * sizeof(T);
-                mbar_expect_tx(&full_bar[stage], bytes * ((with_v ? 1 : 0) + (with_new ? 2 : 0)));
-                if (with_v) tma_load_1d(dst, a.v + e0, bytes, &full_bar[stage]);
-                if (with_new)
+                if constexpr (FORM)
                 {
-                    tma_load_1d(dst + kGramTE, snew + e0, bytes, &full_bar[stage]);
-                    tma_load_1d(dst + 2 * kGramTE, ynew + e0, bytes, &full_bar[stage]);
+                    mbar_expect_tx(&full_bar[stage], bytes * 4);
+                    tma_load_1d(dst, a.v + e0, bytes, &full_bar[stage]);                   // g  (stays: v)
+                    tma_load_1d(dst + kGramTE, a.fx + e0, bytes, &full_bar[stage]);        // x  -> s
+                    tma_load_1d(dst + 2 * kGramTE, a.fgp + e0, bytes, &full_bar[stage]);   // gp -> y
+                    tma_load_1d(dst + 3 * kGramTE, a.fxp + e0, bytes, &full_bar[stage]);   // xp
+                }
+                else
+                {
+                    mbar_expect_tx(&full_bar[stage], bytes * ((with_v ? 1 : 0) + (with_new ? 2 : 0)));
+                    if (with_v) tma_load_1d(dst, a.v + e0, bytes, &full_bar[stage]);
+                    if (with_new)
+                    {
+                        tma_load_1d(dst + kGramTE, snew + e0, bytes, &full_bar[stage]);
+                        tma_load_1d(dst + 2 * kGramTE, ynew + e0, bytes, &full_bar[stage]);
+                    }
                 }
             }
         }
@@ -148,9 +168,22 @@ __device__ __forceinline__ void gram_dots_body(const GramDotsArgs<T>& a, double*
             for (int i = tid; i < kGramTE; i += nthreads)
             {
                 const bool ok = i < len;
-                dst[i] = (with_v && ok) ? a.v[e0 + i] : T(0);
-                dst[kGramTE + i] = (with_new && ok) ? snew[e0 + i] : T(0);
-                dst[2 * kGramTE + i] = (with_new && ok) ? ynew[e0 + i] : T(0);
+                if constexpr (FORM)
+                {
+                    const T gv = ok ? a.v[e0 + i] : T(0);
+                    const T sv = ok ? a.fx[e0 + i] - a.fxp[e0 + i] : T(0);
+                    const T yv = ok ? gv - a.fgp[e0 + i] : T(0);
+                    dst[i] = gv;
+                    dst[kGramTE + i] = sv;
+                    dst[2 * kGramTE + i] = yv;
+                    if (ok) { a.s_out[e0 + i] = sv; a.y_out[e0 + i] = yv; }
+                }
+                else
+                {
+                    dst[i] = (with_v && ok) ? a.v[e0 + i] : T(0);
+                    dst[kGramTE + i] = (with_new && ok) ? snew[e0 + i] : T(0);
+                    dst[2 * kGramTE + i] = (with_new && ok) ? ynew[e0 + i] : T(0);
+                }
             }
         }
     };
@@ -168,17 +201,50 @@ __device__ __forceinline__ void gram_dots_body(const GramDotsArgs<T>& a, double*
         if (next_tile < ntiles) stage_tile(next_tile, s);
 
     unsigned phase_bits = 0;  // one parity bit per stage
+    auto wait_tile = [&](int64_t tile, int st) {
+        if (tile_is_tma(tile))
+        {
+            mbar_wait(&full_bar[st], (phase_bits >> st) & 1u);
+            phase_bits ^= (1u << st);
+        }
+    };
+    // FORM: turn a landed TMA tile {g, x, gp, xp} into {g, s = x - xp, y = g - gp} in place and write s, y to the ring columns
+    // (tiles staged element by element were formed by stage_tile already)
+    auto form_tile = [&](int64_t tile, int st) {
+        if (!tile_is_tma(tile)) return;
+        T* t0 = tiles + (size_t)st * NT * kGramTE;
+        const int64_t e0f = tile * kGramTE;
+        for (int i = tid * 4; i < kGramTE; i += nthreads * 4)
+        {
+            Pack<T> ps, py;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+                ps.v[k] = t0[kGramTE + i + k] - t0[3 * kGramTE + i + k];
+                py.v[k] = t0[i + k] - t0[2 * kGramTE + i + k];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) { t0[kGramTE + i + k] = ps.v[k]; t0[2 * kGramTE + i + k] = py.v[k]; }
+            st_pack<Hint::Plain>(a.s_out + e0f + i, ps);
+            st_pack<Hint::Plain>(a.y_out + e0f + i, py);
+        }
+    };
+    if constexpr (FORM)
+    {
+        // the pair of the first tile is formed up front; every later tile is formed by the warps as they finish the dots of
+        // the tile before it, so that the column loads of slower warps keep HBM busy meanwhile
+        if ((int64_t)blockIdx.x < ntiles) { wait_tile(blockIdx.x, 0); form_tile(blockIdx.x, 0); }
+        __syncthreads();
+    }
     int stage = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
     {
-        if (tile_is_tma(tile))
+        if constexpr (!FORM)
         {
-            mbar_wait(&full_bar[stage], (phase_bits >> stage) & 1u);
-            phase_bits ^= (1u << stage);
+            if (tile_is_tma(tile)) wait_tile(tile, stage);
+            else __syncthreads();  // element-wise staged tile: make the stores visible
         }
-        else
-            __syncthreads();  // element-wise staged tile: make the stores visible
-        const T* vt = tiles + (size_t)stage * 3 * kGramTE;
+        const T* vt = tiles + (size_t)stage * NT * kGramTE;
         const T* snt = vt + kGramTE;
         const T* ynt = vt + 2 * kGramTE;
         const int64_t e0 = tile * kGramTE;
@@ -255,7 +321,13 @@ __device__ __forceinline__ void gram_dots_body(const GramDotsArgs<T>& a, double*
                 }
             }
         }
-        __syncthreads();  // everyone is done with this stage's tile
+        if constexpr (FORM)
+        {
+            const int64_t upcoming = tile + gridDim.x;
+            const int nstage = (stage + 1 == kGramStages) ? 0 : stage + 1;
+            if (upcoming < ntiles) { wait_tile(upcoming, nstage); form_tile(upcoming, nstage); }
+        }
+        __syncthreads();  // everyone is done with this stage's tile (and the next tile's pair is formed)
         if (next_tile < ntiles) stage_tile(next_tile, stage);
         next_tile += gridDim.x;
         stage = (stage + 1 == kGramStages) ? 0 : stage + 1;
@@ -304,6 +376,13 @@ template <class T, int ROUNDS>
 __global__ void __launch_bounds__(kGramMaxThreads, 1) k_gram_dots(GramDotsArgs<T> a, double* partials, unsigned* ticket, double* result, const XComm* xc, unsigned long long epoch)
 {
     gram_dots_body<T, ROUNDS>(a, partials, ticket, result, xc, epoch);
+}
+
+// "update + dots": forms the newest pair from (x, xp, g, gp) while it computes [S Y]'[g s_new y_new]  (see GramDotsArgs)
+template <class T, int ROUNDS>
+__global__ void __launch_bounds__(kGramMaxThreads, 1) k_pair_dots(GramDotsArgs<T> a, double* partials, unsigned* ticket, double* result, const XComm* xc, unsigned long long epoch)
+{
+    gram_dots_body<T, ROUNDS, true>(a, partials, ticket, result, xc, epoch);
 }
 
 // ---- the O(c^2) recursion on coefficients ---------------------------------------------------------------------

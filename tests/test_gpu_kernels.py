@@ -219,3 +219,92 @@ def test_dense_hessian_approximations(n, m, npairs):
                                          Yc.ctypes.data_as(dp) if npairs else None, inverse, out.ctypes.data_as(dp), err, 256)
         assert st == 0, err.value
         assert np.max(np.abs(out - ref)) <= 1e-9 * np.max(np.abs(ref))
+
+
+@pytest.mark.parametrize("n", [10, 2048, 2052, 100_003, (1 << 20) + 4])
+@pytest.mark.parametrize("m,prior", [(4, 0), (4, 1), (4, 4), (4, 6), (10, 3), (20, 25)])
+def test_fused_update_apply_Hv_matches_separate_calls(gpu_ctx, n, m, prior):
+    """lbfgs_b200_hist_update_apply_Hv (pair formed inside the dots pass) == hist_update followed by apply_Hv."""
+    rng = np.random.default_rng(1000 * m + prior + n)
+    ha, hb = lb.History(gpu_ctx, n, m), lb.History(gpu_ctx, n, m)
+    for _ in range(prior):
+        s = rng.standard_normal(n)
+        y = s + 0.1 * rng.standard_normal(n)
+        ds, dy = gpu_ctx.array(s), gpu_ctx.array(y)
+        ha.add(ds, dy)
+        hb.add(ds, dy)
+    xp, gp = rng.standard_normal(n), rng.standard_normal(n)
+    s = 0.3 * rng.standard_normal(n)
+    x, g = xp + s, gp + s + 0.1 * rng.standard_normal(n)
+    dx, dxp, dg, dgp = (gpu_ctx.array(v) for v in (x, xp, g, gp))
+    ra, rb_ = gpu_ctx.empty(n), gpu_ctx.empty(n)
+    acc_a, _, _ = ha.update(dx, dxp, dg, dgp)
+    dot_a = ha.apply_Hv(dg, -1.0, ra, lb.HV_GRAM, want_dot=True)
+    acc_b, dot_b = hb.update_apply_Hv(dx, dxp, dg, dgp, -1.0, rb_, lb.HV_GRAM)
+    assert acc_a and acc_b and ha.ncorr == hb.ncorr == min(prior + 1, m)
+    assert np.array_equal(ha.column("s", 0), hb.column("s", 0)) and np.array_equal(ha.column("y", 0), hb.column("y", 0))
+    assert np.array_equal(hb.column("s", 0), x - xp) and np.array_equal(hb.column("y", 0), g - gp)
+    ta, ysa, _ = ha.scalars()
+    tb, ysb, _ = hb.scalars()
+    assert abs(ta - tb) <= 1e-13 * abs(ta) and np.max(np.abs(ysa - ysb)) <= 1e-13 * np.max(np.abs(ysa))
+    va, vb = ra.get(), rb_.get()
+    assert np.max(np.abs(va - vb)) <= 1e-11 * (np.max(np.abs(va)) + 1e-300)
+    assert abs(dot_a - dot_b) <= 1e-11 * abs(dot_a)
+    # a second round on top (exercises the fold of the pair committed by the fused call)
+    x2 = x + 0.2 * rng.standard_normal(n)
+    g2 = g + (x2 - x) + 0.05 * rng.standard_normal(n)
+    dx2, dg2 = gpu_ctx.array(x2), gpu_ctx.array(g2)
+    ha.update(dx2, dx, dg2, dg)
+    dot_a = ha.apply_Hv(dg2, -1.0, ra, lb.HV_GRAM, want_dot=True)
+    _, dot_b = hb.update_apply_Hv(dx2, dx, dg2, dg, -1.0, rb_, lb.HV_GRAM)
+    va, vb = ra.get(), rb_.get()
+    assert np.max(np.abs(va - vb)) <= 1e-10 * (np.max(np.abs(va)) + 1e-300)
+    assert abs(dot_a - dot_b) <= 1e-10 * abs(dot_a)
+    # literal two-loop on the history built by the fused calls: an independent algorithm on the same ring
+    hb.apply_Hv(dg2, -1.0, ra, lb.HV_TWO_LOOP)
+    assert np.max(np.abs(ra.get() - vb)) <= 1e-10 * (np.max(np.abs(vb)) + 1e-300)
+
+
+@pytest.mark.parametrize("prior", [0, 2, 5])
+def test_fused_update_apply_Hv_rejected_pair_leaves_history_untouched(gpu_ctx, prior):
+    """y = 0 fails the curvature gate s'y > eps*y'y: the old history must answer (reference LBFGS.h:161-165)."""
+    n, m = 50_000, 4
+    rng = np.random.default_rng(prior)
+    h = lb.History(gpu_ctx, n, m)
+    for _ in range(prior):
+        s = rng.standard_normal(n)
+        ds, dy = gpu_ctx.array(s), gpu_ctx.array(s + 0.1 * rng.standard_normal(n))
+        h.add(ds, dy)
+    before = h.ncorr
+    xp, g = rng.standard_normal(n), rng.standard_normal(n)
+    dx, dxp, dg = gpu_ctx.array(xp + 0.1), gpu_ctx.array(xp), gpu_ctx.array(g)
+    res, ref = gpu_ctx.empty(n), gpu_ctx.empty(n)
+    acc, dot = h.update_apply_Hv(dx, dxp, dg, dg, -1.0, res, lb.HV_GRAM)
+    assert not acc and h.ncorr == before
+    h.apply_Hv(dg, -1.0, ref, lb.HV_TWO_LOOP)
+    r = ref.get()
+    assert np.max(np.abs(res.get() - r)) <= 1e-11 * np.max(np.abs(r))
+    assert abs(dot - np.dot(g, r)) <= 1e-10 * abs(np.dot(g, r))
+    # and the ring still accepts the next good pair
+    x2, g2 = xp + 0.3 * rng.standard_normal(n), None
+    g2 = g + (x2 - xp) * 1.5
+    acc, _ = h.update_apply_Hv(gpu_ctx.array(x2), dxp, gpu_ctx.array(g2), dg, -1.0, res, lb.HV_GRAM)
+    assert acc and h.ncorr == min(before + 1, m)
+
+
+def test_fused_update_apply_Hv_unaligned_falls_back(gpu_ctx):
+    n, m = 10_001, 3
+    rng = np.random.default_rng(2)
+    xp, gp = rng.standard_normal(n), rng.standard_normal(n)
+    x, g = xp + 0.1 * rng.standard_normal(n), gp + 0.2 * rng.standard_normal(n)
+    g = gp + (x - xp) * 2.0
+    outs = []
+    for off in (0, 1):
+        h = lb.History(gpu_ctx, n, m)
+        arrs = [lb.DeviceArray(gpu_ctx, v, offset_elems=off) for v in (x, xp, g, gp)]
+        res = lb.DeviceArray(gpu_ctx, None, np.float64, n, offset_elems=off)
+        acc, dot = h.update_apply_Hv(*arrs, -1.0, res, lb.HV_AUTO)
+        assert acc
+        outs.append((res.get(), dot))
+    assert np.max(np.abs(outs[0][0] - outs[1][0])) <= 1e-12 * np.max(np.abs(outs[0][0]))
+    assert abs(outs[0][1] - outs[1][1]) <= 1e-12 * abs(outs[0][1])
