@@ -290,7 +290,8 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as fh:
-            traffic = json.load(fh).get("apply_Hv_dram_bytes_per_call_c10_n1e7")
+            traffic = json.load(fh).get("apply_Hv_dram_bytes_per_call_c10_n1e7" if args.hv == "two_loop" else
+                                        "update_apply_Hv_dram_bytes_per_call_c10_n1e7")
 
     value = iters / dev_seconds
     line = {
@@ -299,16 +300,19 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "n": N_GLOBAL, "n_per_gpu": n_local, "m": M_HIST, "line_search": "MoreThuente",
                    "step": "one full minimize(): %d iterations, %d objective evaluations" % (niter, nfev),
-                   "apply_Hv": args.hv, "sharding": "n split over %d rank(s); reductions all-reduced %s" % (
+                   "apply_Hv": args.hv, "sharding": "single GPU, no collective" if world == 1 else
+                   "n split over %d ranks; reductions all-reduced %s" % (
                        world, "in-kernel over NVLink peer memory" if args.comm == "p2p" else "with ncclAllReduce"),
                    "l2": "inputs larger than L2 (S,Y = %.2f GB per GPU)" % (2 * 8 * n_local * (M_HIST + 1) / 1e9)},
         "clocks": clocks,
         "e2e": {"value": e2e_iters / e2e_seconds, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "apply_Hv (k_gram_dots + k_gram_solve + k_gram_combine)" if args.hv != "two_loop" else "apply_Hv (k_hv_stage x 2c+1)",
+        "roofline": {"kernel": "pair update + apply_Hv, fused (k_pair_dots + k_gram_combine)" if args.hv != "two_loop" else "apply_Hv (k_hv_stage x 2c+1)",
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes": "8*n*(4c+2) per call, c = pairs in the history at that call (SURVEY.md 8d)",
+                     "algorithmic_bytes": ("8*n*(4c+2) per apply_Hv call" if args.hv == "two_loop" else
+                                           "8*n*((4c+2) + 6) per fused call = SURVEY.md 8d's apply_Hv unit + its update unit (the update kernel no longer exists)")
+                                          + ", c = pairs in the history at that call",
                      "calls": hv_phase["calls"], "full_history": hv_full},
         "phase_ms_per_step": {k: v["ms"] / prof_steps for k, v in phases.items()},
         "solver_loop": "device-resident (one CUDA graph launch per minimize; conditional WHILE/IF nodes)" if resident else "host-driven",
