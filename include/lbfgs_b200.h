@@ -51,8 +51,11 @@ enum {
     LBFGS_B200_HV_AUTO = 0,      /* currently GRAM                                                             */
     LBFGS_B200_HV_TWO_LOOP = 1,  /* literal two-loop recursion, one fused AXPY+dot stage kernel per history column:
                                     (8c+4) n words of traffic, 2c+1 launches, 2c collectives when sharded      */
-    LBFGS_B200_HV_GRAM = 2       /* the same recursion carried out on 2c coefficients: two passes over S,Y,
+    LBFGS_B200_HV_GRAM = 2,      /* the same recursion carried out on 2c coefficients: two passes over S,Y,
                                     (4c+3) n words, 3 launches, 1 collective; differs from TWO_LOOP by rounding */
+    LBFGS_B200_HV_GRAM_UNFUSED = 3 /* GRAM, but hist_update_apply_Hv keeps the separate update kernel (s'y, y'y from
+                                    its own reduction): the exact arithmetic of the device-resident solve, kept so
+                                    that the two solver loops can be compared bit for bit                       */
 };
 
 /* ---------------------------------------------------------------- context, memory, communicator */

@@ -20,7 +20,7 @@ from . import build as _build
 PKG = os.path.dirname(os.path.abspath(__file__))
 
 OBJ_ROSENBROCK_PAIRED, OBJ_QUAD_SHIFT, OBJ_ROSENBROCK_CHAINED, OBJ_QUAD_TRIDIAG = 0, 1, 2, 3
-HV_AUTO, HV_TWO_LOOP, HV_GRAM = 0, 1, 2
+HV_AUTO, HV_TWO_LOOP, HV_GRAM, HV_GRAM_UNFUSED = 0, 1, 2, 3
 LINE_SEARCHES = {"Backtracking": 0, "Bracketing": 1, "NocedalWright": 2, "MoreThuente": 3}
 LBFGS_LINESEARCH_BACKTRACKING_ARMIJO = 1
 LBFGS_LINESEARCH_BACKTRACKING = 2

@@ -1355,7 +1355,7 @@ static lbfgs_b200_status do_hist_apply_Hv(lbfgs_b200_hist* h, const T* v, T a, T
     if (auto st = hist_check<T>(h)) return st;
     lbfgs_b200_ctx* ctx = h->ctx;
     REQUIRE(ctx, v && res && v != res, "apply_Hv: v/res NULL or aliased");
-    REQUIRE(ctx, algo >= LBFGS_B200_HV_AUTO && algo <= LBFGS_B200_HV_GRAM, "apply_Hv: unknown algorithm %d", algo);
+    REQUIRE(ctx, algo >= LBFGS_B200_HV_AUTO && algo <= LBFGS_B200_HV_GRAM_UNFUSED, "apply_Hv: unknown algorithm %d", algo);
     const bool gram = (algo != LBFGS_B200_HV_TWO_LOOP) && h->ncorr > 0;
     ProfSpan span(ctx, PH_APPLY_HV, double(sizeof(T)) * double(h->n) * (4.0 * h->ncorr + 2.0));
     lbfgs_b200_status st = gram ? hv_gram<T>(h, v, a, res, vdot_host != nullptr)
@@ -1382,8 +1382,8 @@ static lbfgs_b200_status do_hist_update_apply_Hv(lbfgs_b200_hist* h, const T* x,
     lbfgs_b200_ctx* ctx = h->ctx;
     REQUIRE(ctx, x && xp && g && gp && res, "update_apply_Hv: NULL vector");
     REQUIRE(ctx, res != g && res != x && res != xp && res != gp, "update_apply_Hv: res aliases an input");
-    REQUIRE(ctx, algo >= LBFGS_B200_HV_AUTO && algo <= LBFGS_B200_HV_GRAM, "update_apply_Hv: unknown algorithm %d", algo);
-    if (algo == LBFGS_B200_HV_TWO_LOOP || !all_aligned<T>({x, xp, g, gp}))
+    REQUIRE(ctx, algo >= LBFGS_B200_HV_AUTO && algo <= LBFGS_B200_HV_GRAM_UNFUSED, "update_apply_Hv: unknown algorithm %d", algo);
+    if (algo == LBFGS_B200_HV_TWO_LOOP || algo == LBFGS_B200_HV_GRAM_UNFUSED || !all_aligned<T>({x, xp, g, gp}))
     {
         if (auto st = do_hist_update<T>(h, x, xp, g, gp, eps, accepted_host, nullptr)) return st;
         return do_hist_apply_Hv<T>(h, g, a, res, algo, vdot_host);

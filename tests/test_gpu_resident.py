@@ -13,7 +13,9 @@ LS_NAMES = ["Backtracking", "Bracketing", "NocedalWright", "MoreThuente"]
 
 
 def both(objective, x0, prm, ls, dtype=np.float64, **kw):
-    host = lb.LBFGSSolver(prm, ls, dtype=dtype, resident=False).minimize(objective, x0, **kw)
+    # HV_GRAM_UNFUSED: the host-driven loop with the separate update kernel, i.e. the arithmetic the graph runs (the default
+    # host-driven loop forms the pair inside the dots pass and takes s'y, y'y from there -- equal up to rounding only)
+    host = lb.LBFGSSolver(prm, ls, dtype=dtype, resident=False, hv_algo=lb.HV_GRAM_UNFUSED).minimize(objective, x0, **kw)
     res = lb.LBFGSSolver(prm, ls, dtype=dtype, resident=True).minimize(objective, x0, **kw)
     return host, res
 
@@ -79,3 +81,17 @@ def test_resident_on_golden_cases(case):
     host, res = both(case["objective"], unhex(case["x0"]), prm, case["ls"], data0=d0, data1=d1)
     assert_identical(host, res)
     assert res["status"] == case["status"] and res["msg"] == case["msg"]
+
+
+@pytest.mark.parametrize("ls", LS_NAMES)
+def test_default_host_loop_agrees_with_resident_to_rounding(ls):
+    """The default host-driven loop forms the pair inside the dots pass (s'y, y'y summed in a different order than the update
+    kernel of the graph): same counts and fx within the parity tolerance on a well-conditioned run."""
+    n = 100000
+    prm = lb.LBFGSParam(m=10)
+    host = lb.LBFGSSolver(prm, ls, resident=False).minimize(lb.OBJ_ROSENBROCK_PAIRED, np.zeros(n))
+    res = lb.LBFGSSolver(prm, ls, resident=True).minimize(lb.OBJ_ROSENBROCK_PAIRED, np.zeros(n))
+    assert host["status"] == res["status"] == "ok"
+    assert (host["niter"], host["nfev"]) == (res["niter"], res["nfev"])
+    assert abs(host["fx"] - res["fx"]) <= 1e-10 * max(1.0, abs(res["fx"]))
+    assert np.max(np.abs(host["x"] - res["x"])) <= 1e-8
