@@ -99,3 +99,35 @@ extern "C" int bkldlt_solve_f64(int n, const double* a, int uplo, const double* 
     catch (const std::invalid_argument&) { return -1; }
     catch (const std::logic_error&) { return -2; }
 }
+
+// ---- option structs (include/LBFGSpp/Param.h): what() of check_param(), "" when the parameters are valid ---------------------
+#include "../../include/LBFGSpp/Param.h"
+
+extern "C" const char* param_check_message(int lbfgsb, int m, double epsilon, double epsilon_rel, int past, double delta, int max_iterations,
+                                           int linesearch, int max_submin, int max_linesearch, double min_step, double max_step, double ftol,
+                                           double wolfe)
+{
+    static thread_local std::string msg;
+    msg.clear();
+    try
+    {
+        if (lbfgsb)
+        {
+            LBFGSBParam<double> p;
+            p.m = m; p.epsilon = epsilon; p.epsilon_rel = epsilon_rel; p.past = past; p.delta = delta; p.max_iterations = max_iterations;
+            p.max_submin = max_submin; p.max_linesearch = max_linesearch; p.min_step = min_step; p.max_step = max_step; p.ftol = ftol;
+            p.wolfe = wolfe;
+            p.check_param();
+        }
+        else
+        {
+            LBFGSParam<double> p;
+            p.m = m; p.epsilon = epsilon; p.epsilon_rel = epsilon_rel; p.past = past; p.delta = delta; p.max_iterations = max_iterations;
+            p.linesearch = linesearch; p.max_linesearch = max_linesearch; p.min_step = min_step; p.max_step = max_step; p.ftol = ftol;
+            p.wolfe = wolfe;
+            p.check_param();
+        }
+    }
+    catch (const std::invalid_argument& e) { msg = e.what(); }
+    return msg.c_str();
+}

@@ -133,3 +133,46 @@ def test_bunch_kaufman_error_paths(harness):
     assert bk_solve(harness, np.eye(2), np.ones(2), probe=-1)[0] == -1
     assert bk_solve(harness, np.eye(2), np.ones(2), probe=-2)[0] == -2
     assert bk_solve(harness, np.zeros((3, 3)), np.ones(3))[0] == 2
+
+
+# ---- option structs (include/LBFGSpp/Param.h) ------------------------------------------------------------------------------
+PARAM_FIELDS = ("m", "epsilon", "epsilon_rel", "past", "delta", "max_iterations", "linesearch", "max_submin", "max_linesearch",
+                "min_step", "max_step", "ftol", "wolfe")
+BAD_PARAMS = [dict(m=0), dict(m=-3), dict(epsilon=-1e-9), dict(epsilon_rel=-1.0), dict(past=-1), dict(delta=-1e-3),
+              dict(max_iterations=-1), dict(linesearch=0), dict(linesearch=4), dict(max_linesearch=0), dict(min_step=-1.0),
+              dict(max_step=1e-30), dict(ftol=0.0), dict(ftol=0.5), dict(wolfe=1e-5), dict(wolfe=1.0), dict(max_submin=-1),
+              dict(m=0, epsilon=-1.0), dict(ftol=0.7, wolfe=0.6)]
+
+
+@pytest.mark.parametrize("lbfgsb", [False, True])
+def test_check_param_messages_equal_the_reference(harness, orc, lbfgsb):
+    """LBFGSParam / LBFGSBParam::check_param (reference Param.h:191-218, 350-376): same rule order, same messages; defaults valid."""
+    harness.param_check_message.restype = C.c_char_p
+    harness.param_check_message.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
+                                            C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
+    for bad in [dict()] + BAD_PARAMS:
+        if lbfgsb and "linesearch" in bad or not lbfgsb and "max_submin" in bad:
+            continue
+        p = orc.default_param(lbfgsb=lbfgsb, **bad)
+        got = harness.param_check_message(int(lbfgsb), *[getattr(p, f) for f in PARAM_FIELDS]).decode()
+        if lbfgsb:
+            r = orc.lbfgsb(po.OBJ_QUAD_SHIFT, np.zeros(4), -1.0, 1.0, p)
+        else:
+            r = orc.lbfgs(po.OBJ_QUAD_SHIFT, np.zeros(4), po.LS_BACKTRACKING, p)
+        expect = r["msg"] if r["status"] == "invalid_argument" else ""
+        assert got == expect, (bad, got, expect)
+        assert (got == "") == (not bad)
+
+
+def test_product_sources_never_reach_into_the_oracle():
+    """The checker is test infrastructure: nothing under include/ or lbfgspp_b200/ may include, link or load oracle/ files."""
+    offenders = []
+    for top in ("include", "lbfgspp_b200"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".h", ".hpp", ".cu", ".cuh", ".cpp", ".py")):
+                    for line in open(os.path.join(dirpath, f), errors="replace"):
+                        uses = any(tok in line for tok in ("#include", "import ", "CDLL", "dlopen", "sys.path", "-L", "-l:"))
+                        if uses and any(needle in line for needle in ("oracle", "libref_lbfgspp", "minieigen")):
+                            offenders.append((os.path.join(dirpath, f), line.strip()))
+    assert not offenders, offenders
