@@ -308,3 +308,32 @@ def test_fused_update_apply_Hv_unaligned_falls_back(gpu_ctx):
         outs.append((res.get(), dot))
     assert np.max(np.abs(outs[0][0] - outs[1][0])) <= 1e-12 * np.max(np.abs(outs[0][0]))
     assert abs(outs[0][1] - outs[1][1]) <= 1e-12 * abs(outs[0][1])
+
+
+@pytest.mark.parametrize("n", [2048, 20_000, 300_001])
+def test_fused_update_apply_Hv_float32(gpu_ctx, n):
+    """The fp32 instantiation of the pair-forming dots pass (TMA tiles of 2048 floats) against the separate calls."""
+    m, prior = 5, 7
+    rng = np.random.default_rng(n)
+    f32 = np.float32
+    ha, hb = lb.History(gpu_ctx, n, m, f32), lb.History(gpu_ctx, n, m, f32)
+    for _ in range(prior):
+        s = rng.standard_normal(n).astype(f32)
+        y = (s + 0.1 * rng.standard_normal(n)).astype(f32)
+        ds, dy = gpu_ctx.array(s), gpu_ctx.array(y)
+        ha.add(ds, dy)
+        hb.add(ds, dy)
+    xp, gp = rng.standard_normal(n).astype(f32), rng.standard_normal(n).astype(f32)
+    s = (0.3 * rng.standard_normal(n)).astype(f32)
+    x = (xp + s).astype(f32)
+    g = (gp + s + 0.1 * rng.standard_normal(n)).astype(f32)
+    dx, dxp, dg, dgp = (gpu_ctx.array(v) for v in (x, xp, g, gp))
+    ra, rb_ = gpu_ctx.empty(n, f32), gpu_ctx.empty(n, f32)
+    acc_a, _, _ = ha.update(dx, dxp, dg, dgp)
+    dot_a = ha.apply_Hv(dg, f32(-1.0), ra, lb.HV_GRAM, want_dot=True)
+    acc_b, dot_b = hb.update_apply_Hv(dx, dxp, dg, dgp, f32(-1.0), rb_, lb.HV_GRAM)
+    assert acc_a and acc_b and ha.ncorr == hb.ncorr == m
+    assert np.array_equal(hb.column("s", 0), x - xp) and np.array_equal(hb.column("y", 0), g - gp)
+    va, vb = ra.get(), rb_.get()
+    assert np.max(np.abs(va - vb)) <= 2e-4 * np.max(np.abs(va))
+    assert abs(dot_a - dot_b) <= 2e-4 * abs(dot_a)
