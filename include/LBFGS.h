@@ -10,8 +10,9 @@
 //   dg = m_grad.dot(m_drt)            LBFGS.h:123      comes out of the tail of apply_Hv (v.res)
 //   line search trials                LBFGS.h:127      one fused kernel per trial (built-in objectives)
 //   m_grad.norm(), x.norm()           LBFGS.h:130,137  by-products of the accepted trial's kernel
-//   s, y, gate, add_correction        LBFGS.h:159-162  one kernel, written straight into the ring slot
-//   apply_Hv(m_grad, -1, m_drt)       LBFGS.h:165      2c+1 fused stage kernels / Gram form / resident kernel
+//   s, y, gate, add_correction        LBFGS.h:159-162  formed inside the first apply_Hv pass, straight into the ring slot
+//   apply_Hv(m_grad, -1, m_drt)       LBFGS.h:165      Gram form: pair-forming dots + combination (2 kernels); or the
+//                                                      literal 2c+1 stage kernels; or the device-resident graph
 //
 // The objective is any callable `Scalar f(const Vector& x, Vector& grad)` working on device vectors (taken by
 // non-const reference, called once per trial, exactly like the reference).  Objectives that additionally offer
