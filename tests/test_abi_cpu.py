@@ -65,3 +65,17 @@ def test_no_cpu_fallback_solver_reports_runtime_error():
 
 def test_version_string():
     assert b"sm_100a" in lb.abi().lbfgs_b200_version()
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/lbfgs_b200.h in a C99 translation unit (-pedantic -Werror), linked against the library, run without a GPU."""
+    import subprocess
+    lb.build_all()
+    exe = str(tmp_path / "abi_is_plain_c")
+    libdir = os.path.join(ROOT, "lbfgspp_b200")
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", "abi_is_plain_c.c"), "-o", exe, "-L", libdir, "-l:liblbfgs_b200.so",
+                    "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode in (0, 3), (r.returncode, r.stdout, r.stderr)
+    assert "lbfgs" in r.stdout.lower()
