@@ -1,0 +1,286 @@
+// mock_abi.cpp -- TEST DOUBLE of the C ABI (include/lbfgs_b200.h) on host memory.  TEST INFRASTRUCTURE ONLY.
+//
+// Purpose: run the product's header-only front (include/LBFGS.h, LBFGSpp/*.h: the solver loop, the line-search drivers and
+// state machines, DeviceVector, the objective adapters, the host-functor compatibility mode) on a machine without a GPU, so
+// that tests/test_front_cpu.py can hold that host logic to the CPU checker bit for bit.  Every "device" pointer is a host
+// pointer; every sum is taken strictly left to right with the CPU checker's own routines (oracle/lbfgs_oracle.hpp), so any
+// difference from the checker is a difference in the front's logic, not in rounding.
+//
+// This is NOT a backend of the product: it lives under tests/, is linked only into tests/cpp/front_harness.so, ignores the
+// apply_Hv algorithm selector (always the literal recursion), has no device-resident solve, no communicator and no L-BFGS-B
+// entry points (those return an error).  The product library refuses to run without a CUDA device (tests/test_abi_cpu.py).
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/lbfgs_b200.h"
+#include "../../oracle/lbfgs_oracle.hpp"
+#include "../../oracle/objectives.hpp"
+
+struct lbfgs_b200_ctx
+{
+    std::string err;
+    uint64_t calls = 0;
+    int64_t index_offset = 0;
+};
+
+struct lbfgs_b200_hist
+{
+    lbfgs_b200_ctx* ctx;
+    int elem;
+    std::unique_ptr<orc::History<double> > h64;
+    std::unique_ptr<orc::History<float> > h32;
+    std::vector<double> s64, y64;
+    std::vector<float> s32, y32;
+    template <class T> orc::History<T>& get();
+    template <class T> std::vector<T>& sbuf();
+    template <class T> std::vector<T>& ybuf();
+};
+template <> orc::History<double>& lbfgs_b200_hist::get<double>() { return *h64; }
+template <> orc::History<float>& lbfgs_b200_hist::get<float>() { return *h32; }
+template <> std::vector<double>& lbfgs_b200_hist::sbuf<double>() { return s64; }
+template <> std::vector<float>& lbfgs_b200_hist::sbuf<float>() { return s32; }
+template <> std::vector<double>& lbfgs_b200_hist::ybuf<double>() { return y64; }
+template <> std::vector<float>& lbfgs_b200_hist::ybuf<float>() { return y32; }
+
+struct lbfgs_b200_box { int unused; };
+struct lbfgs_b200_solver { int unused; };
+
+namespace {
+
+std::string g_last_error;
+
+lbfgs_b200_status fail(lbfgs_b200_ctx* ctx, lbfgs_b200_status st, const char* what)
+{
+    (ctx ? ctx->err : g_last_error) = what;
+    return st;
+}
+lbfgs_b200_status unsupported(lbfgs_b200_ctx* ctx, const char* what)
+{
+    return fail(ctx, LBFGS_B200_ERR_INVALID, (std::string("test double: ") + what + " is not provided").c_str());
+}
+
+const orc::Blas1<double> kSeq64(ORC_SUM_SEQUENTIAL, 1);
+const orc::Blas1<float> kSeq32(ORC_SUM_SEQUENTIAL, 1);
+template <class T> const orc::Blas1<T>& seq();
+template <> const orc::Blas1<double>& seq<double>() { return kSeq64; }
+template <> const orc::Blas1<float>& seq<float>() { return kSeq32; }
+
+template <class T>
+lbfgs_b200_status do_objective(lbfgs_b200_ctx* ctx, int objective, const T* d0, const T* d1, int64_t n, const T* x, T* g, T* out4)
+{
+    if (!ctx || !x || !g || !out4 || n < 1) return fail(ctx, LBFGS_B200_ERR_INVALID, "objective: bad arguments");
+    if (objective == LBFGS_B200_OBJ_ROSENBROCK_PAIRED && n % 2) return fail(ctx, LBFGS_B200_ERR_INVALID, "paired Rosenbrock needs an even n");
+    ctx->calls++;
+    out4[0] = orc::evaluate<T>(objective, d0, d1, long(n), x, g);
+    out4[1] = T(0);
+    out4[2] = seq<T>().dot(g, g, long(n));
+    out4[3] = seq<T>().dot(x, x, long(n));
+    return LBFGS_B200_OK;
+}
+
+template <class T>
+lbfgs_b200_status do_trial(lbfgs_b200_ctx* ctx, int objective, const T* d0, const T* d1, int64_t n, const T* xp, const T* d, T step, T* x,
+                           T* g, T* out4)
+{
+    if (!ctx || !xp || !d || !x || !g || !out4 || n < 1) return fail(ctx, LBFGS_B200_ERR_INVALID, "trial: bad arguments");
+    for (int64_t i = 0; i < n; i++) x[i] = xp[i] + step * d[i];
+    if (auto st = do_objective<T>(ctx, objective, d0, d1, n, x, g, out4)) return st;
+    out4[1] = seq<T>().dot(g, d, long(n));
+    return LBFGS_B200_OK;
+}
+
+template <class T> lbfgs_b200_status check_hist(lbfgs_b200_hist* h)
+{
+    if (!h) return LBFGS_B200_ERR_INVALID;
+    if (h->elem != int(sizeof(T))) return fail(h->ctx, LBFGS_B200_ERR_INVALID, "history element size mismatch");
+    return LBFGS_B200_OK;
+}
+
+template <class T>
+lbfgs_b200_status do_update(lbfgs_b200_hist* h, const T* x, const T* xp, const T* g, const T* gp, T eps, int* accepted, T* sy_yy)
+{
+    if (auto st = check_hist<T>(h)) return st;
+    orc::History<T>& H = h->get<T>();
+    std::vector<T>& s = h->sbuf<T>();
+    std::vector<T>& y = h->ybuf<T>();
+    seq<T>().diff(s.data(), x, xp, H.n);
+    seq<T>().diff(y.data(), g, gp, H.n);
+    const T sy = seq<T>().dot(s.data(), y.data(), H.n), yy = seq<T>().sqnorm(y.data(), H.n);
+    const bool ok = sy > eps * yy;   // LBFGS.h:161
+    if (ok) H.add(s.data(), y.data());
+    if (accepted) *accepted = ok ? 1 : 0;
+    if (sy_yy) { sy_yy[0] = sy; sy_yy[1] = yy; }
+    h->ctx->calls++;
+    return LBFGS_B200_OK;
+}
+
+template <class T>
+lbfgs_b200_status do_apply_Hv(lbfgs_b200_hist* h, const T* v, T a, T* res, T* vdot)
+{
+    if (auto st = check_hist<T>(h)) return st;
+    if (!v || !res || v == res) return fail(h->ctx, LBFGS_B200_ERR_INVALID, "apply_Hv: v/res NULL or aliased");
+    orc::History<T>& H = h->get<T>();
+    H.apply_Hv(v, a, res);
+    if (vdot) *vdot = seq<T>().dot(v, res, H.n);
+    h->ctx->calls++;
+    return LBFGS_B200_OK;
+}
+
+template <class T> const void* column(const lbfgs_b200_hist* h, bool s, int age)
+{
+    orc::History<T>& H = const_cast<lbfgs_b200_hist*>(h)->get<T>();
+    if (age < 0 || age >= H.ncorr) return nullptr;
+    const int slot = ((H.ptr - 1 - age) % H.m + H.m) % H.m;
+    return s ? H.s_col(slot) : H.y_col(slot);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* lbfgs_b200_version(void) { return "lbfgs_b200 test double (host memory, sequential sums)"; }
+lbfgs_b200_status lbfgs_b200_ctx_create(lbfgs_b200_ctx** out, int, void*)
+{
+    if (!out) return fail(nullptr, LBFGS_B200_ERR_INVALID, "ctx_create: NULL out");
+    *out = new lbfgs_b200_ctx();
+    return LBFGS_B200_OK;
+}
+void lbfgs_b200_ctx_destroy(lbfgs_b200_ctx* ctx) { delete ctx; }
+const char* lbfgs_b200_last_error(const lbfgs_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+void* lbfgs_b200_stream(const lbfgs_b200_ctx*) { return nullptr; }
+int lbfgs_b200_sm_count(const lbfgs_b200_ctx*) { return 1; }
+uint64_t lbfgs_b200_launch_count(const lbfgs_b200_ctx* ctx) { return ctx ? ctx->calls : 0; }
+
+lbfgs_b200_status lbfgs_b200_malloc(lbfgs_b200_ctx* ctx, void** p, size_t bytes)
+{
+    if (!ctx || !p) return fail(ctx, LBFGS_B200_ERR_INVALID, "malloc: NULL argument");
+    *p = std::aligned_alloc(256, (bytes + 255) / 256 * 256 + 256);
+    return *p ? LBFGS_B200_OK : fail(ctx, LBFGS_B200_ERR_ALLOC, "out of memory");
+}
+lbfgs_b200_status lbfgs_b200_free(lbfgs_b200_ctx*, void* p) { std::free(p); return LBFGS_B200_OK; }
+lbfgs_b200_status lbfgs_b200_malloc_host(lbfgs_b200_ctx* ctx, void** p, size_t bytes) { return lbfgs_b200_malloc(ctx, p, bytes); }
+lbfgs_b200_status lbfgs_b200_free_host(lbfgs_b200_ctx*, void* p) { std::free(p); return LBFGS_B200_OK; }
+lbfgs_b200_status lbfgs_b200_memcpy_h2d(lbfgs_b200_ctx*, void* d, const void* s, size_t b) { std::memcpy(d, s, b); return LBFGS_B200_OK; }
+lbfgs_b200_status lbfgs_b200_memcpy_d2h(lbfgs_b200_ctx*, void* d, const void* s, size_t b) { std::memcpy(d, s, b); return LBFGS_B200_OK; }
+lbfgs_b200_status lbfgs_b200_memcpy_d2d(lbfgs_b200_ctx*, void* d, const void* s, size_t b) { std::memmove(d, s, b); return LBFGS_B200_OK; }
+lbfgs_b200_status lbfgs_b200_memset_zero(lbfgs_b200_ctx*, void* d, size_t b) { std::memset(d, 0, b); return LBFGS_B200_OK; }
+lbfgs_b200_status lbfgs_b200_sync(lbfgs_b200_ctx*) { return LBFGS_B200_OK; }
+lbfgs_b200_status lbfgs_b200_timer_start(lbfgs_b200_ctx*) { return LBFGS_B200_OK; }
+lbfgs_b200_status lbfgs_b200_timer_stop(lbfgs_b200_ctx*, float* ms) { if (ms) *ms = 0.f; return LBFGS_B200_OK; }
+lbfgs_b200_status lbfgs_b200_profile_enable(lbfgs_b200_ctx*, int) { return LBFGS_B200_OK; }
+lbfgs_b200_status lbfgs_b200_profile_read(lbfgs_b200_ctx*, int, double* ms, uint64_t* calls, int)
+{
+    if (ms) *ms = 0;
+    if (calls) *calls = 0;
+    return LBFGS_B200_OK;
+}
+lbfgs_b200_status lbfgs_b200_profile_bytes(lbfgs_b200_ctx*, int, double* b, int) { if (b) *b = 0; return LBFGS_B200_OK; }
+lbfgs_b200_status lbfgs_b200_set_index_offset(lbfgs_b200_ctx* ctx, int64_t off) { ctx->index_offset = off; return LBFGS_B200_OK; }
+lbfgs_b200_status lbfgs_b200_set_global_extent(lbfgs_b200_ctx* ctx, int64_t off, int64_t) { ctx->index_offset = off; return LBFGS_B200_OK; }
+lbfgs_b200_status lbfgs_b200_comm_unique_id(void*) { return unsupported(nullptr, "a communicator"); }
+lbfgs_b200_status lbfgs_b200_comm_init(lbfgs_b200_ctx* c, const void*, int, int) { return unsupported(c, "a communicator"); }
+int lbfgs_b200_comm_size(const lbfgs_b200_ctx*) { return 1; }
+lbfgs_b200_status lbfgs_b200_comm_p2p_export(lbfgs_b200_ctx* c, void*) { return unsupported(c, "a communicator"); }
+lbfgs_b200_status lbfgs_b200_comm_p2p_attach(lbfgs_b200_ctx* c, const void*, int, int) { return unsupported(c, "a communicator"); }
+
+#define MOCK_L1(T, SUF)                                                                                                          \
+    lbfgs_b200_status lbfgs_b200_dot_##SUF(lbfgs_b200_ctx* c, int64_t n, const T* a, const T* b, T* o)                           \
+    { c->calls++; *o = seq<T>().dot(a, b, long(n)); return LBFGS_B200_OK; }                                                      \
+    lbfgs_b200_status lbfgs_b200_dot3_##SUF(lbfgs_b200_ctx* c, int64_t n, const T* g, const T* d, const T* x, T* o)              \
+    { c->calls++; o[0] = seq<T>().dot(g, d, long(n)); o[1] = seq<T>().dot(g, g, long(n)); o[2] = seq<T>().dot(x, x, long(n)); return LBFGS_B200_OK; } \
+    lbfgs_b200_status lbfgs_b200_axpy_out_##SUF(lbfgs_b200_ctx* c, int64_t n, const T* a, T s, const T* b, T* o)                 \
+    { c->calls++; for (int64_t i = 0; i < n; i++) o[i] = a[i] + s * b[i]; return LBFGS_B200_OK; }                                \
+    lbfgs_b200_status lbfgs_b200_scale_out_##SUF(lbfgs_b200_ctx* c, int64_t n, T s, const T* a, T* o)                            \
+    { c->calls++; for (int64_t i = 0; i < n; i++) o[i] = s * a[i]; return LBFGS_B200_OK; }                                       \
+    lbfgs_b200_status lbfgs_b200_objective_##SUF(lbfgs_b200_ctx* c, int obj, const T* d0, const T* d1, int64_t n, const T* x, T* g, T* o4) \
+    { return do_objective<T>(c, obj, d0, d1, n, x, g, o4); }                                                                     \
+    lbfgs_b200_status lbfgs_b200_trial_##SUF(lbfgs_b200_ctx* c, int obj, const T* d0, const T* d1, int64_t n, const T* xp,       \
+                                             const T* d, T step, T* x, T* g, T* o4)                                              \
+    { return do_trial<T>(c, obj, d0, d1, n, xp, d, step, x, g, o4); }
+MOCK_L1(double, f64)
+MOCK_L1(float, f32)
+
+lbfgs_b200_status lbfgs_b200_hist_create(lbfgs_b200_ctx* ctx, lbfgs_b200_hist** out, int64_t n, int m, int elem)
+{
+    if (!ctx || !out || n < 1 || m < 1 || (elem != 4 && elem != 8)) return fail(ctx, LBFGS_B200_ERR_INVALID, "hist_create: bad arguments");
+    lbfgs_b200_hist* h = new lbfgs_b200_hist();
+    h->ctx = ctx;
+    h->elem = elem;
+    if (elem == 8) { h->h64.reset(new orc::History<double>(kSeq64)); h->h64->reset(long(n), m); h->s64.resize(n); h->y64.resize(n); }
+    else { h->h32.reset(new orc::History<float>(kSeq32)); h->h32->reset(long(n), m); h->s32.resize(n); h->y32.resize(n); }
+    *out = h;
+    return LBFGS_B200_OK;
+}
+void lbfgs_b200_hist_destroy(lbfgs_b200_hist* h) { delete h; }
+lbfgs_b200_status lbfgs_b200_hist_reset(lbfgs_b200_hist* h)
+{
+    if (!h) return LBFGS_B200_ERR_INVALID;
+    if (h->elem == 8) h->h64->reset(h->h64->n, h->h64->m);
+    else h->h32->reset(h->h32->n, h->h32->m);
+    return LBFGS_B200_OK;
+}
+int lbfgs_b200_hist_ncorr(const lbfgs_b200_hist* h) { return h->elem == 8 ? h->h64->ncorr : h->h32->ncorr; }
+int lbfgs_b200_hist_m(const lbfgs_b200_hist* h) { return h->elem == 8 ? h->h64->m : h->h32->m; }
+const void* lbfgs_b200_hist_s_col(const lbfgs_b200_hist* h, int age) { return h->elem == 8 ? column<double>(h, true, age) : column<float>(h, true, age); }
+const void* lbfgs_b200_hist_y_col(const lbfgs_b200_hist* h, int age) { return h->elem == 8 ? column<double>(h, false, age) : column<float>(h, false, age); }
+
+#define MOCK_HIST(T, SUF)                                                                                                        \
+    lbfgs_b200_status lbfgs_b200_hist_update_##SUF(lbfgs_b200_hist* h, const T* x, const T* xp, const T* g, const T* gp, T eps,  \
+                                                   int* acc, T* sy_yy) { return do_update<T>(h, x, xp, g, gp, eps, acc, sy_yy); } \
+    lbfgs_b200_status lbfgs_b200_hist_add_##SUF(lbfgs_b200_hist* h, const T* s, const T* y)                                      \
+    { if (auto st = check_hist<T>(h)) return st; h->get<T>().add(s, y); return LBFGS_B200_OK; }                                  \
+    lbfgs_b200_status lbfgs_b200_hist_apply_Hv_##SUF(lbfgs_b200_hist* h, const T* v, T a, T* res, int, T* vdot)                  \
+    { return do_apply_Hv<T>(h, v, a, res, vdot); }                                                                               \
+    lbfgs_b200_status lbfgs_b200_hist_update_apply_Hv_##SUF(lbfgs_b200_hist* h, const T* x, const T* xp, const T* g,             \
+                                                            const T* gp, T eps, T a, T* res, int, int* acc, T* vdot)             \
+    { if (auto st = do_update<T>(h, x, xp, g, gp, eps, acc, nullptr)) return st; return do_apply_Hv<T>(h, g, a, res, vdot); }    \
+    lbfgs_b200_status lbfgs_b200_hist_scalars_##SUF(lbfgs_b200_hist* h, T* th, T* ys, T* al)                                     \
+    {                                                                                                                            \
+        if (auto st = check_hist<T>(h)) return st;                                                                               \
+        orc::History<T>& H = h->get<T>();                                                                                        \
+        if (th) *th = H.theta;                                                                                                   \
+        for (int age = 0; age < H.ncorr; age++)                                                                                  \
+        {                                                                                                                        \
+            const int slot = ((H.ptr - 1 - age) % H.m + H.m) % H.m;                                                              \
+            if (ys) ys[age] = H.ys[slot];                                                                                        \
+            if (al) al[age] = H.alpha[slot];                                                                                     \
+        }                                                                                                                        \
+        return LBFGS_B200_OK;                                                                                                    \
+    }
+MOCK_HIST(double, f64)
+MOCK_HIST(float, f32)
+
+// ---- bound-constrained path and device-resident solve: not provided by the test double ---------------------------------------
+lbfgs_b200_status lbfgs_b200_box_create(lbfgs_b200_hist* h, lbfgs_b200_box**) { return unsupported(h ? h->ctx : nullptr, "the L-BFGS-B workspace"); }
+void lbfgs_b200_box_destroy(lbfgs_b200_box*) {}
+const void* lbfgs_b200_box_xcp(const lbfgs_b200_box*) { return nullptr; }
+const unsigned char* lbfgs_b200_box_classes(const lbfgs_b200_box*) { return nullptr; }
+void* lbfgs_b200_box_vector(lbfgs_b200_box*, int) { return nullptr; }
+#define MOCK_BOX(T, SUF)                                                                                                         \
+    lbfgs_b200_status lbfgs_b200_box_clamp_##SUF(lbfgs_b200_ctx* c, int64_t, T*, const T*, const T*) { return unsupported(c, "L-BFGS-B"); } \
+    lbfgs_b200_status lbfgs_b200_box_proj_grad_norm_##SUF(lbfgs_b200_ctx* c, int64_t, const T*, const T*, const T*, const T*, T*) { return unsupported(c, "L-BFGS-B"); } \
+    lbfgs_b200_status lbfgs_b200_box_dir_info_##SUF(lbfgs_b200_ctx* c, int64_t, const T*, const T*, const T*, const T*, const T*, T*) { return unsupported(c, "L-BFGS-B"); } \
+    lbfgs_b200_status lbfgs_b200_hist_wt_dot_##SUF(lbfgs_b200_hist* h, const T*, T*) { return unsupported(h->ctx, "L-BFGS-B"); } \
+    lbfgs_b200_status lbfgs_b200_hist_gram_##SUF(lbfgs_b200_hist* h, T*, T*, T*, T*, T*) { return unsupported(h->ctx, "L-BFGS-B"); } \
+    lbfgs_b200_status lbfgs_b200_hist_lincomb_##SUF(lbfgs_b200_hist* h, lbfgs_b200_box*, T, const T*, const T*, const unsigned char*, int, T*) { return unsupported(h->ctx, "L-BFGS-B"); } \
+    lbfgs_b200_status lbfgs_b200_hist_masked_gram_##SUF(lbfgs_b200_hist* h, lbfgs_b200_box*, const unsigned char*, int, T*) { return unsupported(h->ctx, "L-BFGS-B"); } \
+    lbfgs_b200_status lbfgs_b200_box_cauchy_breaks_##SUF(lbfgs_b200_box*, const T*, const T*, const T*, const T*, T*) { return unsupported(nullptr, "L-BFGS-B"); } \
+    lbfgs_b200_status lbfgs_b200_box_cauchy_sweep_##SUF(lbfgs_b200_box*, const T*, const T*, const T*, T, T, int64_t, int64_t, T*) { return unsupported(nullptr, "L-BFGS-B"); } \
+    lbfgs_b200_status lbfgs_b200_box_cauchy_build_##SUF(lbfgs_b200_box*, const T*, const T*, const T*, T, T, T*) { return unsupported(nullptr, "L-BFGS-B"); } \
+    lbfgs_b200_status lbfgs_b200_box_sub_step_##SUF(lbfgs_b200_box*, int, int, const T*, const T*, const T*, const T*, T*, T, T*) { return unsupported(nullptr, "L-BFGS-B"); }
+MOCK_BOX(double, f64)
+MOCK_BOX(float, f32)
+
+lbfgs_b200_status lbfgs_b200_solver_create(lbfgs_b200_ctx* c, int64_t, int, int, lbfgs_b200_solver**) { return unsupported(c, "the device-resident solve"); }
+void lbfgs_b200_solver_destroy(lbfgs_b200_solver*) {}
+const void* lbfgs_b200_solver_final_grad(const lbfgs_b200_solver*) { return nullptr; }
+lbfgs_b200_hist* lbfgs_b200_solver_history(lbfgs_b200_solver*) { return nullptr; }
+lbfgs_b200_status lbfgs_b200_solver_minimize_f64(lbfgs_b200_solver*, int, const double*, const double*, const lbfgs_b200_param*, int, double*,
+                                                 double*, long long, lbfgs_b200_outcome*) { return unsupported(nullptr, "the device-resident solve"); }
+lbfgs_b200_status lbfgs_b200_solver_minimize_f32(lbfgs_b200_solver*, int, const float*, const float*, const lbfgs_b200_param*, int, float*,
+                                                 double*, long long, lbfgs_b200_outcome*) { return unsupported(nullptr, "the device-resident solve"); }
+
+}  // extern "C"
