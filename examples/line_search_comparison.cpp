@@ -7,6 +7,7 @@
 #include <iostream>
 #include <random>
 #include <stdexcept>
+#include <string>
 #include <vector>
 
 #include <LBFGS.h>
@@ -21,10 +22,13 @@ static void validate_solution(const Vector& x)
         if (std::abs(v - 1.0) > 1e-4) throw std::runtime_error("Error is larger than 1e-4");
 }
 
+static int g_solver_loop = -1;   // -1: automatic (device-resident for built-in objectives up to n = 4e6), 0: host-driven, 1: resident
+
 template <template <class> class LS>
 static void run(const char* name, const LBFGSParam<double>& param, const std::vector<std::vector<double> >& starts)
 {
     LBFGSSolver<double, LS> solver(param);
+    if (g_solver_loop >= 0) solver.set_device_resident(g_solver_loop == 1);
     BuiltinObjective<double> fun(LBFGS_B200_OBJ_ROSENBROCK_PAIRED);
     long niter = 0;
     for (const std::vector<double>& x0 : starts)
@@ -40,6 +44,7 @@ static void run(const char* name, const LBFGSParam<double>& param, const std::ve
 int main(int argc, char** argv)
 {
     const int trials = argc > 1 ? std::atoi(argv[1]) : 32;
+    if (argc > 2) g_solver_loop = (std::string(argv[2]) == "resident") ? 1 : 0;   // usage: line_search_comparison [trials [host|resident]]
     LBFGSParam<double> param;
     param.linesearch = LBFGS_LINESEARCH_BACKTRACKING_STRONG_WOLFE;
     param.max_linesearch = 256;

@@ -7,8 +7,8 @@
 // difference from the checker is a difference in the front's logic, not in rounding.
 //
 // This is NOT a backend of the product: it lives under tests/, is linked only into tests/cpp/front_harness.so, ignores the
-// apply_Hv algorithm selector (always the literal recursion), has no device-resident solve, no communicator and no L-BFGS-B
-// entry points (those return an error).  The product library refuses to run without a CUDA device (tests/test_abi_cpu.py).
+// apply_Hv algorithm selector (always the literal recursion), has no device-resident solve, no communicator and none of the
+// L-BFGS-B workspace entry points (those return an error).  The product library refuses to run without a CUDA device (tests/test_abi_cpu.py).
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -137,6 +137,44 @@ template <class T> const void* column(const lbfgs_b200_hist* h, bool s, int age)
     return s ? H.s_col(slot) : H.y_col(slot);
 }
 
+// the c x c Gram blocks by age and W'v: shared by the dense B / H accessors (final_approx_hessian) and L-BFGS-B
+template <class T>
+lbfgs_b200_status do_gram(lbfgs_b200_hist* h, T* SY, T* SS, T* YY, T* ys, T* theta)
+{
+    if (auto st = check_hist<T>(h)) return st;
+    orc::History<T>& H = h->get<T>();
+    const int c = H.ncorr;
+    for (int i = 0; i < c; i++)
+    {
+        const T* si = static_cast<const T*>(column<T>(h, true, i));
+        const T* yi = static_cast<const T*>(column<T>(h, false, i));
+        for (int j = 0; j < c; j++)
+        {
+            const T* sj = static_cast<const T*>(column<T>(h, true, j));
+            const T* yj = static_cast<const T*>(column<T>(h, false, j));
+            if (SY) SY[i * c + j] = seq<T>().dot(si, yj, H.n);
+            if (SS) SS[i * c + j] = seq<T>().dot(si, sj, H.n);
+            if (YY) YY[i * c + j] = seq<T>().dot(yi, yj, H.n);
+        }
+        if (ys) ys[i] = H.ys[((H.ptr - 1 - i) % H.m + H.m) % H.m];
+    }
+    if (theta) *theta = H.theta;
+    return LBFGS_B200_OK;
+}
+template <class T>
+lbfgs_b200_status do_wt_dot(lbfgs_b200_hist* h, const T* v, T* raw)
+{
+    if (auto st = check_hist<T>(h)) return st;
+    orc::History<T>& H = h->get<T>();
+    const int c = H.ncorr;
+    for (int i = 0; i < c; i++)
+    {
+        raw[i] = seq<T>().dot(static_cast<const T*>(column<T>(h, false, i)), v, H.n);
+        raw[c + i] = seq<T>().dot(static_cast<const T*>(column<T>(h, true, i)), v, H.n);
+    }
+    return LBFGS_B200_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -263,8 +301,8 @@ void* lbfgs_b200_box_vector(lbfgs_b200_box*, int) { return nullptr; }
     lbfgs_b200_status lbfgs_b200_box_clamp_##SUF(lbfgs_b200_ctx* c, int64_t, T*, const T*, const T*) { return unsupported(c, "L-BFGS-B"); } \
     lbfgs_b200_status lbfgs_b200_box_proj_grad_norm_##SUF(lbfgs_b200_ctx* c, int64_t, const T*, const T*, const T*, const T*, T*) { return unsupported(c, "L-BFGS-B"); } \
     lbfgs_b200_status lbfgs_b200_box_dir_info_##SUF(lbfgs_b200_ctx* c, int64_t, const T*, const T*, const T*, const T*, const T*, T*) { return unsupported(c, "L-BFGS-B"); } \
-    lbfgs_b200_status lbfgs_b200_hist_wt_dot_##SUF(lbfgs_b200_hist* h, const T*, T*) { return unsupported(h->ctx, "L-BFGS-B"); } \
-    lbfgs_b200_status lbfgs_b200_hist_gram_##SUF(lbfgs_b200_hist* h, T*, T*, T*, T*, T*) { return unsupported(h->ctx, "L-BFGS-B"); } \
+    lbfgs_b200_status lbfgs_b200_hist_wt_dot_##SUF(lbfgs_b200_hist* h, const T* v, T* raw) { return do_wt_dot<T>(h, v, raw); }  \
+    lbfgs_b200_status lbfgs_b200_hist_gram_##SUF(lbfgs_b200_hist* h, T* sy, T* ss, T* yy, T* ys, T* th) { return do_gram<T>(h, sy, ss, yy, ys, th); } \
     lbfgs_b200_status lbfgs_b200_hist_lincomb_##SUF(lbfgs_b200_hist* h, lbfgs_b200_box*, T, const T*, const T*, const unsigned char*, int, T*) { return unsupported(h->ctx, "L-BFGS-B"); } \
     lbfgs_b200_status lbfgs_b200_hist_masked_gram_##SUF(lbfgs_b200_hist* h, lbfgs_b200_box*, const unsigned char*, int, T*) { return unsupported(h->ctx, "L-BFGS-B"); } \
     lbfgs_b200_status lbfgs_b200_box_cauchy_breaks_##SUF(lbfgs_b200_box*, const T*, const T*, const T*, const T*, T*) { return unsupported(nullptr, "L-BFGS-B"); } \

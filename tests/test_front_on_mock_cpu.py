@@ -123,3 +123,29 @@ def test_front_float32_equals_checker(front, orc):
         prm = lb.LBFGSParam()
         c = orc.lbfgs(po.OBJ_ROSENBROCK_PAIRED, np.zeros(10), LS[ls], cpu_param(orc, prm), dtype=np.float32)
         assert_same(run_front(front, lb.OBJ_ROSENBROCK_PAIRED, np.zeros(10), LS[ls], prm, dtype=np.float32), c, ls)
+
+
+# ---- the reference's example programs (examples/*.cpp) against the test double: host-functor compatibility mode, dense B / H ----
+@pytest.fixture(scope="module")
+def example_bins(tmp_path_factory):
+    out = tmp_path_factory.mktemp("examples_on_mock")
+    mock_o = str(out / "mock_abi.o")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wno-unknown-pragmas", "-c", "-o", mock_o,
+                    os.path.join(ROOT, "tests", "cpp", "mock_abi.cpp")], check=True)
+    bins = {}
+    for name in ("rosenbrock_host_functor", "quadratic_free_function", "line_search_comparison"):
+        exe = str(out / name)
+        subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                        os.path.join(ROOT, "examples", name + ".cpp"), mock_o], check=True)
+        bins[name] = exe
+    return bins
+
+
+def test_examples_run_on_the_test_double(example_bins):
+    """Same expectations as tests/test_gpu_examples.py (the reference's own self-checks), host logic only."""
+    r = subprocess.run([example_bins["quadratic_free_function"]], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.startswith("2 iterations"), r.stdout + r.stderr
+    r = subprocess.run([example_bins["rosenbrock_host_functor"]], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "iterations" in r.stdout and "max |B*H - I|" in r.stdout, r.stdout + r.stderr
+    r = subprocess.run([example_bins["line_search_comparison"], "12", "host"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "FAILED" not in r.stdout and r.stdout.count("LineSearchMoreThuente") == 12, r.stdout + r.stderr
