@@ -7,9 +7,13 @@
 // difference from the checker is a difference in the front's logic, not in rounding.
 //
 // This is NOT a backend of the product: it lives under tests/, is linked only into tests/cpp/front_harness.so, ignores the
-// apply_Hv algorithm selector (always the literal recursion), has no device-resident solve, no communicator and none of the
-// L-BFGS-B workspace entry points (those return an error).  The product library refuses to run without a CUDA device (tests/test_abi_cpu.py).
+// apply_Hv algorithm selector (always the literal recursion) and has no device-resident solve and no communicator (those return
+// an error).  The bound-constrained entry points restate the semantics of lbfgspp_b200/csrc/lbfgsb_kernels.cuh with plain loops
+// (the breakpoint sweep walks the sorted positions one by one and evaluates the same closed forms at every tie-group end).  The product library refuses to run without a CUDA device (tests/test_abi_cpu.py).
+#include <algorithm>
+#include <cmath>
 #include <cstdlib>
+#include <limits>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -45,7 +49,18 @@ template <> std::vector<float>& lbfgs_b200_hist::sbuf<float>() { return s32; }
 template <> std::vector<double>& lbfgs_b200_hist::ybuf<double>() { return y64; }
 template <> std::vector<float>& lbfgs_b200_hist::ybuf<float>() { return y32; }
 
-struct lbfgs_b200_box { int unused; };
+// workspace of the bound-constrained path: the n-vectors of lbfgsb_impl.cuh (LBFGS_B200_BOXV_* order) and the class bytes
+struct lbfgs_b200_box
+{
+    lbfgs_b200_hist* h;
+    int64_t n;
+    std::vector<unsigned char> cls;
+    std::vector<double> v64[10];
+    std::vector<float> v32[10];
+    template <class T> T* vec(int which);
+};
+template <> double* lbfgs_b200_box::vec<double>(int which) { return v64[which].data(); }
+template <> float* lbfgs_b200_box::vec<float>(int which) { return v32[which].data(); }
 struct lbfgs_b200_solver { int unused; };
 
 namespace {
@@ -175,6 +190,232 @@ lbfgs_b200_status do_wt_dot(lbfgs_b200_hist* h, const T* v, T* raw)
     return LBFGS_B200_OK;
 }
 
+// ---- bound-constrained primitives: the semantics of lbfgspp_b200/csrc/lbfgsb_kernels.cuh, one coordinate after the other ----------
+enum : unsigned char { CLS_FIXED = 1, CLS_ACT = 2, CLS_FREE = 4, SUB_L = 8, SUB_U = 16, SUB_P = 32 };
+enum { V_VECC = 0, V_VECY = 1, V_LAMBDA = 2, V_MU = 3, V_TMP = 4, V_TMP2 = 5, V_YFB = 6, V_DVEC = 7, V_BRK = 8, V_XCP = 9 };
+
+template <class T> lbfgs_b200_status check_box(lbfgs_b200_box* b)
+{
+    if (!b || !b->h) return LBFGS_B200_ERR_INVALID;
+    return check_hist<T>(b->h);
+}
+
+template <class T>
+lbfgs_b200_status do_lincomb(lbfgs_b200_hist* h, T a0, const T* v0, const T* coef, const unsigned char* cls, int mask, T* out)
+{
+    if (auto st = check_hist<T>(h)) return st;
+    orc::History<T>& H = h->get<T>();
+    const int c = H.ncorr;
+    for (long i = 0; i < H.n; i++)
+    {
+        if (cls && !(cls[i] & mask)) continue;
+        T r = v0 ? a0 * v0[i] : T(0);
+        for (int j = 0; j < c; j++) r += coef[j] * static_cast<const T*>(column<T>(h, false, j))[i];
+        for (int j = 0; j < c; j++) r += coef[c + j] * static_cast<const T*>(column<T>(h, true, j))[i];
+        out[i] = r;
+    }
+    return LBFGS_B200_OK;
+}
+
+template <class T>
+lbfgs_b200_status do_masked_gram(lbfgs_b200_hist* h, const unsigned char* cls, int mask, T* G)
+{
+    if (auto st = check_hist<T>(h)) return st;
+    orc::History<T>& H = h->get<T>();
+    const int c = H.ncorr, w = 2 * c;
+    std::vector<const T*> col(static_cast<size_t>(w));
+    for (int j = 0; j < c; j++) { col[j] = static_cast<const T*>(column<T>(h, false, j)); col[c + j] = static_cast<const T*>(column<T>(h, true, j)); }
+    for (int a = 0; a < w; a++)
+        for (int b = 0; b < w; b++)
+        {
+            T acc = T(0);
+            for (long i = 0; i < H.n; i++)
+                if (!cls || (cls[i] & mask)) acc += col[a][i] * col[b][i];
+            G[a * w + b] = acc;
+        }
+    return LBFGS_B200_OK;
+}
+
+template <class T>
+lbfgs_b200_status do_cauchy_breaks(lbfgs_b200_box* b, const T* x, const T* g, const T* lb, const T* ub, T* out5)
+{
+    if (auto st = check_box<T>(b)) return st;
+    T* brk = b->vec<T>(V_BRK);
+    T* dvec = b->vec<T>(V_DVEC);
+    const T inf = std::numeric_limits<T>::infinity();
+    double nfixed = 0, ninf = 0, nord = 0;
+    T dd = T(0), tmin = inf;
+    for (int64_t i = 0; i < b->n; i++)
+    {
+        T t;
+        if (lb[i] == ub[i]) t = T(0);
+        else if (g[i] < T(0)) t = (x[i] - ub[i]) / g[i];
+        else if (g[i] > T(0)) t = (x[i] - lb[i]) / g[i];
+        else t = inf;
+        const bool zero = (t == T(0));
+        const T di = zero ? T(0) : -g[i];
+        brk[i] = t;
+        dvec[i] = di;
+        dd += di * di;
+        if (t == inf) { ninf += 1; b->cls[i] = CLS_FREE; }
+        else if (!zero) { nord += 1; tmin = std::min(tmin, t); b->cls[i] = 0; }
+        else { nfixed += 1; b->cls[i] = CLS_FIXED; }
+    }
+    out5[0] = T(nfixed); out5[1] = T(ninf); out5[2] = T(nord); out5[3] = dd; out5[4] = tmin;
+    return LBFGS_B200_OK;
+}
+
+template <class T>
+lbfgs_b200_status do_cauchy_sweep(lbfgs_b200_box* b, const T* g, const T* Mmat, const T* p0, T theta, T gt, int64_t nord, int64_t nfree_inf,
+                                  T* out)
+{
+    if (auto st = check_box<T>(b)) return st;
+    lbfgs_b200_hist* h = b->h;
+    orc::History<T>& H = h->get<T>();
+    const int c = H.ncorr, w = 2 * c;
+    const T* brk = b->vec<T>(V_BRK);
+    std::vector<int64_t> ord;
+    for (int64_t i = 0; i < b->n; i++)
+        if (b->cls[i] == 0) ord.push_back(i);
+    if (int64_t(ord.size()) != nord || nord < 1) return fail(h->ctx, LBFGS_B200_ERR_INVALID, "cauchy_sweep: nord does not match the classes");
+    std::sort(ord.begin(), ord.end(), [brk](int64_t a, int64_t bb) { return brk[a] < brk[bb] || (brk[a] == brk[bb] && a < bb); });
+    std::vector<const T*> ycol(static_cast<size_t>(c)), scol(static_cast<size_t>(c));
+    for (int j = 0; j < c; j++) { ycol[j] = static_cast<const T*>(column<T>(h, false, j)); scol[j] = static_cast<const T*>(column<T>(h, true, j)); }
+    // running prefix sums: G = sum g^2 ; A[2c] = sum g*w ; C[2c] = sum t*g*w  with w = (y_j[i], theta*s_j[i]) by age
+    T G = T(0);
+    std::vector<T> A(static_cast<size_t>(w), T(0)), Cc(static_cast<size_t>(w), T(0)), pvec(static_cast<size_t>(w)), cvec(static_cast<size_t>(w));
+    const T inf = std::numeric_limits<T>::infinity();
+    for (int64_t k = 0; k < nord; k++)
+    {
+        const int64_t i = ord[k];
+        const T gi = g[i], t = brk[i];
+        G += gi * gi;
+        for (int j = 0; j < c; j++)
+        {
+            const T wy = ycol[j][i], ws = theta * scol[j][i];
+            A[j] += gi * wy;
+            A[c + j] += gi * ws;
+            Cc[j] += t * gi * wy;
+            Cc[c + j] += t * gi * ws;
+        }
+        const bool last = (k + 1 == nord);
+        const T tnext = last ? inf : brk[ord[k + 1]];
+        if (!last && tnext == t) continue;   // not the end of its tie group
+        // quantities at the start of the segment that follows position k
+        const T rest = gt - G;
+        for (int q = 0; q < w; q++) { pvec[q] = p0[q] + A[q]; cvec[q] = t * pvec[q] - Cc[q]; }
+        T pMc = T(0), pMp = T(0);
+        for (int r = 0; r < w; r++)
+        {
+            T mc = T(0), mp = T(0);
+            for (int q = 0; q < w; q++) { mc += Mmat[r * w + q] * cvec[q]; mp += Mmat[r * w + q] * pvec[q]; }
+            pMc += pvec[r] * mc;
+            pMp += pvec[r] * mp;
+        }
+        const T fp = -rest * (T(1) - theta * t) - pMc;
+        const T fpp = theta * rest - pMp;
+        T dtmin = -fp / fpp;
+        const T dt = tnext - t;
+        const bool all_crossed = last && nfree_inf == 0;
+        if ((dtmin >= dt) && !all_crossed) continue;   // Cauchy.h:183: keep sweeping
+        const T eps = std::numeric_limits<T>::epsilon();
+        if (fpp < eps) dtmin = -fp / eps;
+        dtmin = std::max(dtmin, T(0));
+        if (all_crossed) dtmin = T(0);
+        out[0] = t; out[1] = t + dtmin; out[2] = fp; out[3] = fpp; out[4] = all_crossed ? T(1) : T(0);
+        for (int q = 0; q < w; q++) out[5 + q] = cvec[q] + dtmin * pvec[q];
+        return LBFGS_B200_OK;
+    }
+    return fail(h->ctx, LBFGS_B200_ERR_INVALID, "cauchy sweep found no segment (internal error)");
+}
+
+template <class T>
+lbfgs_b200_status do_cauchy_build(lbfgs_b200_box* b, const T* x, const T* lb, const T* ub, T t_cross, T tfinal, T* counts2)
+{
+    if (auto st = check_box<T>(b)) return st;
+    const T* brk = b->vec<T>(V_BRK);
+    const T* dvec = b->vec<T>(V_DVEC);
+    T* xcp = b->vec<T>(V_XCP);
+    double nact = 0, nfree = 0;
+    for (int64_t i = 0; i < b->n; i++)
+    {
+        const unsigned char c0 = b->cls[i];
+        T out = x[i];
+        unsigned char c1 = c0;
+        if (c0 != CLS_FIXED)
+        {
+            const bool crossed = (c0 != CLS_FREE) && (brk[i] <= t_cross);
+            if (crossed) { out = (dvec[i] > T(0)) ? ub[i] : lb[i]; c1 = CLS_ACT; nact += 1; }
+            else { out = x[i] + tfinal * dvec[i]; c1 = CLS_FREE; nfree += 1; }
+        }
+        xcp[i] = out;
+        b->cls[i] = c1;
+    }
+    counts2[0] = T(nact); counts2[1] = T(nfree);
+    return LBFGS_B200_OK;
+}
+
+template <class T>
+lbfgs_b200_status do_sub_step(lbfgs_b200_box* b, int op, int flag, const T* x0, const T* g, const T* lb, const T* ub, T* drt, T theta, T* out3)
+{
+    if (auto st = check_box<T>(b)) return st;
+    T *vecc = b->vec<T>(V_VECC), *vecy = b->vec<T>(V_VECY), *lambda = b->vec<T>(V_LAMBDA), *mu = b->vec<T>(V_MU), *tmp = b->vec<T>(V_TMP),
+      *tmp2 = b->vec<T>(V_TMP2), *yfb = b->vec<T>(V_YFB), *xcp = b->vec<T>(V_XCP);
+    double c0 = 0, c1 = 0, c2 = 0;
+    T dotacc = T(0);
+    for (int64_t i = 0; i < b->n; i++)
+    {
+        const unsigned char c = b->cls[i];
+        const bool is_free = (c & CLS_FREE) != 0;
+        switch (op)
+        {
+        case LBFGS_B200_SUB_INIT: drt[i] = xcp[i] - x0[i]; lambda[i] = mu[i] = vecc[i] = vecy[i] = T(0); break;
+        case LBFGS_B200_SUB_ACT_DIR: tmp[i] = (c & CLS_ACT) ? (xcp[i] - x0[i]) : T(0); break;
+        case LBFGS_B200_SUB_ADD_G: if (is_free) vecc[i] += g[i]; break;
+        case LBFGS_B200_SUB_NEG_C_FREE: tmp[i] = is_free ? -vecc[i] : T(0); break;
+        case LBFGS_B200_SUB_CHECK_BOUNDS:
+            if (is_free && (vecy[i] < lb[i] - x0[i] || vecy[i] > ub[i] - x0[i])) c0 += 1;
+            break;
+        case LBFGS_B200_SUB_CLASSIFY:
+            if (is_free)
+            {
+                const T l = lb[i] - x0[i], u = ub[i] - x0[i], y = vecy[i];
+                unsigned char nc = c & static_cast<unsigned char>(~(SUB_L | SUB_U | SUB_P));
+                if ((y < l) || (y == l && lambda[i] >= T(0))) { nc |= SUB_L; vecy[i] = l; mu[i] = T(0); c0 += 1; }
+                else if ((y > u) || (y == u && mu[i] >= T(0))) { nc |= SUB_U; vecy[i] = u; lambda[i] = T(0); c1 += 1; }
+                else { nc |= SUB_P; lambda[i] = T(0); mu[i] = T(0); c2 += 1; }
+                b->cls[i] = nc;
+            }
+            break;
+        case LBFGS_B200_SUB_LU_VEC: tmp[i] = (c & SUB_L) ? (lb[i] - x0[i]) : ((c & SUB_U) ? (ub[i] - x0[i]) : T(0)); break;
+        case LBFGS_B200_SUB_RHS_P: tmp[i] = (c & SUB_P) ? -(vecc[i] + (flag ? tmp2[i] : T(0))) : T(0); break;
+        case LBFGS_B200_SUB_FREE_VEC: tmp[i] = is_free ? vecy[i] : T(0); break;
+        case LBFGS_B200_SUB_MULTIPLIERS:
+            if (c & SUB_L) lambda[i] = tmp2[i] + vecc[i] + theta * vecy[i];
+            if (c & SUB_U) mu[i] = -(tmp2[i] + vecc[i] + theta * vecy[i]);
+            break;
+        case LBFGS_B200_SUB_CONVERGED:
+            if (is_free && (c & SUB_L) && lambda[i] < T(0)) c0 += 1;
+            if (is_free && (c & SUB_U) && mu[i] < T(0)) c1 += 1;
+            if (is_free && (c & SUB_P) && (vecy[i] < lb[i] - x0[i] || vecy[i] > ub[i] - x0[i])) c2 += 1;
+            break;
+        case LBFGS_B200_SUB_WRITE_DRT:
+            if (is_free)
+            {
+                T y = (flag & 2) ? yfb[i] : vecy[i];
+                if (flag & 1) y = std::min(std::max(y, lb[i] - x0[i]), ub[i] - x0[i]);
+                drt[i] = y;
+            }
+            dotacc += drt[i] * g[i];
+            break;
+        default: return fail(b->h->ctx, LBFGS_B200_ERR_INVALID, "box_sub_step: unknown op");
+        }
+    }
+    if (op == LBFGS_B200_SUB_WRITE_DRT) c0 = double(dotacc);
+    if (out3) { out3[0] = T(c0); out3[1] = T(c1); out3[2] = T(c2); }
+    return LBFGS_B200_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -291,27 +532,76 @@ const void* lbfgs_b200_hist_y_col(const lbfgs_b200_hist* h, int age) { return h-
 MOCK_HIST(double, f64)
 MOCK_HIST(float, f32)
 
-// ---- bound-constrained path and device-resident solve: not provided by the test double ---------------------------------------
-lbfgs_b200_status lbfgs_b200_box_create(lbfgs_b200_hist* h, lbfgs_b200_box**) { return unsupported(h ? h->ctx : nullptr, "the L-BFGS-B workspace"); }
-void lbfgs_b200_box_destroy(lbfgs_b200_box*) {}
-const void* lbfgs_b200_box_xcp(const lbfgs_b200_box*) { return nullptr; }
-const unsigned char* lbfgs_b200_box_classes(const lbfgs_b200_box*) { return nullptr; }
-void* lbfgs_b200_box_vector(lbfgs_b200_box*, int) { return nullptr; }
+// ---- bound-constrained path ---------------------------------------------------------------------------------------------------
+lbfgs_b200_status lbfgs_b200_box_create(lbfgs_b200_hist* h, lbfgs_b200_box** out)
+{
+    if (!h || !out) return LBFGS_B200_ERR_INVALID;
+    if (lbfgs_b200_hist_m(h) > 20) return fail(h->ctx, LBFGS_B200_ERR_INVALID, "the bound-constrained path supports m <= 20");
+    lbfgs_b200_box* b = new lbfgs_b200_box();
+    b->h = h;
+    b->n = h->elem == 8 ? h->h64->n : h->h32->n;
+    b->cls.assign(size_t(b->n), 0);
+    for (int k = 0; k < 10; k++)
+    {
+        if (h->elem == 8) b->v64[k].assign(size_t(b->n), 0.0);
+        else b->v32[k].assign(size_t(b->n), 0.f);
+    }
+    *out = b;
+    return LBFGS_B200_OK;
+}
+void lbfgs_b200_box_destroy(lbfgs_b200_box* b) { delete b; }
+const void* lbfgs_b200_box_xcp(const lbfgs_b200_box* b) { return lbfgs_b200_box_vector(const_cast<lbfgs_b200_box*>(b), V_XCP); }
+const unsigned char* lbfgs_b200_box_classes(const lbfgs_b200_box* b) { return b ? b->cls.data() : nullptr; }
+void* lbfgs_b200_box_vector(lbfgs_b200_box* b, int which)
+{
+    if (!b || which < 0 || which >= 10) return nullptr;
+    return b->h->elem == 8 ? static_cast<void*>(b->v64[which].data()) : static_cast<void*>(b->v32[which].data());
+}
 #define MOCK_BOX(T, SUF)                                                                                                         \
-    lbfgs_b200_status lbfgs_b200_box_clamp_##SUF(lbfgs_b200_ctx* c, int64_t, T*, const T*, const T*) { return unsupported(c, "L-BFGS-B"); } \
-    lbfgs_b200_status lbfgs_b200_box_proj_grad_norm_##SUF(lbfgs_b200_ctx* c, int64_t, const T*, const T*, const T*, const T*, T*) { return unsupported(c, "L-BFGS-B"); } \
-    lbfgs_b200_status lbfgs_b200_box_dir_info_##SUF(lbfgs_b200_ctx* c, int64_t, const T*, const T*, const T*, const T*, const T*, T*) { return unsupported(c, "L-BFGS-B"); } \
+    lbfgs_b200_status lbfgs_b200_box_clamp_##SUF(lbfgs_b200_ctx*, int64_t n, T* x, const T* lb, const T* ub)                     \
+    { for (int64_t i = 0; i < n; i++) x[i] = std::min(std::max(x[i], lb[i]), ub[i]); return LBFGS_B200_OK; }                     \
+    lbfgs_b200_status lbfgs_b200_box_proj_grad_norm_##SUF(lbfgs_b200_ctx*, int64_t n, const T* x, const T* g, const T* lb,       \
+                                                          const T* ub, T* o)                                                     \
+    {                                                                                                                            \
+        T m = T(0);                                                                                                              \
+        for (int64_t i = 0; i < n; i++) m = std::max(m, std::abs(std::min(std::max(x[i] - g[i], lb[i]), ub[i]) - x[i]));         \
+        *o = m;                                                                                                                  \
+        return LBFGS_B200_OK;                                                                                                    \
+    }                                                                                                                            \
+    lbfgs_b200_status lbfgs_b200_box_dir_info_##SUF(lbfgs_b200_ctx*, int64_t n, const T* x, const T* d, const T* g, const T* lb, \
+                                                    const T* ub, T* o2)                                                          \
+    {                                                                                                                            \
+        T dot = T(0), step = std::numeric_limits<T>::infinity();                                                                 \
+        for (int64_t i = 0; i < n; i++)                                                                                          \
+        {                                                                                                                        \
+            dot += g[i] * d[i];                                                                                                  \
+            if (d[i] > T(0)) step = std::min(step, (ub[i] - x[i]) / d[i]);                                                       \
+            else if (d[i] < T(0)) step = std::min(step, (lb[i] - x[i]) / d[i]);                                                  \
+        }                                                                                                                        \
+        o2[0] = dot; o2[1] = step;                                                                                               \
+        return LBFGS_B200_OK;                                                                                                    \
+    }                                                                                                                            \
     lbfgs_b200_status lbfgs_b200_hist_wt_dot_##SUF(lbfgs_b200_hist* h, const T* v, T* raw) { return do_wt_dot<T>(h, v, raw); }  \
     lbfgs_b200_status lbfgs_b200_hist_gram_##SUF(lbfgs_b200_hist* h, T* sy, T* ss, T* yy, T* ys, T* th) { return do_gram<T>(h, sy, ss, yy, ys, th); } \
-    lbfgs_b200_status lbfgs_b200_hist_lincomb_##SUF(lbfgs_b200_hist* h, lbfgs_b200_box*, T, const T*, const T*, const unsigned char*, int, T*) { return unsupported(h->ctx, "L-BFGS-B"); } \
-    lbfgs_b200_status lbfgs_b200_hist_masked_gram_##SUF(lbfgs_b200_hist* h, lbfgs_b200_box*, const unsigned char*, int, T*) { return unsupported(h->ctx, "L-BFGS-B"); } \
-    lbfgs_b200_status lbfgs_b200_box_cauchy_breaks_##SUF(lbfgs_b200_box*, const T*, const T*, const T*, const T*, T*) { return unsupported(nullptr, "L-BFGS-B"); } \
-    lbfgs_b200_status lbfgs_b200_box_cauchy_sweep_##SUF(lbfgs_b200_box*, const T*, const T*, const T*, T, T, int64_t, int64_t, T*) { return unsupported(nullptr, "L-BFGS-B"); } \
-    lbfgs_b200_status lbfgs_b200_box_cauchy_build_##SUF(lbfgs_b200_box*, const T*, const T*, const T*, T, T, T*) { return unsupported(nullptr, "L-BFGS-B"); } \
-    lbfgs_b200_status lbfgs_b200_box_sub_step_##SUF(lbfgs_b200_box*, int, int, const T*, const T*, const T*, const T*, T*, T, T*) { return unsupported(nullptr, "L-BFGS-B"); }
+    lbfgs_b200_status lbfgs_b200_hist_lincomb_##SUF(lbfgs_b200_hist* h, lbfgs_b200_box*, T a0, const T* v0, const T* coef,       \
+                                                    const unsigned char* cls, int mask, T* out)                                  \
+    { return do_lincomb<T>(h, a0, v0, coef, cls, mask, out); }                                                                   \
+    lbfgs_b200_status lbfgs_b200_hist_masked_gram_##SUF(lbfgs_b200_hist* h, lbfgs_b200_box*, const unsigned char* cls, int mask, T* G) \
+    { return do_masked_gram<T>(h, cls, mask, G); }                                                                               \
+    lbfgs_b200_status lbfgs_b200_box_cauchy_breaks_##SUF(lbfgs_b200_box* b, const T* x, const T* g, const T* lb, const T* ub, T* o5) \
+    { return do_cauchy_breaks<T>(b, x, g, lb, ub, o5); }                                                                         \
+    lbfgs_b200_status lbfgs_b200_box_cauchy_sweep_##SUF(lbfgs_b200_box* b, const T* g, const T* M, const T* p0, T theta, T gt,    \
+                                                        int64_t nord, int64_t ninf, T* out)                                      \
+    { return do_cauchy_sweep<T>(b, g, M, p0, theta, gt, nord, ninf, out); }                                                      \
+    lbfgs_b200_status lbfgs_b200_box_cauchy_build_##SUF(lbfgs_b200_box* b, const T* x, const T* lb, const T* ub, T tc, T tf, T* c2) \
+    { return do_cauchy_build<T>(b, x, lb, ub, tc, tf, c2); }                                                                     \
+    lbfgs_b200_status lbfgs_b200_box_sub_step_##SUF(lbfgs_b200_box* b, int op, int flag, const T* x0, const T* g, const T* lb,   \
+                                                    const T* ub, T* drt, T theta, T* o3)                                         \
+    { return do_sub_step<T>(b, op, flag, x0, g, lb, ub, drt, theta, o3); }
 MOCK_BOX(double, f64)
 MOCK_BOX(float, f32)
 
+// ---- device-resident solve: not provided by the test double ------------------------------------------------------------------------
 lbfgs_b200_status lbfgs_b200_solver_create(lbfgs_b200_ctx* c, int64_t, int, int, lbfgs_b200_solver**) { return unsupported(c, "the device-resident solve"); }
 void lbfgs_b200_solver_destroy(lbfgs_b200_solver*) {}
 const void* lbfgs_b200_solver_final_grad(const lbfgs_b200_solver*) { return nullptr; }

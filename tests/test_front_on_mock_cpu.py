@@ -149,3 +149,80 @@ def test_examples_run_on_the_test_double(example_bins):
     assert r.returncode == 0 and "iterations" in r.stdout and "max |B*H - I|" in r.stdout, r.stdout + r.stderr
     r = subprocess.run([example_bins["line_search_comparison"], "12", "host"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "FAILED" not in r.stdout and r.stdout.count("LineSearchMoreThuente") == 12, r.stdout + r.stderr
+
+
+# ---- the bound-constrained front (include/LBFGSB.h, LBFGSpp/{Cauchy,SubspaceMin,BFGSMat,BKLDLT}.h) on the test double -------------
+def run_front_box(lib, objective, x0, lbv, ubv, prm, data0=None, data1=None, cap=100000):
+    dp = C.POINTER(C.c_double)
+    lib.lbfgsb200_drv_lbfgsb_f64.argtypes = [C.c_int, C.c_int, dp, dp, C.c_long, C.POINTER(lb._DrvParam), dp, dp, dp, dp, dp, C.c_long,
+                                             C.POINTER(lb._DrvResult)]
+    ptr = lambda a: a.ctypes.data_as(dp) if a is not None else None
+    x = np.array(x0, dtype=np.float64).copy()
+    n = x.size
+    lbv = np.ascontiguousarray(np.broadcast_to(lbv, n), dtype=np.float64)
+    ubv = np.ascontiguousarray(np.broadcast_to(ubv, n), dtype=np.float64)
+    grad, trace, res = np.zeros(n), np.zeros(cap), lb._DrvResult()
+    d0 = None if data0 is None else np.ascontiguousarray(data0, dtype=np.float64)
+    d1 = None if data1 is None else np.ascontiguousarray(data1, dtype=np.float64)
+    p = prm._c()
+    lib.lbfgsb200_drv_lbfgsb_f64(0, objective, ptr(d0), ptr(d1), n, C.byref(p), ptr(x), ptr(lbv), ptr(ubv), ptr(grad), ptr(trace), cap,
+                                 C.byref(res))
+    return dict(status=STATUS[res.status], msg=res.msg.decode(), niter=res.niter, nfev=res.nfev, fx=res.fx, gnorm=res.gnorm, x=x,
+                grad=grad, trace=trace[:res.trace_len].copy())
+
+
+def check_box(f, c, lbv, ubv, iter_slack=0):
+    """The product's Cauchy sweep (prefix sums over sorted breakpoints) and BOXCQP algebra re-associate sums, so this is parity
+    to rounding, not bit for bit: same iterations, evaluations within one, fx to 1e-9, x to 1e-6 (the bar of the GPU tests)."""
+    assert f["status"] == c["status"], (f["status"], f["msg"], c["status"], c["msg"])
+    if c["status"] != "ok":
+        assert f["msg"].replace("lbfgs_b200: ", "") == c["msg"]
+        return
+    assert abs(f["niter"] - c["niter"]) <= iter_slack, (f["niter"], c["niter"])
+    assert abs(f["nfev"] - c["nfev"]) <= iter_slack + 1, (f["nfev"], c["nfev"])
+    assert abs(f["fx"] - c["fx"]) <= 1e-9 * max(1.0, abs(c["fx"])), (f["fx"], c["fx"])
+    assert np.max(np.abs(f["x"] - c["x"])) <= 1e-6 * max(1.0, np.max(np.abs(c["x"])))
+    # feasible up to the rounding of x = xp + step*drt: like the reference, the solver does not clamp the final iterate (LBFGSB.h:208-216
+    # return before force_bounds), and the checker shows the same <= 4e-16 excursions on these inputs
+    lo, hi = np.broadcast_to(lbv, f["x"].size), np.broadcast_to(ubv, f["x"].size)
+    slack = 4 * np.finfo(float).eps * np.maximum(1.0, np.abs(f["x"]))
+    assert np.all(f["x"] >= lo - slack) and np.all(f["x"] <= hi + slack)
+
+
+@pytest.mark.parametrize("case", golden_cases("lbfgsb"), ids=lambda c: c["name"])
+def test_box_front_on_golden_vectors(front, case):
+    prm = lb.LBFGSBParam(**case["param"])
+    lbv, ubv = unhex(case["lb"]), unhex(case["ub"])
+    f = run_front_box(front, case["objective"], unhex(case["x0"]), lbv, ubv, prm)
+    c = dict(status=case["status"], msg=case["msg"], niter=case["niter"], nfev=case["nfev"], fx=float.fromhex(case["fx"]), x=unhex(case["x"]))
+    check_box(f, c, lbv, ubv, iter_slack=0 if case["niter"] < 20 else 2)
+
+
+def test_box_front_equals_checker_on_random_boxes(front, orc):
+    rng = np.random.default_rng(8)
+    for obj in (po.OBJ_ROSENBROCK_CHAINED, po.OBJ_ROSENBROCK_PAIRED, po.OBJ_QUAD_SHIFT, po.OBJ_QUAD_TRIDIAG):
+        for n in (2, 4, 10, 26, 100, 1000):
+            for trial in range(5):
+                lo = rng.uniform(-2, 1, n)
+                hi = lo + rng.uniform(0.1, 3, n)
+                if trial == 0:
+                    lo[:], hi[:] = 2.0, 4.0
+                elif trial == 1:
+                    lo[:], hi[:] = -np.inf, np.inf
+                elif trial == 2:
+                    hi[::3] = lo[::3]
+                elif trial == 3:
+                    lo[::2], hi[1::3] = -np.inf, np.inf
+                x0 = rng.uniform(-3, 5, n)
+                d0, d1 = po.quad_tridiag_data(n, seed=trial)[:2] if obj == po.OBJ_QUAD_TRIDIAG else (None, None)
+                kw = dict(m=int(rng.choice([1, 3, 6, 10])), max_iterations=12, max_submin=int(rng.choice([0, 1, 10])))
+                c = orc.lbfgsb(obj, x0, lo, hi, orc.default_param(lbfgsb=True, **kw), data0=d0, data1=d1)
+                f = run_front_box(front, obj, x0, lo, hi, lb.LBFGSBParam(**kw), data0=d0, data1=d1)
+                # short runs (<= 12 iterations) keep the comparison in the regime where rounding has not yet moved the path
+                check_box(f, c, lo, hi)
+
+
+def test_box_front_parameter_and_size_errors(front, orc):
+    f = run_front_box(front, po.OBJ_QUAD_SHIFT, np.zeros(4), 0.0, 1.0, lb.LBFGSBParam(m=0))
+    c = orc.lbfgsb(po.OBJ_QUAD_SHIFT, np.zeros(4), 0.0, 1.0, orc.default_param(lbfgsb=True, m=0))
+    assert f["status"] == c["status"] == "invalid_argument" and f["msg"].replace("lbfgs_b200: ", "") == c["msg"]
