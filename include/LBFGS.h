@@ -118,7 +118,7 @@ private:
     LineSearchWorkspace<Scalar> m_ws;
     Scalar m_gnorm;
     long m_nfev;
-    // device-resident solve (built-in objectives): the whole minimize() is one CUDA graph launch
+    // device-resident solve (built-in objectives): the whole minimize() is one persistent kernel launch
     int m_resident;   // -1 automatic, 0 host-driven loop, 1 device-resident solve
     lbfgs_b200_solver* m_rsolver;
     Device* m_rdev;
@@ -149,6 +149,7 @@ private:
         lbfgs_b200_outcome out;
         dev.check(detail::resident_abi<Scalar>::minimize(m_rsolver, f.builtin_kind(), f.builtin_data0(), f.builtin_data1(), &p,
                                                          detail::line_search_id<LineSearch>::value, x.data(), m_trace, m_trace_cap, &out));
+        m_bfgs.borrow(dev, lbfgs_b200_solver_history(m_rsolver), n, m_param.m);   // final_approx_hessian() describes this solve
         f.add_calls(long(out.nfev));
         m_nfev = long(out.nfev);
         if (!m_grad.is_bound_to(dev)) m_grad = Vector(dev);
@@ -162,9 +163,12 @@ private:
     template <typename Foo>
     typename std::enable_if<detail::is_builtin_objective<Foo>::value, bool>::type try_resident(Foo& f, Vector& x, Scalar& fx, int& niter)
     {
-        // automatic: the graph's per-node latency (~3 us) beats host round trips for small and medium shards; for very long
-        // vectors both are noise next to the HBM time and the host-driven loop keeps the per-phase profiling hooks
-        const bool want = (m_resident == 1) || (m_resident == -1 && x.size() <= 4000000);
+        // automatic: built-in objectives run as ONE persistent kernel launch (no host round trip per trial, pair update and first
+        // trial fused into the two apply_Hv passes) unless the caller pinned another apply_Hv algorithm (the literal two-loop
+        // recursion or the unfused Gram form exist only in the host-driven loop)
+        const int algo = m_bfgs.algorithm();
+        const bool algo_ok = algo == LBFGS_B200_HV_AUTO || algo == LBFGS_B200_HV_GRAM;
+        const bool want = (m_resident == 1) || (m_resident == -1 && algo_ok);
         if (!want || m_param.past > 64) return false;
         niter = minimize_resident(f, x, fx);
         return true;
@@ -187,12 +191,15 @@ public:
     }
     ~LBFGSSolver() { lbfgs_b200_solver_destroy(m_rsolver); }
 
-    // Built-in objectives can be minimised by the device-resident solve (one CUDA graph launch, no host round trips, results
-    // bit-identical to the host-driven loop below).  Default: automatic (resident up to n = 4e6 per GPU).
+    // Built-in objectives can be minimised by the device-resident solve (one persistent kernel launch, no host round trips; same
+    // decisions as the host-driven loop below, sums re-associated).  Default: automatic (resident whenever the objective is built in).
     void set_device_resident(bool on) { m_resident = on ? 1 : 0; }
     void set_device_resident_auto() { m_resident = -1; }
     // resident solve only: record f of every evaluation into a host buffer (tests)
     void set_trace_buffer(double* host, long cap) { m_trace = host; m_trace_cap = cap; }
+    // the device-resident solver behind the last minimize() of a built-in objective (nullptr before the first one): accounting via
+    // lbfgs_b200_solver_profile()
+    lbfgs_b200_solver* resident_handle() const { return m_rsolver; }
 
     // apply_Hv implementation selector (LBFGS_B200_HV_*); not part of the reference API
     void set_hv_algorithm(int algo) { m_bfgs.set_algorithm(algo); }
@@ -237,6 +244,9 @@ public:
         int k = 1;
         for (;;)
         {
+            // the line search validates its inputs before it touches x (the reference throws from LineSearch() with x still the
+            // current point): run that validation before the buffers rotate
+            { typename LineSearch<Scalar>::Machine probe(m_param, fx, dg, step, m_param.max_step); (void)probe; }
             // the current point becomes the "previous" one: rotate buffers instead of copying
             m_xp.swap(x);
             m_gradp.swap(m_grad);

@@ -27,6 +27,7 @@ class BFGSMat
 
     Device* m_dev;
     lbfgs_b200_hist* m_hist;
+    bool m_owned;      // false: m_hist belongs to a device-resident solver (borrow())
     std::ptrdiff_t m_n;
     int m_m;
     int m_algo;  // LBFGS_B200_HV_*
@@ -35,11 +36,11 @@ class BFGSMat
     BFGSMat& operator=(const BFGSMat&);
 
 public:
-    BFGSMat() : m_dev(nullptr), m_hist(nullptr), m_n(0), m_m(0), m_algo(LBFGS_B200_HV_AUTO), m_theta_host(1), m_c_host(0), m_box(nullptr) {}
+    BFGSMat() : m_dev(nullptr), m_hist(nullptr), m_owned(true), m_n(0), m_m(0), m_algo(LBFGS_B200_HV_AUTO), m_theta_host(1), m_c_host(0), m_box(nullptr) {}
     ~BFGSMat()
     {
         lbfgs_b200_box_destroy(m_box);
-        lbfgs_b200_hist_destroy(m_hist);
+        if (m_owned) lbfgs_b200_hist_destroy(m_hist);
     }
 
     // Which apply_Hv implementation to run (LBFGS_B200_HV_AUTO picks by problem size).
@@ -50,12 +51,13 @@ public:
     // minimize() repeatedly does not reallocate 2*n*m words each time.
     void reset(Device& dev, std::ptrdiff_t n, int m)
     {
-        if (m_hist && (m_dev != &dev || m_n != n || m_m != m))
+        if (m_hist && (!m_owned || m_dev != &dev || m_n != n || m_m != m))
         {
             lbfgs_b200_box_destroy(m_box);
             m_box = nullptr;
-            lbfgs_b200_hist_destroy(m_hist);
+            if (m_owned) lbfgs_b200_hist_destroy(m_hist);
             m_hist = nullptr;
+            m_owned = true;
         }
         m_dev = &dev;
         m_n = n;
@@ -66,6 +68,24 @@ public:
             dev.check(lbfgs_b200_hist_reset(m_hist));
     }
     void reset(std::ptrdiff_t n, int m) { reset(Device::get_default(), n, m); }
+
+    // Look at a ring that somebody else owns (the device-resident solver's, after its minimize()): dense() and the Gram accessors
+    // then describe that solve's final approximation.  The ring must outlive this object's use of it.
+    void borrow(Device& dev, lbfgs_b200_hist* hist, std::ptrdiff_t n, int m)
+    {
+        lbfgs_b200_box_destroy(m_box);
+        m_box = nullptr;
+        if (m_owned) lbfgs_b200_hist_destroy(m_hist);
+        m_hist = hist;
+        m_owned = false;
+        m_dev = &dev;
+        m_n = n;
+        m_m = m;
+    }
+    void require_history() const
+    {
+        if (!m_hist || !m_dev) throw std::logic_error("BFGSMat: no history yet (minimize() has not run)");
+    }
 
     int num_corrections() const { return lbfgs_b200_hist_ncorr(m_hist); }
 
@@ -139,6 +159,7 @@ public:
     // Download the Gram blocks and rebuild Minv / M.  Call after reset() and after every accepted update().
     void refresh_middle()
     {
+        require_history();
         const int c = num_corrections();
         m_c_host = c;
         m_theta_host = Scalar(1);

@@ -240,11 +240,18 @@ LBFGS_B200_DECLARE_BOX(double, f64)
 LBFGS_B200_DECLARE_BOX(float, f32)
 
 /* ---------------------------------------------------------------- device-resident solve (built-in objectives)
- * LBFGSSolver<Scalar, LineSearch>::minimize() (reference LBFGS.h:78-173) as ONE CUDA graph launch: line-search state machine
- * (the cores of include/LBFGSpp/LineSearchCore.h), convergence tests, curvature gate and buffer rotation all run on the
- * device; conditional WHILE/IF graph nodes carry the control flow; the host is not involved between launch and completion.
- * Same kernels bodies, grids and reduction orders as the host-driven entry points: results are bit-identical to them.
- * When n is sharded the in-kernel NVLink exchange must be attached (lbfgs_b200_comm_p2p_*). */
+ * LBFGSSolver<Scalar, LineSearch>::minimize() (reference LBFGS.h:78-173) as ONE persistent cooperative kernel launch, for one problem
+ * or for a batch of B independent problems of the same shape (BASELINE config 5).  One CTA per SM stays resident for the whole
+ * solve; the work proceeds in rounds of one streaming pass per running problem (first evaluation / line-search trial /
+ * pair-forming dots [S Y]'[g s y] / combination d = -H g fused with the first trial of the next search) separated by one grid-wide
+ * synchronisation in which CTA 0 sums the CTAs' partial sums in a fixed order, exchanges them with the other ranks when n is
+ * sharded (ONE exchange per round for all running problems: a B-vector all-reduce per dot) and runs every problem's scalar logic:
+ * the line-search state machines (include/LBFGSpp/LineSearchCore.h, the code the host front uses), the convergence tests of
+ * LBFGS.h:137-154, the curvature gate of :161, the ring bookkeeping of BFGSMat.h:81-97 and the buffer rotation.  The host is not
+ * involved between launch and completion.  Reductions are deterministic and a problem's result does not depend on what else is
+ * in the batch: every problem of a batch is bit-identical to the same problem solved alone.
+ * When n is sharded the in-kernel NVLink exchange must be attached (lbfgs_b200_comm_p2p_*); neighbour-coupled objectives then
+ * also need lbfgs_b200_set_global_extent (their boundary coordinates travel with the sums). */
 typedef struct lbfgs_b200_solver lbfgs_b200_solver;
 typedef struct {             /* LBFGSParam (reference Param.h:67-219); doubles for both precisions */
     int m;
@@ -261,13 +268,27 @@ typedef struct {
     int niter;               /* return value of minimize()                                                          */
     long long nfev;          /* objective evaluations                                                               */
     double fx, gnorm;
+    long long rounds;        /* streaming passes (= grid-wide synchronisations) this problem took part in           */
 } lbfgs_b200_outcome;
 enum { LBFGS_B200_LS_BACKTRACKING = 0, LBFGS_B200_LS_BRACKETING = 1, LBFGS_B200_LS_NOCEDAL_WRIGHT = 2, LBFGS_B200_LS_MORE_THUENTE = 3 };
 
 lbfgs_b200_status lbfgs_b200_solver_create(lbfgs_b200_ctx* ctx, int64_t n, int m, int elem_bytes, lbfgs_b200_solver** out);
+/* batch problems of n coordinates each (n = this rank's block when sharded), all with history size m */
+lbfgs_b200_status lbfgs_b200_solver_create_batch(lbfgs_b200_ctx* ctx, int64_t n, int m, int elem_bytes, int batch, lbfgs_b200_solver** out);
 void lbfgs_b200_solver_destroy(lbfgs_b200_solver* s);
-const void* lbfgs_b200_solver_final_grad(const lbfgs_b200_solver* s);   /* device pointer, valid until the next minimize */
-lbfgs_b200_hist* lbfgs_b200_solver_history(lbfgs_b200_solver* s);       /* the S/Y ring the solver owns                  */
+int lbfgs_b200_solver_batch(const lbfgs_b200_solver* s);
+/* Accounting of the last solve.  kernel_ms: device time of the one kernel (CUDA events around its launch).  The arrays have 8 slots
+ * indexed by the pass a round ran: 0 = rounds in which the problems of a batch ran different passes, 1 FIRST, 2 TRIAL, 3 DOTS_FORM,
+ * 4 DOTS_PLAIN, 5 COMBINE, 6 COMBINE_TRIAL, 7 RESTORE.  ms_by_op8: the kernel's time split by round (CTA 0's cycle counter scaled
+ * to kernel_ms; includes each round's synchronisation); alg_bytes_by_op8: algorithmic bytes of those passes (whole vectors read and
+ * written: FIRST 3n, TRIAL 4n, DOTS_FORM (2c+4)n, DOTS_PLAIN (2c+1)n, COMBINE (2c+2)n, COMBINE_TRIAL (2c+5)n words, + the objective's
+ * data vectors per evaluation); sync_ms: the part of kernel_ms between CTA 0's arrival at a grid barrier and its release. */
+lbfgs_b200_status lbfgs_b200_solver_profile(const lbfgs_b200_solver* s, double* kernel_ms, double* ms_by_op8, unsigned long long* rounds_by_op8,
+                                            double* alg_bytes_by_op8, double* sync_ms);
+const void* lbfgs_b200_solver_final_grad(const lbfgs_b200_solver* s);   /* device pointer (problem 0), valid until the next minimize */
+const void* lbfgs_b200_solver_final_grad_of(const lbfgs_b200_solver* s, int problem);
+lbfgs_b200_hist* lbfgs_b200_solver_history(lbfgs_b200_solver* s);       /* the S/Y ring of problem 0 as left by the last solve   */
+lbfgs_b200_hist* lbfgs_b200_solver_history_of(lbfgs_b200_solver* s, int problem);
 /* x_inout: device vector (start point in, solution out).  trace_host (optional): f of every evaluation. */
 lbfgs_b200_status lbfgs_b200_solver_minimize_f64(lbfgs_b200_solver* s, int objective, const double* data0, const double* data1,
                                                  const lbfgs_b200_param* prm, int line_search, double* x_inout,
@@ -275,6 +296,14 @@ lbfgs_b200_status lbfgs_b200_solver_minimize_f64(lbfgs_b200_solver* s, int objec
 lbfgs_b200_status lbfgs_b200_solver_minimize_f32(lbfgs_b200_solver* s, int objective, const float* data0, const float* data1,
                                                  const lbfgs_b200_param* prm, int line_search, float* x_inout,
                                                  double* trace_host, long long trace_cap, lbfgs_b200_outcome* out);
+/* Batch: problem b starts from x_inout + b*ldx (device) and leaves its solution there; data0/data1 (optional) per problem at
+ * data + b*ldd (ldd = 0: shared by all problems); outs[batch]. */
+lbfgs_b200_status lbfgs_b200_solver_minimize_batch_f64(lbfgs_b200_solver* s, int objective, const double* data0, const double* data1,
+                                                       int64_t ldd, const lbfgs_b200_param* prm, int line_search, double* x_inout,
+                                                       int64_t ldx, lbfgs_b200_outcome* outs);
+lbfgs_b200_status lbfgs_b200_solver_minimize_batch_f32(lbfgs_b200_solver* s, int objective, const float* data0, const float* data1,
+                                                       int64_t ldd, const lbfgs_b200_param* prm, int line_search, float* x_inout,
+                                                       int64_t ldx, lbfgs_b200_outcome* outs);
 
 #ifdef __cplusplus
 }

@@ -107,6 +107,22 @@ def abi():
         getattr(lib, "lbfgs_b200_hist_apply_Hv_" + suf).argtypes = [vp, vp, ct, vp, ci, pt]
         getattr(lib, "lbfgs_b200_hist_update_apply_Hv_" + suf).argtypes = [vp, vp, vp, vp, vp, ct, ct, vp, ci, C.POINTER(ci), pt]
         getattr(lib, "lbfgs_b200_hist_scalars_" + suf).argtypes = [vp, pt, pt, pt]
+    # device-resident solve (persistent kernel; single problem or batch)
+    lib.lbfgs_b200_solver_create.argtypes = [vp, i64, ci, ci, C.POINTER(vp)]
+    lib.lbfgs_b200_solver_create_batch.argtypes = [vp, i64, ci, ci, ci, C.POINTER(vp)]
+    lib.lbfgs_b200_solver_destroy.argtypes = [vp]
+    lib.lbfgs_b200_solver_destroy.restype = None
+    lib.lbfgs_b200_solver_batch.argtypes = [vp]
+    lib.lbfgs_b200_solver_profile.argtypes = [vp, vp, vp, vp, vp, vp]
+    for name in ("lbfgs_b200_solver_final_grad", "lbfgs_b200_solver_history"):
+        getattr(lib, name).restype = vp
+        getattr(lib, name).argtypes = [vp]
+    for name in ("lbfgs_b200_solver_final_grad_of", "lbfgs_b200_solver_history_of"):
+        getattr(lib, name).restype = vp
+        getattr(lib, name).argtypes = [vp, ci]
+    for suf in ("f64", "f32"):
+        getattr(lib, "lbfgs_b200_solver_minimize_" + suf).argtypes = [vp, ci, vp, vp, vp, ci, vp, vp, C.c_longlong, vp]
+        getattr(lib, "lbfgs_b200_solver_minimize_batch_" + suf).argtypes = [vp, ci, vp, vp, i64, vp, ci, vp, i64, vp]
     lib._typed = True
     return lib
 
@@ -151,6 +167,11 @@ def driver():
     lib.lbfgsb200_drv_session_solve.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(_DrvResult)]
     lib.lbfgsb200_drv_session_result.restype = dp
     lib.lbfgsb200_drv_session_result.argtypes = [C.c_void_p]
+    lib.lbfgsb200_drv_batch_session_create.restype = C.c_void_p
+    lib.lbfgsb200_drv_batch_session_create.argtypes = [C.c_int, C.c_int, C.c_long, C.c_int, dp, C.c_int, C.POINTER(_DrvParam), C.c_char_p, C.c_int]
+    lib.lbfgsb200_drv_batch_session_destroy.argtypes = [C.c_void_p]
+    lib.lbfgsb200_drv_batch_session_destroy.restype = None
+    lib.lbfgsb200_drv_batch_session_solve.argtypes = [C.c_void_p, C.POINTER(_BatchItem), C.POINTER(C.c_long), dp, dp, C.c_char_p, C.c_int]
     lib.lbfgsb200_drv_comm_init.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_char_p, C.c_int]
     lib.lbfgsb200_drv_p2p_export.argtypes = [C.c_int, C.c_void_p, C.c_char_p, C.c_int]
     lib.lbfgsb200_drv_p2p_attach.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_char_p, C.c_int]
@@ -232,7 +253,7 @@ class LBFGSSolver:
         self.dtype = np.dtype(dtype)
         self.device = device
         self.hv_algo = hv_algo
-        self.fused = 2 if resident else fused   # 2: device-resident solve (one CUDA graph launch per minimize)
+        self.fused = 2 if resident else fused   # 2: device-resident solve (one persistent kernel launch per minimize)
 
     def minimize(self, objective, x0, data0=None, data1=None, trace_cap=100000, raise_errors=False, want_grad=True):
         drv = driver()
@@ -500,6 +521,19 @@ class Session:
         return dict(niter=res.niter, nfev=res.nfev, fx=res.fx, gnorm=res.gnorm, launches=res.launches,
                     h2d_bytes=res.h2d_bytes, d2h_bytes=res.d2h_bytes)
 
+    OPS = ("mixed", "first", "trial", "dots_form", "dots_plain", "combine", "combine_trial", "restore")
+
+    def profile(self):
+        """Accounting of the last device-resident solve: dict(kernel_ms, sync_ms, ops={name: dict(ms, rounds, alg_bytes)}); None for
+        the host-driven loop."""
+        ms, rounds, nbytes = (C.c_double * 8)(), (C.c_ulonglong * 8)(), (C.c_double * 8)()
+        kms, sync = C.c_double(0), C.c_double(0)
+        self.drv.lbfgsb200_drv_session_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+        if self.drv.lbfgsb200_drv_session_profile(self.h, C.byref(kms), ms, rounds, nbytes, C.byref(sync)):
+            return None
+        return dict(kernel_ms=kms.value, sync_ms=sync.value,
+                    ops={self.OPS[k]: dict(ms=ms[k], rounds=int(rounds[k]), alg_bytes=nbytes[k]) for k in range(8) if rounds[k]})
+
     def result(self):
         p = self.drv.lbfgsb200_drv_session_result(self.h)
         return np.ctypeslib.as_array(p, shape=(self.n,)).copy()
@@ -531,6 +565,44 @@ def solve_batch(objective, X0, param=None, linesearch="MoreThuente", device=0, h
                                 X.ctypes.data_as(dp) if return_x else None, C.byref(secs))
     res = [dict(status=STATUS_NAMES[it.status], niter=it.niter, nfev=it.nfev, fx=it.fx, gnorm=it.gnorm) for it in items]
     return res, X, secs.value
+
+
+class BatchSession:
+    """B independent problems (rows of X0) minimised by ONE persistent kernel launch per solve() (LBFGSpp::LBFGSBatchSolver,
+    include/LBFGSBatch.h).  The start points stay resident; with a communicator attached to the device's driver context the rows
+    are this rank's blocks of n-sharded problems."""
+
+    def __init__(self, objective, X0, param=None, linesearch="MoreThuente", device=0):
+        self.drv = driver()
+        X0 = np.ascontiguousarray(X0, dtype=np.float64)
+        self.B, self.n = X0.shape
+        param = param if param is not None else LBFGSParam()
+        p = param._c()
+        ls = LINE_SEARCHES[linesearch] if isinstance(linesearch, str) else int(linesearch)
+        err = C.create_string_buffer(256)
+        self.h = self.drv.lbfgsb200_drv_batch_session_create(device, objective, self.n, self.B, X0.ctypes.data_as(C.POINTER(C.c_double)), ls,
+                                                             C.byref(p), err, 256)
+        if not self.h:
+            raise RuntimeError("batch_session_create failed: " + err.value.decode())
+
+    def solve(self, return_x=True):
+        items = (_BatchItem * self.B)()
+        rounds = (C.c_long * self.B)()
+        X = np.empty((self.B, self.n)) if return_x else None
+        secs = C.c_double(0)
+        err = C.create_string_buffer(256)
+        bad = self.drv.lbfgsb200_drv_batch_session_solve(self.h, items, rounds, X.ctypes.data_as(C.POINTER(C.c_double)) if return_x else None,
+                                                         C.byref(secs), err, 256)
+        if bad < 0:
+            raise RuntimeError("batch solve failed: " + err.value.decode())
+        res = [dict(status=STATUS_NAMES[it.status], niter=it.niter, nfev=it.nfev, fx=it.fx, gnorm=it.gnorm, rounds=int(r))
+               for it, r in zip(items, rounds)]
+        return res, X, secs.value
+
+    def close(self):
+        if self.h:
+            self.drv.lbfgsb200_drv_batch_session_destroy(self.h)
+            self.h = None
 
 
 def driver_ctx(device=0):

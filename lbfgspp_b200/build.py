@@ -39,13 +39,26 @@ def _sources(*dirs, exts=(".cu", ".cuh", ".h", ".cpp", ".hpp")):
     return out
 
 
+KERNEL_UNITS = ["lbfgs_b200.cu", "persist_f64.cu", "persist_f32.cu"]   # compiled in parallel, linked into one library
+
+
 def build_kernels(force=False, verbose=False):
     srcs = _sources(CSRC, os.path.join(ROOT, "include"))
     if not force and _newer(LIB, srcs):
         return LIB
-    cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB, os.path.join(CSRC, "lbfgs_b200.cu"), "-lnccl"]
-    subprocess.run(cmd, check=True)
+    objdir = os.path.join(PKG, "build")
+    os.makedirs(objdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    procs, objs = [], []
+    for unit in KERNEL_UNITS:
+        obj = os.path.join(objdir, unit.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [NVCC] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, unit)]
+        procs.append((cmd, subprocess.Popen(cmd)))
+    for cmd, p in procs:
+        if p.wait() != 0:
+            raise subprocess.CalledProcessError(p.returncode, cmd)
+    subprocess.run([NVCC, "-shared", "-ccbin", CXX, "-o", LIB] + objs + ["-lnccl"], check=True)
     return LIB
 
 

@@ -12,6 +12,7 @@
 
 #include "../../include/LBFGS.h"
 #include "../../include/LBFGSB.h"
+#include "../../include/LBFGSBatch.h"
 #include "../../include/LBFGSpp/DeviceObjectives.h"
 
 using namespace LBFGSpp;
@@ -420,6 +421,24 @@ int lbfgsb200_drv_session_solve(void* handle, int from_host, int to_host, drv_re
 
 const double* lbfgsb200_drv_session_result(void* handle) { return static_cast<Session*>(handle)->pinned_out; }
 
+// accounting of the session's last device-resident solve (lbfgs_b200_solver_profile); returns 1 when the session runs the
+// host-driven loop
+int lbfgsb200_drv_session_profile(void* handle, double* kernel_ms, double* ms_by_op8, unsigned long long* rounds_by_op8, double* alg_bytes_by_op8,
+                                  double* sync_ms)
+{
+    Session* s = static_cast<Session*>(handle);
+    lbfgs_b200_solver* r = nullptr;
+    switch (s->ls)
+    {
+    case DRV_LS_BACKTRACKING: r = s->s_bt.resident_handle(); break;
+    case DRV_LS_BRACKETING: r = s->s_br.resident_handle(); break;
+    case DRV_LS_NOCEDAL_WRIGHT: r = s->s_nw.resident_handle(); break;
+    default: r = s->s_mt.resident_handle(); break;
+    }
+    if (!r) return 1;
+    return lbfgs_b200_solver_profile(r, kernel_ms, ms_by_op8, rounds_by_op8, alg_bytes_by_op8, sync_ms) == LBFGS_B200_OK ? 0 : 2;
+}
+
 }  // extern "C"
 
 extern "C" int lbfgsb200_drv_comm_init(int device_ordinal, const void* unique_id_128, int rank, int nranks, long long index_offset,
@@ -608,6 +627,7 @@ void batch_worker(int dev_ordinal, bool use_shared_device, int objective, long n
     typedef DeviceVector<double> Vector;
     std::unique_ptr<Device> own;
     Device* dev = nullptr;
+    int next = first;   // first item this worker has not finished yet
     try
     {
         if (use_shared_device) dev = &device(dev_ordinal);
@@ -634,11 +654,13 @@ void batch_worker(int dev_ordinal, bool use_shared_device, int objective, long n
             catch (const std::invalid_argument&) { it.status = 1; }
             catch (const std::logic_error&) { it.status = 2; }
             catch (const std::runtime_error&) { it.status = 3; }
+            catch (const std::exception&) { it.status = 4; }   // e.g. std::bad_alloc from a resize: this item only
+            next = b + stride;
         }
     }
     catch (...)
     {
-        for (int b = first; b < B; b += stride) items[b].status = 4;
+        for (int b = next; b < B; b += stride) items[b].status = 4;   // items already processed keep their outcome
     }
 }
 
@@ -672,6 +694,88 @@ extern "C" int lbfgsb200_drv_batch_f64(int device_ordinal, int objective, long n
     int bad = 0;
     for (int b = 0; b < B; b++) bad += items[b].status != 0;
     return bad;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// The same batch as ONE persistent kernel launch (LBFGSBatchSolver, include/LBFGSBatch.h): the start points stay
+// resident, solve() can be repeated (bench_batched.py), every problem bit-identical to a lone resident solve.
+// ----------------------------------------------------------------------------------------------------------
+namespace {
+struct BatchSession
+{
+    Device* dev;
+    long n;
+    int B, ls;
+    LBFGSParam<double> prm;
+    DeviceVector<double> X0, X;
+    BuiltinObjective<double> obj;
+    LBFGSBatchSolver<double, LineSearchBacktracking> s_bt;
+    LBFGSBatchSolver<double, LineSearchBracketing> s_br;
+    LBFGSBatchSolver<double, LineSearchNocedalWright> s_nw;
+    LBFGSBatchSolver<double, LineSearchMoreThuente> s_mt;
+    BatchSession(Device& d, long n_, int B_, int ls_, const drv_param* q, int objective) :
+        dev(&d), n(n_), B(B_), ls(ls_), prm(to_param<double>(q)), X0(d), X(d), obj(objective), s_bt(prm), s_br(prm), s_nw(prm), s_mt(prm) {}
+};
+}  // namespace
+
+extern "C" void* lbfgsb200_drv_batch_session_create(int device_ordinal, int objective, long n, int B, const double* x0s_host, int ls,
+                                                    const drv_param* prm, char* err, int errlen)
+{
+    try
+    {
+        Device& dev = device(device_ordinal);
+        std::unique_ptr<BatchSession> s(new BatchSession(dev, n, B, ls, prm, objective));
+        s->X0.copy_from_host(x0s_host, std::ptrdiff_t(n) * B);
+        s->X.resize(std::ptrdiff_t(n) * B);
+        return s.release();
+    }
+    catch (const std::exception& e)
+    {
+        if (err && errlen > 0) { std::strncpy(err, e.what(), size_t(errlen) - 1); err[errlen - 1] = 0; }
+        return nullptr;
+    }
+}
+extern "C" void lbfgsb200_drv_batch_session_destroy(void* handle) { delete static_cast<BatchSession*>(handle); }
+
+// One batched solve from the resident start points.  items[B]; rounds_out[B] (optional); seconds_out: host wall clock around the
+// synchronised call; xs_out_host (optional, B*n): the solutions.  Returns the number of problems that did not finish cleanly.
+extern "C" int lbfgsb200_drv_batch_session_solve(void* handle, drv_batch_item* items, long* rounds_out, double* xs_out_host, double* seconds_out,
+                                                 char* err, int errlen)
+{
+    BatchSession* s = static_cast<BatchSession*>(handle);
+    try
+    {
+        Device& dev = *s->dev;
+        dev.check(lbfgs_b200_memcpy_d2d(dev.ctx(), s->X.data(), s->X0.data(), sizeof(double) * size_t(s->n) * size_t(s->B)));
+        dev.synchronize();
+        const double t0 = now();
+        std::vector<BatchOutcome<double> > out;
+        switch (s->ls)
+        {
+        case DRV_LS_BACKTRACKING: out = s->s_bt.minimize(s->obj, s->X, s->B); break;
+        case DRV_LS_BRACKETING: out = s->s_br.minimize(s->obj, s->X, s->B); break;
+        case DRV_LS_NOCEDAL_WRIGHT: out = s->s_nw.minimize(s->obj, s->X, s->B); break;
+        default: out = s->s_mt.minimize(s->obj, s->X, s->B); break;
+        }
+        dev.synchronize();
+        if (seconds_out) *seconds_out = now() - t0;
+        int bad = 0;
+        for (int b = 0; b < s->B; b++)
+        {
+            const BatchOutcome<double>& o = out[size_t(b)];
+            items[b].status = o.status == 0 ? 0 : ls_error_kind(o.status);
+            items[b].niter = o.niter; items[b].nfev = o.nfev; items[b].fx = o.fx; items[b].gnorm = o.gnorm;
+            if (rounds_out) rounds_out[b] = o.rounds;
+            bad += o.status != 0;
+        }
+        if (xs_out_host) s->X.copy_to_host(xs_out_host);
+        return bad;
+    }
+    catch (const std::exception& e)
+    {
+        if (err && errlen > 0) { std::strncpy(err, e.what(), size_t(errlen) - 1); err[errlen - 1] = 0; }
+        return -1;
+    }
 }
 
 // dense B or H of an explicit history (test hook for final_approx_hessian / final_approx_inverse_hessian)

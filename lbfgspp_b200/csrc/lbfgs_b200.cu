@@ -10,127 +10,10 @@
 //   k_update          s = x-xp, y = g-gp -> ring slot ; {s.y, y.y}               [R 4 + W 2]
 //   k_hv_stage<KIND>  one fused AXPY+dot stage of the two-loop recursion         [R 3 + W 1]
 //   (k_gram_*, k_hv_resident live in two_loop_fast.cuh)
-#include <cuda_runtime.h>
-#include <nccl.h>
-
-#include <cstdarg>
-#include <cstdio>
-#include <cstring>
-#include <limits>
-#include <new>
-#include <atomic>
-#include <string>
-#include <vector>
-
-#include "../../include/lbfgs_b200.h"
-#include "device_utils.cuh"
-#include "objectives.cuh"
+#include "internal.cuh"
 #include "two_loop_gram.cuh"
 
 using namespace lb;
-
-// =====================================================================================================
-// context
-// =====================================================================================================
-struct lbfgs_b200_ctx
-{
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    int sm_count = 148;
-    int ctas_per_sm_cap = 8;       // streaming grids: at most this many CTAs per SM (tuning knob LBFGS_B200_CTAS_PER_SM, 1..8)
-    ReduceBuf rb{};                // device scratch for grid_reduce
-    double* h_result = nullptr;    // pinned mirror of rb.result (+ extra slots)
-    double* gram_partials = nullptr;  // [sm_count][kMaxM*kGramVals] block partials of k_gram_dots
-    double* gram_raw = nullptr;    // [kMaxM*kGramVals] reduced dots
-    int* d_flag = nullptr;         // device int flags (accepted, ...)
-    int* h_flag = nullptr;         // pinned
-    // mapped pinned mailbox: kernels publish host-bound scalars here (see deliver_to_host)
-    struct Mail { volatile unsigned long long word; int flag; int pad; double vals[kXMaxVals]; };
-    Mail* h_mail = nullptr;        // host view
-    Mail* d_mail = nullptr;        // device view of the same memory
-    unsigned long long mail_seq = 0;
-    unsigned smem_optin = 0;       // which k_gram_dots instantiations already have their shared-memory opt-in on this device
-    ncclComm_t comm = nullptr;
-    int rank = 0, nranks = 1;
-    // in-kernel exchange over peer memory (lbfgs_b200_comm_p2p_*): replaces the NCCL all-reduce when attached
-    XInbox* x_inbox = nullptr;          // this rank's inbox (cudaMalloc, exported through cudaIpc)
-    XComm* x_comm = nullptr;            // device copy of the peer table
-    void* x_peer[kXMaxRanks] = {};      // cudaIpcOpenMemHandle results (to close)
-    bool x_active = false;
-    unsigned long long x_epoch = 0;
-    int64_t index_offset = 0;      // global index of this rank's element 0
-    int64_t n_global = 0;          // global vector length (0 = not declared; needed only by neighbour-coupled objectives)
-    double* d_halo = nullptr;      // kHaloDoubles: boundary coordinates of this rank and of its two neighbours (objectives.cuh)
-    uint64_t launches = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    // optional per-phase device timing (lbfgs_b200_profile_*): event pairs recorded around each call
-    bool profiling = false;
-    struct Span { cudaEvent_t a, b; };
-    std::vector<Span> spans[3];   // recorded, not yet read
-    std::vector<Span> free_spans;
-    double prof_ms[3] = {0, 0, 0};
-    uint64_t prof_calls[3] = {0, 0, 0};
-    double prof_bytes[3] = {0, 0, 0};   // algorithmic bytes of the calls made while profiling
-    std::string err;
-};
-
-enum { PH_APPLY_HV = 0, PH_TRIAL = 1, PH_UPDATE = 2 };
-
-// RAII span: records an event pair on the context's stream around a C-ABI call when profiling is on
-struct ProfSpan
-{
-    lbfgs_b200_ctx* ctx;
-    int phase;
-    lbfgs_b200_ctx::Span sp{nullptr, nullptr};
-    ProfSpan(lbfgs_b200_ctx* c, int ph, double alg_bytes = 0.0) : ctx(c), phase(ph)
-    {
-        if (!ctx || !ctx->profiling) return;
-        ctx->prof_bytes[ph] += alg_bytes;
-        if (!ctx->free_spans.empty()) { sp = ctx->free_spans.back(); ctx->free_spans.pop_back(); }
-        else { cudaEventCreate(&sp.a); cudaEventCreate(&sp.b); }
-        cudaEventRecord(sp.a, ctx->stream);
-    }
-    void stop()
-    {
-        if (!sp.a) return;
-        cudaEventRecord(sp.b, ctx->stream);
-        ctx->spans[phase].push_back(sp);
-        sp.a = nullptr;
-    }
-    ~ProfSpan() { stop(); }
-};
-
-static thread_local std::string g_create_err;
-
-static lbfgs_b200_status fail(lbfgs_b200_ctx* ctx, lbfgs_b200_status st, const char* fmt, ...)
-{
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof(buf), fmt, ap);
-    va_end(ap);
-    if (ctx) ctx->err = buf; else g_create_err = buf;
-    return st;
-}
-
-#define CU(ctx, call)                                                                                      \
-    do {                                                                                                   \
-        cudaError_t e__ = (call);                                                                          \
-        if (e__ != cudaSuccess)                                                                            \
-            return fail(ctx, e__ == cudaErrorMemoryAllocation ? LBFGS_B200_ERR_ALLOC : LBFGS_B200_ERR_CUDA, \
-                        "%s failed: %s", #call, cudaGetErrorString(e__));                                  \
-    } while (0)
-
-#define NC(ctx, call)                                                                                      \
-    do {                                                                                                   \
-        ncclResult_t r__ = (call);                                                                         \
-        if (r__ != ncclSuccess)                                                                            \
-            return fail(ctx, LBFGS_B200_ERR_COMM, "%s failed: %s", #call, ncclGetErrorString(r__));        \
-    } while (0)
-
-#define REQUIRE(ctx, cond, ...)                                                                            \
-    do { if (!(cond)) return fail(ctx, LBFGS_B200_ERR_INVALID, __VA_ARGS__); } while (0)
 
 // grid for a streaming kernel over n elements: a multiple of the SM count, capped so that every CTA has
 // at least a few packs; 4 CTAs of 256 threads per SM are resident (register budget <= 64/thread).
@@ -411,24 +294,6 @@ template <class T> struct HistDev
     T* theta;     // [1]
 };
 
-struct lbfgs_b200_hist
-{
-    lbfgs_b200_ctx* ctx = nullptr;
-    int64_t n = 0, ld = 0;
-    int m = 0, M = 0, elem = 8;
-    void *S = nullptr, *Y = nullptr, *ys = nullptr, *alpha = nullptr, *theta = nullptr;
-    void* SY[2] = {nullptr, nullptr};  // Gram matrices [M][M] by physical slot, double-buffered (see k_gram_combine)
-    void* YY[2] = {nullptr, nullptr};
-    void* SS[2] = {nullptr, nullptr};
-    int gram_cur = 0;  // which buffer is current
-    int pending = -1;  // physical slot of the newest pair whose Gram row/column has not been folded in yet
-    int head = 0;   // physical slot the next pair is written to
-    int ncorr = 0;  // valid pairs (<= m)
-    // physical slot of the pair with the given age (0 = newest)
-    int slot(int age) const { return ((head - 1 - age) % M + M) % M; }
-    template <class T> T* s_col(int phys) const { return static_cast<T*>(S) + (int64_t)phys * ld; }
-    template <class T> T* y_col(int phys) const { return static_cast<T*>(Y) + (int64_t)phys * ld; }
-};
 
 // s = x - xp ; y = g - gp -> slot ; {s.y, y.y}
 template <class T, bool VEC>
@@ -1553,4 +1418,3 @@ DEFINE_HIST(float, f32)
 
 }  // extern "C"
 #include "lbfgsb_impl.cuh"
-#include "resident.cuh"

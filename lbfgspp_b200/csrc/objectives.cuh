@@ -27,6 +27,7 @@ constexpr int kHaloLeftA = 6, kHaloLeftB = 7, kHaloRightA = 8, kHaloRightB = 9;
 template <class T> struct RosenbrockPaired
 {
     static constexpr bool kHalo = false;
+    static constexpr int kDataVectors = 0;   // per-coordinate data vectors read by every evaluation
     int64_t n;
     __device__ __forceinline__ T eval(int64_t, int cnt, const T (&x)[4], T, T, T (&g)[4]) const
     {
@@ -52,6 +53,7 @@ template <class T> struct RosenbrockPaired
 template <class T> struct QuadShift
 {
     static constexpr bool kHalo = false;
+    static constexpr int kDataVectors = 0;
     int64_t n;
     int64_t index_offset;  // global index of local element 0 (n-sharding)
     __device__ __forceinline__ T eval(int64_t i0, int cnt, const T (&x)[4], T, T, T (&g)[4]) const
@@ -71,6 +73,7 @@ template <class T> struct QuadShift
 template <class T> struct RosenbrockChained
 {
     static constexpr bool kHalo = true;
+    static constexpr int kDataVectors = 0;
     int64_t n;             // local length
     int64_t gofs, n_glob;  // global index of local element 0, global length (gofs = 0, n_glob = n unsharded)
     const double* halo;
@@ -105,6 +108,7 @@ template <class T> struct RosenbrockChained
 template <class T> struct QuadTridiag
 {
     static constexpr bool kHalo = true;
+    static constexpr int kDataVectors = 2;
     int64_t n;
     const T* diag;  // d (this rank's block)
     const T* rhs;   // b

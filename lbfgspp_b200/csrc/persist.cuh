@@ -1,0 +1,1109 @@
+// persist.cuh -- the device-resident L-BFGS solve: LBFGSSolver::minimize() (reference LBFGS.h:78-173) for built-in objectives as
+// ONE persistent cooperative kernel launch, for one problem or for a batch of B independent problems (BASELINE config 5).
+// Included at the end of lbfgs_b200.cu.
+//
+// The kernel is a "phase machine".  One CTA per SM (768 threads), all co-resident (cooperative launch).  Work proceeds in ROUNDS;
+// in a round every problem that is still running executes the ONE streaming pass its state asks for:
+//     FIRST          g = grad f(x0), d = -g                      ; {f, g.g, x.x}                            LBFGS.h:91-108
+//     TRIAL          x = xp + step*d, g = grad f(x)              ; {f, g.d, g.g, x.x}                       LineSearch*.h trial, LBFGS.h:130,137
+//     DOTS_FORM      s = x - xp, y = g - gp -> free ring slot    ; [S Y]'[g s y] (6 dots per column pair)   LBFGS.h:159-162, BFGSMat.h:85-92 + apply_Hv pass 1
+//     DOTS_PLAIN     (pair rejected by the curvature gate)       ; [S Y]'g over the old history
+//     COMBINE        coefficient recursion (every CTA, shared memory) ; d = cv*g + sum cy_j y_j + cs_j s_j ; {g.d}   BFGSMat.h:283-301 in Gram form
+//     COMBINE_TRIAL  COMBINE + the first trial of the next line search in the same pass: the reference restarts every search
+//                    at step = 1 (LBFGS.h:168), so x1 = x + d, g1 = grad f(x1) ; {g.d, f1, g1.d, g1.g1, x1.x1}
+//     RESTORE        x = xp, g = gp (a search that never improved on its start point; LineSearchMoreThuente.h:602-614)
+// Every CTA owns the same contiguous chunk [t0, t1) of 2048-element tiles of EVERY vector in EVERY pass, so a CTA only ever reads
+// vector elements it wrote itself (halo coordinates excepted, those are read through L2).  Between rounds there is one grid-wide
+// synchronisation: CTAs deposit their partial sums in fixed slots, CTA 0 adds them in a fixed order (deterministic: no
+// floating-point atomics, result independent of which other problems are in flight), exchanges them with the other ranks when
+// n is sharded (ONE exchange per round carrying the sums of all running problems = "one all-reduce of a B-vector per dot"), and
+// runs each problem's scalar logic: line-search state machine (the cores of include/LBFGSpp/LineSearchCore.h, the same code the
+// host front uses), convergence tests (LBFGS.h:137-154), curvature gate (:161), ring bookkeeping (BFGSMat.h:81-97), buffer rotation
+// (pointer swaps).  The host is not involved between launch and completion: 1 launch per minimize(), 2 + (T - 1) rounds per
+// iteration with T line-search trials.
+#pragma once
+
+#include "../../include/LBFGSpp/LineSearchCore.h"
+
+namespace lb {
+
+constexpr int kMaxPast = 64;
+constexpr int kPThreads = kGramMaxThreads;   // 768: one CTA per SM
+constexpr int kPWarps = kPThreads / 32;
+
+enum { POP_IDLE = 0, POP_FIRST = 1, POP_TRIAL = 2, POP_DOTS_FORM = 3, POP_DOTS_PLAIN = 4, POP_COMBINE = 5, POP_COMBINE_TRIAL = 6, POP_RESTORE = 7 };
+
+// ---- per-problem state (device memory; written by the leader CTA only, read by everyone through L2) --------------------------
+template <class T> struct PState
+{
+    // vectors (rotate by pointer swap)
+    T *x, *xp, *g, *gp, *drt, *x_lo, *g_lo;
+    // history storage (fixed)
+    T *S, *Y, *ys, *alpha, *theta;
+    T *SY[2], *YY[2], *SS[2];
+    const T *data0, *data1;
+    double* raw;               // [pstride] reduced values of the last round
+    double* halo;              // kHaloDoubles (neighbour-coupled objectives under n-sharding)
+    // ring geometry
+    int head, ncorr, M, m, gram_cur, pending;
+    // what the next round does
+    int op, c_round;
+    // options (LBFGSParam)
+    T epsilon, epsilon_rel, delta, max_step, eps_gate;
+    int past, max_iterations, ls_kind, fuse_first_trial;
+    LBFGSpp::LineSearchOptions<T> ls_opt;
+    // line-search state
+    LBFGSpp::BacktrackingCore<T> bt;
+    LBFGSpp::BracketingCore<T> br;
+    LBFGSpp::NocedalWrightCore<T> nw;
+    LBFGSpp::MoreThuenteCore<T> mt;
+    int have_lo;
+    T lo_gg, lo_xx, start_gg, start_xx;
+    // iteration scalars
+    T fx, dg, gg, xx, gnorm, step;
+    int k;
+    long long nfev;
+    int status;     // 0 ok, otherwise a LineSearchError code
+    int finished;
+    int niter;      // return value of minimize()
+    T fx_hist[kMaxPast];
+    double* trace;              // optional: f of every evaluation
+    long long trace_cap;
+    long long rounds;           // rounds this problem took part in
+};
+
+struct PCtl
+{
+    unsigned arrive;            // grid barrier: arrivals so far (monotonic)
+    unsigned release;           // grid barrier: last round released by the leader
+    int abort;                  // watchdog tripped (a wait exceeded its budget): everybody leaves
+    int nactive;                // problems still running
+    unsigned long long epoch;   // cross-rank exchange sequence number (continues the context's)
+    unsigned long long rounds;
+    // accounting by CTA 0 (clock64 cycles of its SM): wall time of the rounds by the op they ran (bucket 0: rounds in which
+    // problems ran different ops), the part of it spent between CTA 0's own arrival and the release (waiting for the slowest
+    // CTA + the leader's work), and the algorithmic n-words of the passes (what the design has to move, see words_of)
+    long long cyc_op[8];
+    long long cyc_sync;
+    unsigned long long n_op[8];
+    double words_op[8];
+};
+
+template <class T> struct PArgs
+{
+    PState<T>* probs;
+    int B;
+    PCtl* ctl;
+    double* partials;           // [B][pstride][G]
+    int pstride;
+    int64_t n, ld;
+    const XComm* xc;
+    int64_t index_offset, n_global;
+};
+
+template <class V> __device__ __forceinline__ V ldv(const V* p) { return *reinterpret_cast<const volatile V*>(p); }
+
+template <class T> __device__ __forceinline__ T& ls_step_ref(PState<T>* st)
+{
+    switch (st->ls_kind)
+    {
+    case 0: return st->bt.step;
+    case 1: return st->br.step;
+    case 2: return st->nw.step;
+    default: return st->mt.step;
+    }
+}
+template <class T> __device__ __forceinline__ int ls_init(PState<T>* st, T fx, T dg, T step, T step_max)
+{
+    switch (st->ls_kind)
+    {
+    case 0: return st->bt.init(st->ls_opt, fx, dg, step, step_max);
+    case 1: return st->br.init(st->ls_opt, fx, dg, step, step_max);
+    case 2: return st->nw.init(st->ls_opt, fx, dg, step, step_max);
+    default: return st->mt.init(st->ls_opt, fx, dg, step, step_max);
+    }
+}
+template <class T> __device__ __forceinline__ int ls_advance(PState<T>* st, T fx, T dg, bool& keep)
+{
+    switch (st->ls_kind)
+    {
+    case 0: return st->bt.advance(fx, dg, keep);
+    case 1: return st->br.advance(fx, dg, keep);
+    case 2: return st->nw.advance(fx, dg, keep);
+    default: return st->mt.advance(fx, dg, keep);
+    }
+}
+template <class T> __device__ __forceinline__ void ls_best(PState<T>* st, T& fx, T& dg)
+{
+    switch (st->ls_kind)
+    {
+    case 0: fx = st->bt.best_fx; dg = st->bt.best_dg; break;
+    case 1: fx = st->br.best_fx; dg = st->br.best_dg; break;
+    case 2: fx = st->nw.best_fx; dg = st->nw.best_dg; break;
+    default: fx = st->mt.best_fx; dg = st->mt.best_dg; break;
+    }
+}
+template <class P> __device__ __forceinline__ void dswap(P& a, P& b) { P t = a; a = b; b = t; }
+__device__ __forceinline__ int slot_by_age(int head, int M, int age) { return ((head - 1 - age) % M + M) % M; }
+
+// ---- objectives as the persistent kernel builds them ------------------------------------------------------------------------
+template <class T, class OBJ> struct PObjMaker;
+template <class T> struct PObjMaker<T, RosenbrockPaired<T> >
+{ static __device__ RosenbrockPaired<T> make(const PArgs<T>& a, const T*, const T*, const double*) { return RosenbrockPaired<T>{a.n}; } };
+template <class T> struct PObjMaker<T, QuadShift<T> >
+{ static __device__ QuadShift<T> make(const PArgs<T>& a, const T*, const T*, const double*) { return QuadShift<T>{a.n, a.index_offset}; } };
+template <class T> struct PObjMaker<T, RosenbrockChained<T> >
+{ static __device__ RosenbrockChained<T> make(const PArgs<T>& a, const T*, const T*, const double* halo)
+  { return RosenbrockChained<T>{a.n, a.index_offset, a.n_global, halo}; } };
+template <class T> struct PObjMaker<T, QuadTridiag<T> >
+{ static __device__ QuadTridiag<T> make(const PArgs<T>& a, const T* d0, const T* d1, const double* halo)
+  { return QuadTridiag<T>{a.n, d0, d1, a.index_offset, a.n_global, halo}; } };
+
+// ---- shared memory of the kernel ----------------------------------------------------------------------------------------------
+struct PShared
+{
+    uint64_t full_bar[kGramStages];
+    double red[kPWarps][3 * kGramVals];     // block reduction scratch (dots: ROUNDS*6 values per warp)
+    unsigned char slots[kMaxM];
+    const void* ycol[kMaxM];
+    const void* scol[kMaxM];
+    int flag;
+};
+
+// this CTA's chunk of tiles: K = min(G, ntiles) CTAs share the tiles as evenly as whole tiles allow
+__device__ __forceinline__ void chunk_of(int64_t ntiles, int cta, int G, int64_t& t0, int64_t& t1)
+{
+    const int64_t K = ntiles < G ? ntiles : G;
+    if (cta >= K) { t0 = t1 = 0; return; }
+    t0 = (ntiles * cta) / K;
+    t1 = (ntiles * (cta + 1)) / K;
+}
+
+// block-wide sums of NV per-thread values -> dst[k * G] (this CTA's slot of value k).  All threads call.
+template <int NV> __device__ __forceinline__ void block_sums(const double (&acc)[NV], PShared& sh, double* dst, int G)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();   // sh.red may still be read from the previous use
+#pragma unroll
+    for (int k = 0; k < NV; k++)
+    {
+        const double w = warp_sum(acc[k]);
+        if (lane == 0) sh.red[warp][k] = w;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV)
+    {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kPWarps; w++) t += sh.red[w][threadIdx.x];
+        dst[(size_t)threadIdx.x * G] = t;
+    }
+}
+
+// ---- FIRST / TRIAL -------------------------------------------------------------------------------------------------------------
+// MODE 0: FIRST (evaluate at x, write g and d = -g) ; MODE 1: TRIAL (x = xp + step*d, write x and g)
+template <class T, class OBJ, int MODE>
+__device__ __forceinline__ void p_trial(const OBJ& obj, int64_t n, int64_t e0, int64_t e1, const T* __restrict__ xp, const T* __restrict__ d, T step,
+                                        T* __restrict__ x, T* __restrict__ g, T* __restrict__ dout, PShared& sh, double* dst, int G)
+{
+    T acc[4] = {T(0), T(0), T(0), T(0)};
+    const int64_t p1 = (e1 + 3) >> 2;
+#pragma unroll 2
+    for (int64_t p = (e0 >> 2) + threadIdx.x; p < p1; p += kPThreads)
+    {
+        const int64_t i0 = p << 2;
+        const int cnt = (n - i0 >= 4) ? 4 : int(n - i0);
+        T xv[4], dv[4] = {T(0), T(0), T(0), T(0)}, gv[4];
+        T xl = T(0), xr = T(0);
+        if (MODE == 1)
+        {
+            const Pack<T> px = load4<T, Hint::Stream, true>(xp, i0, cnt), pd = load4<T, Hint::Stream, true>(d, i0, cnt);
+#pragma unroll
+            for (int k = 0; k < 4; k++) { dv[k] = pd.v[k]; xv[k] = px.v[k] + step * pd.v[k]; }
+            if constexpr (OBJ::kHalo)
+            {
+                if (i0 > 0) xl = __ldcg(xp + i0 - 1) + step * __ldcg(d + i0 - 1);
+                else if (obj.halo && obj.gofs > 0) xl = T(ldv(obj.halo + kHaloLeftA)) + step * T(ldv(obj.halo + kHaloLeftB));
+                if (i0 + 4 < n) xr = __ldcg(xp + i0 + 4) + step * __ldcg(d + i0 + 4);
+                else if (obj.halo && i0 + 4 == n && obj.gofs + n < obj.n_glob) xr = T(ldv(obj.halo + kHaloRightA)) + step * T(ldv(obj.halo + kHaloRightB));
+            }
+        }
+        else
+        {
+            const Pack<T> px = load4<T, Hint::Stream, true>(x, i0, cnt);
+#pragma unroll
+            for (int k = 0; k < 4; k++) xv[k] = px.v[k];
+            if constexpr (OBJ::kHalo)
+            {
+                if (i0 > 0) xl = __ldcg(x + i0 - 1);
+                else if (obj.halo && obj.gofs > 0) xl = T(ldv(obj.halo + kHaloLeftA));
+                if (i0 + 4 < n) xr = __ldcg(x + i0 + 4);
+                else if (obj.halo && i0 + 4 == n && obj.gofs + n < obj.n_glob) xr = T(ldv(obj.halo + kHaloRightA));
+            }
+        }
+        acc[0] += obj.eval(i0, cnt, xv, xl, xr, gv);
+        Pack<T> pg, po;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            acc[1] += gv[k] * dv[k];
+            acc[2] += gv[k] * gv[k];
+            acc[3] += (k < cnt) ? xv[k] * xv[k] : T(0);
+            pg.v[k] = gv[k];
+            po.v[k] = (MODE == 1) ? xv[k] : T(-1) * gv[k];
+        }
+        if (MODE == 1) store4<T, Hint::Plain, true>(x, i0, cnt, po);
+        else store4<T, Hint::Plain, true>(dout, i0, cnt, po);
+        store4<T, Hint::Plain, true>(g, i0, cnt, pg);
+    }
+    const double dacc[4] = {(double)acc[0], (double)acc[1], (double)acc[2], (double)acc[3]};
+    block_sums<4>(dacc, sh, dst, G);
+}
+
+// ---- RESTORE --------------------------------------------------------------------------------------------------------------------
+template <class T>
+__device__ __forceinline__ void p_restore(int64_t n, int64_t e0, int64_t e1, const T* __restrict__ xp, const T* __restrict__ gp, T* __restrict__ x, T* __restrict__ g)
+{
+    const int64_t p1 = (e1 + 3) >> 2;
+    for (int64_t p = (e0 >> 2) + threadIdx.x; p < p1; p += kPThreads)
+    {
+        const int64_t i0 = p << 2;
+        const int cnt = (n - i0 >= 4) ? 4 : int(n - i0);
+        store4<T, Hint::Plain, true>(x, i0, cnt, load4<T, Hint::Stream, true>(xp, i0, cnt));
+        store4<T, Hint::Plain, true>(g, i0, cnt, load4<T, Hint::Stream, true>(gp, i0, cnt));
+    }
+}
+
+// ---- DOTS -----------------------------------------------------------------------------------------------------------------------
+// [S Y]'[v s_new y_new] over this CTA's tiles; FORM: the newest pair is formed on the fly from (x, xp, v = g, gp) into ring slot
+// `new_slot` and takes part as the newest column (see k_pair_dots in two_loop_gram.cuh: same tile pipeline, TMA-staged right-hand
+// vectors, S/Y columns streamed into registers).  PLAIN: s.v and y.v only.
+template <class T> struct PDots
+{
+    int64_t n, ld;
+    const T* v;
+    const T* S;
+    const T* Y;
+    int c, new_slot, split, cols_per_round;
+    const T *fx, *fxp, *fgp;
+    T *s_out, *y_out;
+};
+
+template <class T, int ROUNDS, bool FORM>
+__device__ __forceinline__ void p_dots(const PDots<T>& a, int64_t t0, int64_t t1, T* tiles, PShared& sh, unsigned& phase_bits, double* dst, int G)
+{
+    constexpr int NT = 4;                                        // stage stride in vectors (FORM uses all four)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int my_col = warp / a.split, my_part = warp % a.split;
+    const int part_len = kGramTE / a.split;
+    uint64_t* full_bar = sh.full_bar;
+
+    auto tile_is_tma = [&](int64_t tile) { return a.n - tile * kGramTE >= kGramTE; };
+    auto stage_tile = [&](int64_t tile, int stage) {
+        T* dstt = tiles + (size_t)stage * NT * kGramTE;
+        const int64_t e0 = tile * kGramTE;
+        const int64_t len = (a.n - e0 < kGramTE) ? (a.n - e0) : kGramTE;
+        if (len == kGramTE)
+        {
+            if (tid == 0)
+            {
+                const unsigned bytes = kGramTE * sizeof(T);
+                // the stage was last touched through the generic proxy (LDS of the dots, STS of form_tile): order those accesses
+                // before the bulk copy that overwrites it
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if constexpr (FORM)
+                {
+                    mbar_expect_tx(&full_bar[stage], bytes * 4);
+                    tma_load_1d(dstt, a.v + e0, bytes, &full_bar[stage]);
+                    tma_load_1d(dstt + kGramTE, a.fx + e0, bytes, &full_bar[stage]);
+                    tma_load_1d(dstt + 2 * kGramTE, a.fgp + e0, bytes, &full_bar[stage]);
+                    tma_load_1d(dstt + 3 * kGramTE, a.fxp + e0, bytes, &full_bar[stage]);
+                }
+                else
+                {
+                    mbar_expect_tx(&full_bar[stage], bytes);
+                    tma_load_1d(dstt, a.v + e0, bytes, &full_bar[stage]);
+                }
+            }
+        }
+        else
+        {
+            for (int i = tid; i < kGramTE; i += kPThreads)
+            {
+                const bool ok = i < len;
+                if constexpr (FORM)
+                {
+                    const T gv = ok ? a.v[e0 + i] : T(0);
+                    const T sv = ok ? a.fx[e0 + i] - a.fxp[e0 + i] : T(0);
+                    const T yv = ok ? gv - a.fgp[e0 + i] : T(0);
+                    dstt[i] = gv;
+                    dstt[kGramTE + i] = sv;
+                    dstt[2 * kGramTE + i] = yv;
+                    if (ok) { a.s_out[e0 + i] = sv; a.y_out[e0 + i] = yv; }
+                }
+                else
+                    dstt[i] = ok ? a.v[e0 + i] : T(0);
+            }
+        }
+    };
+    auto wait_tile = [&](int64_t tile, int st) {
+        if (tile_is_tma(tile))
+        {
+            mbar_wait(&full_bar[st], (phase_bits >> st) & 1u);
+            phase_bits ^= (1u << st);
+        }
+    };
+    auto form_tile = [&](int64_t tile, int st) {
+        if (!tile_is_tma(tile)) return;
+        T* tt = tiles + (size_t)st * NT * kGramTE;
+        const int64_t e0f = tile * kGramTE;
+        for (int i = tid * 4; i < kGramTE; i += kPThreads * 4)
+        {
+            Pack<T> ps, py;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+                ps.v[k] = tt[kGramTE + i + k] - tt[3 * kGramTE + i + k];
+                py.v[k] = tt[i + k] - tt[2 * kGramTE + i + k];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) { tt[kGramTE + i + k] = ps.v[k]; tt[2 * kGramTE + i + k] = py.v[k]; }
+            st_pack<Hint::Plain>(a.s_out + e0f + i, ps);
+            st_pack<Hint::Plain>(a.y_out + e0f + i, py);
+        }
+    };
+
+    T acc[ROUNDS][kGramVals];
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++)
+#pragma unroll
+        for (int k = 0; k < kGramVals; k++) acc[r][k] = T(0);
+
+    __syncthreads();   // the stages (and sh.slots) are free: every thread has left the previous phase
+    int64_t next_tile = t0;
+    for (int s = 0; s < kGramStages; s++, next_tile++)
+        if (next_tile < t1) stage_tile(next_tile, s);
+    if constexpr (FORM)
+    {
+        if (t0 < t1) { wait_tile(t0, 0); form_tile(t0, 0); }
+        __syncthreads();
+    }
+    int stage = 0;
+    for (int64_t tile = t0; tile < t1; tile++)
+    {
+        if constexpr (!FORM)
+        {
+            if (tile_is_tma(tile)) wait_tile(tile, stage);
+            else __syncthreads();
+        }
+        const T* vt = tiles + (size_t)stage * NT * kGramTE;
+        const T* snt = vt + kGramTE;
+        const T* ynt = vt + 2 * kGramTE;
+        const int64_t e0 = tile * kGramTE;
+        const int64_t len = (a.n - e0 < kGramTE) ? (a.n - e0) : kGramTE;
+        const bool full_tile = (len == kGramTE);
+#pragma unroll
+        for (int r = 0; r < ROUNDS; r++)
+        {
+            const int j = r * a.cols_per_round + my_col;
+            if (my_col < a.cols_per_round && j < a.c)
+            {
+                const int slot = sh.slots[j];
+                const bool is_new = FORM && slot == a.new_slot;
+                const T* scol = a.S + (int64_t)slot * a.ld + e0;
+                const T* ycol = a.Y + (int64_t)slot * a.ld + e0;
+#pragma unroll 2
+                for (int base = my_part * part_len + lane * 4; base < (my_part + 1) * part_len; base += 256)
+                {
+                    Pack<T> ps[2], py[2];
+#pragma unroll
+                    for (int u = 0; u < 2; u++)
+                    {
+                        const int off = base + u * 128;
+                        if (is_new)
+                        {
+                            ps[u] = lds_pack(snt + off, lane);
+                            py[u] = lds_pack(ynt + off, lane);
+                        }
+                        else if (full_tile)
+                        {
+                            ps[u] = ld_pack<Hint::Stream>(scol + off);
+                            py[u] = ld_pack<Hint::Stream>(ycol + off);
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                            {
+                                const bool ok = off + k < len;
+                                ps[u].v[k] = ok ? scol[off + k] : T(0);
+                                py[u].v[k] = ok ? ycol[off + k] : T(0);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; u++)
+                    {
+                        const int off = base + u * 128;
+                        const Pack<T> pv = lds_pack(vt + off, lane);
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                        {
+                            acc[r][0] += ps[u].v[k] * pv.v[k];
+                            acc[r][1] += py[u].v[k] * pv.v[k];
+                        }
+                        if constexpr (FORM)
+                        {
+                            const Pack<T> pyn = lds_pack(ynt + off, lane), psn = lds_pack(snt + off, lane);
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                            {
+                                acc[r][2] += ps[u].v[k] * pyn.v[k];
+                                acc[r][3] += py[u].v[k] * pyn.v[k];
+                                acc[r][4] += py[u].v[k] * psn.v[k];
+                                acc[r][5] += ps[u].v[k] * psn.v[k];
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if constexpr (FORM)
+        {
+            const int64_t upcoming = tile + 1;
+            const int nstage = (stage + 1 == kGramStages) ? 0 : stage + 1;
+            if (upcoming < t1) { wait_tile(upcoming, nstage); form_tile(upcoming, nstage); }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads / form_tile writes of this stage before its re-arming bulk copy
+        __syncthreads();
+        if (next_tile < t1) stage_tile(next_tile, stage);
+        next_tile++;
+        stage = (stage + 1 == kGramStages) ? 0 : stage + 1;
+    }
+
+    // block reduction: lanes -> warp, then the `split` warps of a column; value (j, k) -> dst[(j*6 + k) * G]
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++)
+#pragma unroll
+        for (int k = 0; k < kGramVals; k++)
+        {
+            const double w = warp_sum((double)acc[r][k]);
+            if (lane == 0) sh.red[warp][r * kGramVals + k] = w;
+        }
+    __syncthreads();
+    const int nvals = a.c * kGramVals;
+    for (int idx = tid; idx < nvals; idx += kPThreads)
+    {
+        const int j = idx / kGramVals, k = idx % kGramVals;
+        const int r = j / a.cols_per_round, col = j % a.cols_per_round;
+        double t = 0.0;
+        for (int p = 0; p < a.split; p++) t += sh.red[col * a.split + p][r * kGramVals + k];
+        dst[(size_t)idx * G] = t;
+    }
+}
+
+// ---- COMBINE (+ first trial) ---------------------------------------------------------------------------------------------------
+// d = cv*v + sum_j cy_j*y_j + cs_j*s_j ; FUSE: x1 = xc + d, g1 = grad f(x1) written to (x1_out, g1_out) and the four trial sums.
+template <class T, class OBJ, bool FUSE>
+__device__ __forceinline__ void p_combine(const OBJ& obj, int64_t n, int64_t e0, int64_t e1, int c, const T* s_coef, const T* __restrict__ v,
+                                          const T* __restrict__ xc, T* __restrict__ res, T* __restrict__ x1_out, T* __restrict__ g1_out,
+                                          PShared& sh, double* dst, int G)
+{
+    const T cv = s_coef[0];
+    T acc[5] = {T(0), T(0), T(0), T(0), T(0)};
+    const int64_t p1 = (e1 + 3) >> 2;
+    for (int64_t p = (e0 >> 2) + threadIdx.x; p < p1; p += kPThreads)
+    {
+        const int64_t i0 = p << 2;
+        const int cnt = (n - i0 >= 4) ? 4 : int(n - i0);
+        const Pack<T> pv = load4<T, Hint::Stream, true>(v, i0, cnt);
+        Pack<T> px;
+        if (FUSE) px = load4<T, Hint::Stream, true>(xc, i0, cnt);
+        T r[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) r[k] = cv * pv.v[k];
+        // y terms newest -> oldest, then s terms oldest -> newest (the order the recursion would add them)
+#pragma unroll 4
+        for (int j = 0; j < c; j++)
+        {
+            const Pack<T> py = load4<T, Hint::Stream, true>(static_cast<const T*>(sh.ycol[j]), i0, cnt);
+            const T cy = s_coef[1 + j];
+#pragma unroll
+            for (int k = 0; k < 4; k++) r[k] += cy * py.v[k];
+        }
+#pragma unroll 4
+        for (int j = c - 1; j >= 0; j--)
+        {
+            const Pack<T> ps = load4<T, Hint::Stream, true>(static_cast<const T*>(sh.scol[j]), i0, cnt);
+            const T cs = s_coef[1 + c + j];
+#pragma unroll
+            for (int k = 0; k < 4; k++) r[k] += cs * ps.v[k];
+        }
+        Pack<T> out;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            out.v[k] = r[k];
+            acc[0] += (k < cnt) ? pv.v[k] * r[k] : T(0);
+        }
+        store4<T, Hint::Plain, true>(res, i0, cnt, out);
+        if (FUSE)
+        {
+            T xv[4], gv[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) xv[k] = px.v[k] + T(1) * r[k];
+            acc[1] += obj.eval(i0, cnt, xv, T(0), T(0), gv);
+            Pack<T> pg, po;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+                acc[2] += (k < cnt) ? gv[k] * r[k] : T(0);
+                acc[3] += gv[k] * gv[k];
+                acc[4] += (k < cnt) ? xv[k] * xv[k] : T(0);
+                pg.v[k] = gv[k];
+                po.v[k] = xv[k];
+            }
+            store4<T, Hint::Plain, true>(x1_out, i0, cnt, po);
+            store4<T, Hint::Plain, true>(g1_out, i0, cnt, pg);
+        }
+    }
+    if (FUSE)
+    {
+        const double dacc[5] = {(double)acc[0], (double)acc[1], (double)acc[2], (double)acc[3], (double)acc[4]};
+        block_sums<5>(dacc, sh, dst, G);
+    }
+    else
+    {
+        const double dacc[1] = {(double)acc[0]};
+        block_sums<1>(dacc, sh, dst, G);
+    }
+}
+
+// ---- waits with a watchdog ----------------------------------------------------------------------------------------------------
+constexpr long long kPWaitCycles = 6000000000ll;   // ~3 s at 2 GHz: far beyond any legitimate wait, short of gpurun's own limits
+
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(unsigned* p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// ---- the leader's work between two rounds ------------------------------------------------------------------------------------
+template <class T> __device__ __forceinline__ void record_eval(PState<T>* st, T fx)
+{
+    if (st->trace && st->nfev < st->trace_cap) st->trace[st->nfev] = (double)fx;
+    st->nfev++;
+}
+template <class T> __device__ __forceinline__ void finish(PState<T>* st, int niter, int status = 0)
+{
+    st->finished = 1;
+    st->niter = niter;
+    if (status) st->status = status;
+    st->op = POP_IDLE;
+}
+
+// LBFGS.h:137-154 after an accepted / best-so-far point: returns true when the solve is over
+template <class T> __device__ __forceinline__ bool converged_after_search(PState<T>* st)
+{
+    const int k = st->k;
+    st->gnorm = sqrt(st->gg);
+    if (st->gnorm <= st->epsilon || st->gnorm <= st->epsilon_rel * sqrt(st->xx)) { finish(st, k); return true; }
+    if (st->past > 0)
+    {
+        const T fxd = st->fx_hist[k % st->past];
+        const T fx = st->fx;
+        const T afx = fx < T(0) ? -fx : fx, afxd = fxd < T(0) ? -fxd : fxd;
+        T big = afx < afxd ? afxd : afx;       // std::max(abs(fx), abs(fxd))
+        big = big < T(1) ? T(1) : big;         // std::max(., 1)
+        const T diff = (fxd - fx) < T(0) ? -(fxd - fx) : (fxd - fx);
+        if (k >= st->past && diff <= st->delta * big) { finish(st, k); return true; }
+        st->fx_hist[k % st->past] = fx;
+    }
+    if (st->max_iterations != 0 && k >= st->max_iterations) { finish(st, k); return true; }
+    return false;
+}
+
+// the trial at ls_step_ref(st) has been evaluated: {fx, dg, gg, xx}.  Sets the next op.
+template <class T> __device__ __forceinline__ void digest_trial(PState<T>* st, T fx, T dg, T gg, T xx)
+{
+    record_eval(st, fx);
+    bool keep = false;
+    const int rc = ls_advance(st, fx, dg, keep);
+    if (keep)
+    {
+        dswap(st->x, st->x_lo);
+        dswap(st->g, st->g_lo);
+        st->have_lo = 1;
+        st->lo_gg = gg;
+        st->lo_xx = xx;
+    }
+    if (rc == LBFGSpp::LSC_EVALUATE) { st->op = POP_TRIAL; st->step = ls_step_ref(st); return; }
+    if (rc == LBFGSpp::LSC_ACCEPT)
+    {
+        st->fx = fx; st->dg = dg; st->gg = gg; st->xx = xx;
+    }
+    else if (rc == LBFGSpp::LSC_TAKE_BEST)
+    {
+        T bf, bd;
+        ls_best(st, bf, bd);
+        st->fx = bf;
+        st->dg = bd;
+        if (st->have_lo)
+        {
+            dswap(st->x, st->x_lo);
+            dswap(st->g, st->g_lo);
+            st->gg = st->lo_gg;
+            st->xx = st->lo_xx;
+        }
+        else
+        {
+            st->gg = st->start_gg;
+            st->xx = st->start_xx;
+            st->op = POP_RESTORE;   // no trial ever improved on the start point: copy xp/gp back, then carry on
+            return;
+        }
+    }
+    else { finish(st, st->k, rc); return; }
+    if (converged_after_search(st)) return;
+    st->op = POP_DOTS_FORM;
+    st->c_round = st->ncorr < st->m ? st->ncorr + 1 : st->m;
+}
+
+// top of an iteration (LBFGS.h:121-127): the search is armed, the current point becomes the previous one
+template <class T> __device__ __forceinline__ bool begin_search(PState<T>* st, T step)
+{
+    // the search validates its inputs before anything moves (the reference throws before touching x): on failure x stays the
+    // current point
+    const int rc = ls_init(st, st->fx, st->dg, step, st->max_step);
+    if (rc != 0) { finish(st, st->k, rc); return false; }
+    dswap(st->xp, st->x);
+    dswap(st->gp, st->g);
+    st->have_lo = 0;
+    st->start_gg = st->gg;
+    st->start_xx = st->xx;
+    st->op = POP_TRIAL;
+    st->step = ls_step_ref(st);
+    return true;
+}
+
+template <class T> __device__ void advance_problem(PState<T>* st, const double* vals)
+{
+    st->rounds++;
+    switch (st->op)
+    {
+    case POP_FIRST:
+    {
+        const T fx = (T)vals[0], gg = (T)vals[2], xx = (T)vals[3];
+        st->nfev = 0;
+        record_eval(st, fx);
+        st->fx = fx; st->gg = gg; st->xx = xx;
+        st->k = 1;
+        if (st->past > 0) st->fx_hist[0] = fx;
+        st->gnorm = sqrt(gg);
+        if (st->gnorm <= st->epsilon || st->gnorm <= st->epsilon_rel * sqrt(xx)) { finish(st, 1); return; }
+        st->dg = -gg;                       // grad . (-grad)
+        begin_search(st, T(1) / st->gnorm); // LBFGS.h:108
+        return;
+    }
+    case POP_TRIAL:
+        digest_trial(st, (T)vals[0], (T)vals[1], (T)vals[2], (T)vals[3]);
+        return;
+    case POP_RESTORE:
+        if (converged_after_search(st)) return;
+        st->op = POP_DOTS_FORM;
+        st->c_round = st->ncorr < st->m ? st->ncorr + 1 : st->m;
+        return;
+    case POP_DOTS_FORM:
+    {
+        // curvature gate on the pair's own dots (age-0 column: [2] = s'y, [3] = y'y), LBFGS.h:161; commit = BFGSMat.h:89-97
+        const T sy = (T)vals[2], yy = (T)vals[3];
+        if (sy > st->eps_gate * yy)
+        {
+            st->ys[st->head] = sy;
+            *st->theta = yy / sy;
+            st->pending = st->head;
+            st->head = (st->head + 1) % st->M;
+            st->ncorr = st->c_round;
+            st->op = st->fuse_first_trial ? POP_COMBINE_TRIAL : POP_COMBINE;
+        }
+        else if (st->ncorr > 0) { st->op = POP_DOTS_PLAIN; st->c_round = st->ncorr; }
+        else { st->op = st->fuse_first_trial ? POP_COMBINE_TRIAL : POP_COMBINE; st->c_round = 0; }
+        return;
+    }
+    case POP_DOTS_PLAIN:
+        st->op = st->fuse_first_trial ? POP_COMBINE_TRIAL : POP_COMBINE;
+        return;
+    case POP_COMBINE:
+    case POP_COMBINE_TRIAL:
+    {
+        const bool fused = st->op == POP_COMBINE_TRIAL;
+        if (st->pending >= 0) { st->gram_cur = 1 - st->gram_cur; st->pending = -1; }
+        st->dg = (T)vals[0];                // LBFGS.h:123 for the next pass
+        st->k += 1;
+        if (!begin_search(st, T(1))) return;   // LBFGS.h:168
+        // the pass already evaluated x + 1*d into the buffers that the rotation just made (x, g)
+        if (fused && ls_step_ref(st) == T(1)) digest_trial(st, (T)vals[1], (T)vals[2], (T)vals[3], (T)vals[4]);
+        return;
+    }
+    default: return;
+    }
+}
+
+// n-words a pass has to move (reads + writes of whole vectors): the roofline numerator of the persistent kernel
+__device__ __forceinline__ double words_of(int op, int c, int data_vectors)
+{
+    switch (op)
+    {
+    case POP_FIRST: return 3.0 + data_vectors;              // R x ; W g, d
+    case POP_TRIAL: return 4.0 + data_vectors;              // R xp, d ; W x, g
+    case POP_RESTORE: return 4.0;                           // R xp, gp ; W x, g
+    case POP_DOTS_FORM: return 2.0 * c + 4.0;               // R x, xp, g, gp, 2(c-1) columns ; W s, y
+    case POP_DOTS_PLAIN: return 2.0 * c + 1.0;              // R g, 2c columns
+    case POP_COMBINE: return 2.0 * c + 2.0;                 // R g, 2c columns ; W d
+    case POP_COMBINE_TRIAL: return 2.0 * c + 5.0 + data_vectors;   // R g, x, 2c columns ; W d, x1, g1
+    default: return 0.0;
+    }
+}
+
+__device__ __forceinline__ int nvals_of(int op, int c_round)
+{
+    switch (op)
+    {
+    case POP_FIRST: case POP_TRIAL: return 4;
+    case POP_DOTS_FORM: case POP_DOTS_PLAIN: return c_round * kGramVals;
+    case POP_COMBINE: return 1;
+    case POP_COMBINE_TRIAL: return 5;
+    default: return 0;
+    }
+}
+
+// Fixed-order sums of the CTAs' partials of every running problem into raw[], (optional) cross-rank exchange, scalar logic.
+// Called by all threads of CTA 0 once every CTA has arrived.
+template <class T, bool HALO>
+__device__ void leader_round(const PArgs<T>& a, int G)
+{
+    const int tid = threadIdx.x;
+    // 1. local sums: 16 threads per value (CTAs s, s+16, ... then a fixed shuffle tree), 48 values per sweep
+    for (int b = 0; b < a.B; b++)
+    {
+        PState<T>* st = a.probs + b;
+        const int op = st->op;
+        if (op == POP_IDLE) continue;
+        const int nv = nvals_of(op, st->c_round);
+        const double* part = a.partials + (size_t)b * a.pstride * G;
+        for (int v0 = 0; v0 < nv; v0 += kPThreads / 16)
+        {
+            const int v = v0 + tid / 16, sub = tid & 15;
+            double t = 0.0;
+            if (v < nv)
+                for (int cta = sub; cta < G; cta += 16) t += __ldcg(part + (size_t)v * G + cta);
+            t += __shfl_xor_sync(0xffffffffu, t, 8);
+            t += __shfl_xor_sync(0xffffffffu, t, 4);
+            t += __shfl_xor_sync(0xffffffffu, t, 2);
+            t += __shfl_xor_sync(0xffffffffu, t, 1);
+            if (v < nv && sub == 0) st->raw[v] = t;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    // 2. n sharded over ranks: ONE exchange for all running problems (sums in rank order: identical bits on every rank)
+    if (a.xc != nullptr)
+    {
+        const XComm* xc = a.xc;
+        const int me = xc->rank, R = xc->nranks;
+        const unsigned long long epoch = a.ctl->epoch + 1ull;
+        const int slot = (int)(epoch % kXRing);
+        // payload layout: problem after problem, nv sums then (HALO) 4 gathered boundary values
+        int ofs = 0;
+        for (int b = 0; b < a.B; b++)
+        {
+            PState<T>* st = a.probs + b;
+            const int op = st->op;
+            if (op == POP_IDLE) continue;
+            const int nv = nvals_of(op, st->c_round);
+            for (int r = tid; r < R * nv; r += kPThreads)
+                xc->inbox[r / nv]->vals[slot][me][ofs + r % nv] = st->raw[r % nv];
+            ofs += nv;
+            if (HALO)
+            {
+                // boundary coordinates for the neighbours' next evaluations: the next search starts from the current x along drt
+                if (tid < 4 * R)
+                {
+                    const int k = tid & 3;
+                    const T* src = (k & 1) ? st->drt : st->x;
+                    const double val = (double)__ldcg(src + ((k & 2) ? a.n - 1 : 0));
+                    xc->inbox[tid >> 2]->vals[slot][me][ofs + k] = val;
+                }
+                ofs += 4;
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < R) st_release_sys(&xc->inbox[tid]->flag[slot][me], epoch);
+        if (tid < R)
+        {
+            const unsigned long long* f = &xc->inbox[me]->flag[slot][tid];
+            const long long t_start = clock64();
+            while (ld_acquire_sys(f) != epoch)
+                if (clock64() - t_start > 4 * kPWaitCycles || ldv(&a.ctl->abort)) { a.ctl->abort = 1; break; }
+        }
+        __syncthreads();
+        ofs = 0;
+        for (int b = 0; b < a.B; b++)
+        {
+            PState<T>* st = a.probs + b;
+            const int op = st->op;
+            if (op == POP_IDLE) continue;
+            const int nv = nvals_of(op, st->c_round);
+            for (int k = tid; k < nv; k += kPThreads)
+            {
+                double t = 0.0;
+                for (int r = 0; r < R; r++) t += ld_volatile_f64(&xc->inbox[me]->vals[slot][r][ofs + k]);
+                st->raw[k] = t;
+            }
+            ofs += nv;
+            if (HALO)
+            {
+                if ((op == POP_FIRST || op == POP_COMBINE || op == POP_COMBINE_TRIAL) && tid < 8)
+                {
+                    const int side = tid >> 2, k = tid & 3;       // side 0: left neighbour, 1: right neighbour
+                    const int nb = side == 0 ? me - 1 : me + 1;
+                    st->halo[4 + 4 * side + k] = (nb >= 0 && nb < R) ? ld_volatile_f64(&xc->inbox[me]->vals[slot][nb][ofs + k]) : 0.0;
+                }
+                ofs += 4;
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) a.ctl->epoch = epoch;
+    }
+    // 3. scalar logic, one thread per problem
+    int still = 0;
+    for (int b0 = 0; b0 < a.B; b0 += kPThreads)
+    {
+        const int b = b0 + tid;
+        int running = 0;
+        if (b < a.B)
+        {
+            PState<T>* st = a.probs + b;
+            if (st->op != POP_IDLE) advance_problem(st, st->raw);
+            running = st->op != POP_IDLE;
+        }
+        still += __syncthreads_count(running);
+    }
+    if (tid == 0) { a.ctl->nactive = still; a.ctl->rounds++; }
+    __threadfence();
+    __syncthreads();
+}
+
+// exchange-only prelude for neighbour-coupled objectives under n-sharding: the first evaluation needs the neighbours' boundary
+// coordinates of x0 (later rounds piggyback the boundaries of (x, drt) on the sums, see leader_round).  All threads of CTA 0.
+template <class T> __device__ void leader_halo_prelude(const PArgs<T>& a)
+{
+    const int tid = threadIdx.x;
+    const XComm* xc = a.xc;
+    const int me = xc->rank, R = xc->nranks;
+    const unsigned long long epoch = a.ctl->epoch + 1ull;
+    const int slot = (int)(epoch % kXRing);
+    for (int b = 0; b < a.B; b++)
+    {
+        PState<T>* st = a.probs + b;
+        if (tid < 4 * R)
+        {
+            const int k = tid & 3;
+            const double val = (k & 1) ? 0.0 : (double)__ldcg(st->x + ((k & 2) ? a.n - 1 : 0));
+            xc->inbox[tid >> 2]->vals[slot][me][4 * b + k] = val;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < R) st_release_sys(&xc->inbox[tid]->flag[slot][me], epoch);
+    if (tid < R)
+    {
+        const unsigned long long* f = &xc->inbox[me]->flag[slot][tid];
+        const long long t_start = clock64();
+        while (ld_acquire_sys(f) != epoch)
+            if (clock64() - t_start > 4 * kPWaitCycles || ldv(&a.ctl->abort)) { a.ctl->abort = 1; break; }
+    }
+    __syncthreads();
+    for (int b = 0; b < a.B; b++)
+    {
+        PState<T>* st = a.probs + b;
+        if (tid < 8)
+        {
+            const int side = tid >> 2, k = tid & 3;
+            const int nb = side == 0 ? me - 1 : me + 1;
+            st->halo[4 + 4 * side + k] = (nb >= 0 && nb < R) ? ld_volatile_f64(&xc->inbox[me]->vals[slot][nb][4 * b + k]) : 0.0;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) a.ctl->epoch = epoch;
+}
+
+// ---- the kernel ----------------------------------------------------------------------------------------------------------------
+template <class T, class OBJ, int ROUNDS>
+__global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
+{
+    extern __shared__ __align__(128) unsigned char p_smem[];
+    T* tiles = reinterpret_cast<T*>(p_smem);      // [stage][4][TE] for the dots; the combine passes keep their coefficients here
+    __shared__ PShared sh;
+    const int tid = threadIdx.x, G = gridDim.x, cta = blockIdx.x;
+    const int64_t ntiles = (a.n + kGramTE - 1) / kGramTE;
+    int64_t t0, t1;
+    chunk_of(ntiles, cta, G, t0, t1);
+    const int64_t e0 = t0 * kGramTE, e1 = (t1 * kGramTE < a.n) ? t1 * kGramTE : a.n;
+    if (tid == 0)
+    {
+        for (int s = 0; s < kGramStages; s++) mbar_init(&sh.full_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned phase_bits = 0;
+    unsigned episode = 0;    // grid-barrier episodes so far
+    constexpr bool HALO = OBJ::kHalo;
+    constexpr int kDataVectors = OBJ::kDataVectors;
+    long long t_last = clock64(), t_arrive = 0;   // CTA 0, thread 0: accounting (PCtl::cyc_*)
+    int acct_bucket = 0;
+    double acct_words = 0.0;
+
+    // grid-wide barrier; between arrival of the last CTA and the release, CTA 0 runs `leader_work` (all its threads)
+    auto grid_barrier = [&](auto leader_work) {
+        episode++;
+        asm volatile("fence.proxy.async;" ::: "memory");   // this round's generic-proxy stores before later bulk (async-proxy) reads
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicAdd(&a.ctl->arrive, 1u);
+        if (cta == 0)
+        {
+            if (tid == 0)
+            {
+                const long long t_start = clock64();
+                t_arrive = t_start;
+                while (ld_acquire_gpu_u32(&a.ctl->arrive) != episode * (unsigned)G)
+                    if (clock64() - t_start > kPWaitCycles || ldv(&a.ctl->abort)) { a.ctl->abort = 1; break; }
+            }
+            __syncthreads();
+            __threadfence();
+            leader_work();
+            __threadfence();
+            __syncthreads();
+            if (tid == 0)
+            {
+                const long long now = clock64();
+                a.ctl->cyc_op[acct_bucket] += now - t_last;
+                a.ctl->cyc_sync += now - t_arrive;
+                a.ctl->n_op[acct_bucket] += 1ull;
+                a.ctl->words_op[acct_bucket] += acct_words;
+                t_last = now;
+                st_release_gpu_u32(&a.ctl->release, episode);
+            }
+        }
+        if (tid == 0)
+        {
+            const long long t_start = clock64();
+            while (ld_acquire_gpu_u32(&a.ctl->release) < episode)
+                if (clock64() - t_start > 6 * kPWaitCycles || ldv(&a.ctl->abort)) { a.ctl->abort = 1; break; }
+        }
+        __syncthreads();
+    };
+
+    if (HALO && a.xc != nullptr) grid_barrier([&]() { leader_halo_prelude<T>(a); });
+
+    for (;;)
+    {
+        if (ldv(&a.ctl->nactive) == 0 || ldv(&a.ctl->abort)) break;
+        acct_bucket = -1;
+        acct_words = 0.0;
+        for (int b = 0; b < a.B; b++)
+        {
+            const PState<T>* st = a.probs + b;
+            const int op = ldv(&st->op);
+            if (op == POP_IDLE) continue;
+            acct_bucket = (acct_bucket == -1 || acct_bucket == op) ? op : 0;
+            acct_words += words_of(op, ldv(&st->c_round), kDataVectors);
+            double* dst = a.partials + (size_t)b * a.pstride * G + cta;
+            const OBJ obj = PObjMaker<T, OBJ>::make(a, ldv(&st->data0), ldv(&st->data1), (HALO && a.xc != nullptr) ? ldv(&st->halo) : nullptr);
+            switch (op)
+            {
+            case POP_FIRST:
+                p_trial<T, OBJ, 0>(obj, a.n, e0, e1, nullptr, nullptr, T(0), ldv(&st->x), ldv(&st->g), ldv(&st->drt), sh, dst, G);
+                break;
+            case POP_TRIAL:
+                p_trial<T, OBJ, 1>(obj, a.n, e0, e1, ldv(&st->xp), ldv(&st->drt), ldv(&st->step), ldv(&st->x), ldv(&st->g), nullptr, sh, dst, G);
+                break;
+            case POP_RESTORE:
+                p_restore<T>(a.n, e0, e1, ldv(&st->xp), ldv(&st->gp), ldv(&st->x), ldv(&st->g));
+                break;
+            case POP_DOTS_FORM:
+            case POP_DOTS_PLAIN:
+            {
+                const bool form = op == POP_DOTS_FORM;
+                PDots<T> d;
+                d.n = a.n; d.ld = a.ld; d.v = ldv(&st->g); d.S = ldv(&st->S); d.Y = ldv(&st->Y);
+                d.c = ldv(&st->c_round);
+                const int head = ldv(&st->head), M = ldv(&st->M);
+                d.new_slot = form ? head : -1;
+                int split = 8;
+                while (split > 1 && d.c * split > kGramMaxWarps) split >>= 1;
+                d.split = split;
+                d.cols_per_round = d.c < kGramMaxWarps / split ? d.c : kGramMaxWarps / split;
+                d.fx = ldv(&st->x); d.fxp = ldv(&st->xp); d.fgp = ldv(&st->gp);
+                d.s_out = const_cast<T*>(d.S) + (int64_t)head * a.ld;
+                d.y_out = const_cast<T*>(d.Y) + (int64_t)head * a.ld;
+                __syncthreads();   // sh.slots may still be read by the previous problem's pass
+                if (tid < d.c) sh.slots[tid] = (unsigned char)(form ? (tid == 0 ? head : slot_by_age(head, M, tid - 1)) : slot_by_age(head, M, tid));
+                if (form) p_dots<T, ROUNDS, true>(d, t0, t1, tiles, sh, phase_bits, dst, G);
+                else p_dots<T, ROUNDS, false>(d, t0, t1, tiles, sh, phase_bits, dst, G);
+                break;
+            }
+            case POP_COMBINE:
+            case POP_COMBINE_TRIAL:
+            {
+                GramSolveArgs<T> g;
+                g.c = ldv(&st->c_round);
+                g.M = ldv(&st->M); g.new_slot = ldv(&st->pending); g.with_v = 1; g.a = T(-1);
+                g.raw = ldv(&st->raw);
+                const int in = ldv(&st->gram_cur), out = (g.new_slot >= 0) ? 1 - in : in;
+                g.SY_in = ldv(&st->SY[in]); g.YY_in = ldv(&st->YY[in]); g.SS_in = ldv(&st->SS[in]);
+                g.SY_out = ldv(&st->SY[out]); g.YY_out = ldv(&st->YY[out]); g.SS_out = ldv(&st->SS[out]);
+                g.ys = ldv(&st->ys); g.alpha = ldv(&st->alpha); g.theta = ldv(&st->theta);
+                g.ov_slot = -1; g.ov_theta_on = 0;
+                const int head = ldv(&st->head);
+                for (int age = 0; age < g.c; age++) g.slots[age] = (unsigned char)slot_by_age(head, g.M, age);
+                __syncthreads();   // the tile area / pointer tables may still be in use by the previous problem's pass
+                gram_solve_in_smem<T>(g, tiles, cta == 0);
+                const T* S = ldv(&st->S); const T* Y = ldv(&st->Y);
+                for (int j = tid; j < g.c; j += kPThreads)
+                {
+                    sh.ycol[j] = Y + (int64_t)g.slots[j] * a.ld;
+                    sh.scol[j] = S + (int64_t)g.slots[j] * a.ld;
+                }
+                __syncthreads();
+                const T* s_coef = tiles + 2 * g.c * g.c;
+                bool done = false;
+                if constexpr (!OBJ::kHalo)
+                {
+                    if (op == POP_COMBINE_TRIAL)
+                    {
+                        p_combine<T, OBJ, true>(obj, a.n, e0, e1, g.c, s_coef, ldv(&st->g), ldv(&st->x), ldv(&st->drt), ldv(&st->xp), ldv(&st->gp), sh, dst, G);
+                        done = true;
+                    }
+                }
+                if (!done) p_combine<T, OBJ, false>(obj, a.n, e0, e1, g.c, s_coef, ldv(&st->g), nullptr, ldv(&st->drt), nullptr, nullptr, sh, dst, G);
+                break;
+            }
+            default: break;
+            }
+        }
+        if (acct_bucket < 0) acct_bucket = 0;
+        grid_barrier([&]() { leader_round<T, HALO>(a, G); });
+    }
+}
+
+}  // namespace lb

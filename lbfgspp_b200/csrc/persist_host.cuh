@@ -1,0 +1,302 @@
+// persist_host.cuh -- host side of the device-resident solve (persist.cuh): solver handle, state upload, ONE cooperative launch per
+// minimize() (single problem or batch), C ABI.  Included at the end of lbfgs_b200.cu.
+#pragma once
+
+struct lbfgs_b200_solver
+{
+    lbfgs_b200_ctx* ctx = nullptr;
+    int64_t n = 0;
+    int m = 0, elem = 8, B = 1;
+    std::vector<lbfgs_b200_hist*> hist;   // one S/Y ring per problem
+    void* vec_slab = nullptr;             // [B][7][vec_elems] : x, xp, g, gp, drt, x_lo, g_lo
+    size_t vec_elems = 0;                 // n rounded up to a whole number of 256-byte lines
+    void* d_state = nullptr;              // PState<T>[B]
+    lb::PCtl* d_ctl = nullptr;
+    double* d_partials = nullptr;         // [B][pstride][sm_count]
+    double* d_raw = nullptr;              // [B][pstride]
+    double* d_halo = nullptr;             // [B][kHaloDoubles]
+    int pstride = 0;
+    double* d_trace = nullptr;
+    long long trace_cap = 0;
+    std::vector<void*> final_g, final_x;  // device pointers of each problem's final gradient / point (inside vec_slab)
+    std::vector<unsigned char> h_state;   // host copy of the states
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_kernel_ms = 0.f;           // device time of the last solve's kernel (CUDA events around the launch)
+    lb::PCtl last_ctl{};                  // its accounting
+};
+
+template <class T> static void* persist_kernel_for(int objective, int rounds)
+{
+    using namespace lb;
+#define LB_PK(OBJ) (rounds <= 1 ? (void*)k_persist<T, OBJ, 1> : rounds == 2 ? (void*)k_persist<T, OBJ, 2> : (void*)k_persist<T, OBJ, 3>)
+    switch (objective)
+    {
+    case LBFGS_B200_OBJ_ROSENBROCK_PAIRED: return LB_PK(RosenbrockPaired<T>);
+    case LBFGS_B200_OBJ_QUAD_SHIFT: return LB_PK(QuadShift<T>);
+    case LBFGS_B200_OBJ_ROSENBROCK_CHAINED: return LB_PK(RosenbrockChained<T>);
+    case LBFGS_B200_OBJ_QUAD_TRIDIAG: return LB_PK(QuadTridiag<T>);
+    }
+#undef LB_PK
+    return nullptr;
+}
+
+// x_inout: B vectors of n elements, `ldx` elements apart (device).  data0/data1: nullptr, or per-problem vectors `ldd` apart (ldd = 0:
+// every problem shares the same data).  outs: B outcomes.  trace_host: only with B == 1.
+template <class T>
+static lbfgs_b200_status solver_minimize(lbfgs_b200_solver* s, int objective, const T* data0, const T* data1, int64_t ldd, const lbfgs_b200_param* prm,
+                                         int ls_kind, T* x_inout, int64_t ldx, double* trace_host, long long trace_cap, lbfgs_b200_outcome* outs)
+{
+    using namespace lb;
+    lbfgs_b200_ctx* ctx = s->ctx;
+    const int B = s->B;
+    REQUIRE(ctx, s->elem == (int)sizeof(T), "solver element size mismatch");
+    REQUIRE(ctx, prm && outs && x_inout, "solver_minimize: NULL argument");
+    REQUIRE(ctx, prm->m == s->m, "solver was created for m = %d, called with m = %d", s->m, prm->m);
+    REQUIRE(ctx, ls_kind >= 0 && ls_kind <= 3, "unknown line search %d", ls_kind);
+    REQUIRE(ctx, prm->past <= kMaxPast, "past > %d is not supported by the device-resident solve", kMaxPast);
+    REQUIRE(ctx, ctx->nranks == 1 || ctx->x_active, "the device-resident solve needs the in-kernel exchange (comm_p2p) when sharded");
+    REQUIRE(ctx, B == 1 || ldx >= s->n, "solver_minimize: the batch stride of x is shorter than n");
+    REQUIRE(ctx, trace_host == nullptr || B == 1, "solver_minimize: traces are recorded for single problems only");
+    const bool coupled = objective == LBFGS_B200_OBJ_ROSENBROCK_CHAINED || objective == LBFGS_B200_OBJ_QUAD_TRIDIAG;
+    if (objective == LBFGS_B200_OBJ_ROSENBROCK_PAIRED) REQUIRE(ctx, s->n % 2 == 0, "paired Rosenbrock needs an even n");
+    if (objective == LBFGS_B200_OBJ_QUAD_TRIDIAG) REQUIRE(ctx, data0 && data1, "quad_tridiag needs data0 = diag, data1 = rhs");
+    int64_t n_global = s->n, index_offset = ctx->index_offset;
+    if (ctx->nranks > 1 && coupled)
+    {
+        REQUIRE(ctx, ctx->n_global > 0, "a neighbour-coupled objective under n-sharding needs lbfgs_b200_set_global_extent()");
+        REQUIRE(ctx, ctx->index_offset + s->n <= ctx->n_global, "local block exceeds the global extent");
+        REQUIRE(ctx, ctx->rank == ctx->nranks - 1 || s->n % 4 == 0, "every block but the last must hold a multiple of 4 coordinates");
+        n_global = ctx->n_global;
+    }
+    else if (coupled) index_offset = 0;
+    if (ctx->x_active) REQUIRE(ctx, (size_t)B * (s->pstride + 4) <= (size_t)kXMaxVals, "batch of %d problems with m = %d exceeds the exchange buffer", B, s->m);
+    const int split_m = [&] { int sp = 8; while (sp > 1 && s->m * sp > kGramMaxWarps) sp >>= 1; return sp; }();
+    const int per_round = s->m < kGramMaxWarps / split_m ? s->m : kGramMaxWarps / split_m;
+    const int rounds = (s->m + per_round - 1) / per_round;
+    void* kernel = persist_kernel_for<T>(objective, rounds);
+    if (!kernel) return fail(ctx, LBFGS_B200_ERR_INVALID, "unknown objective id %d", objective);
+
+    if (trace_host && trace_cap > s->trace_cap)
+    {
+        cudaFree(s->d_trace);
+        s->d_trace = nullptr;
+        CU(ctx, cudaMalloc(&s->d_trace, sizeof(double) * (size_t)trace_cap));
+        s->trace_cap = trace_cap;
+    }
+
+    // ---- states ----
+    s->h_state.assign(sizeof(PState<T>) * (size_t)B, 0);
+    PState<T>* hs = reinterpret_cast<PState<T>*>(s->h_state.data());
+    const size_t vb = sizeof(T) * (size_t)s->n;
+    for (int b = 0; b < B; b++)
+    {
+        lbfgs_b200_hist* h = s->hist[b];
+        if (auto st = lbfgs_b200_hist_reset(h)) return st;
+        PState<T>& p = hs[b];
+        T* base = static_cast<T*>(s->vec_slab) + (size_t)b * 7 * s->vec_elems;
+        p.x = base; p.xp = base + s->vec_elems; p.g = base + 2 * s->vec_elems; p.gp = base + 3 * s->vec_elems;
+        p.drt = base + 4 * s->vec_elems; p.x_lo = base + 5 * s->vec_elems; p.g_lo = base + 6 * s->vec_elems;
+        p.S = static_cast<T*>(h->S); p.Y = static_cast<T*>(h->Y); p.ys = static_cast<T*>(h->ys);
+        p.alpha = static_cast<T*>(h->alpha); p.theta = static_cast<T*>(h->theta);
+        for (int k = 0; k < 2; k++) { p.SY[k] = static_cast<T*>(h->SY[k]); p.YY[k] = static_cast<T*>(h->YY[k]); p.SS[k] = static_cast<T*>(h->SS[k]); }
+        p.data0 = data0 ? data0 + (size_t)b * ldd : nullptr;
+        p.data1 = data1 ? data1 + (size_t)b * ldd : nullptr;
+        p.raw = s->d_raw + (size_t)b * s->pstride;
+        p.halo = s->d_halo + (size_t)b * kHaloDoubles;
+        p.head = 0; p.ncorr = 0; p.M = h->M; p.m = h->m; p.gram_cur = h->gram_cur; p.pending = -1;
+        p.op = POP_FIRST; p.c_round = 0;
+        p.epsilon = (T)prm->epsilon; p.epsilon_rel = (T)prm->epsilon_rel; p.delta = (T)prm->delta; p.max_step = (T)prm->max_step;
+        p.eps_gate = std::numeric_limits<T>::epsilon();
+        p.past = prm->past; p.max_iterations = prm->max_iterations; p.ls_kind = ls_kind;
+        p.fuse_first_trial = coupled ? 0 : 1;
+        p.ls_opt.linesearch = (ls_kind == 3) ? 3 : prm->linesearch;
+        p.ls_opt.max_linesearch = prm->max_linesearch;
+        p.ls_opt.min_step = (T)prm->min_step; p.ls_opt.max_step = (T)prm->max_step; p.ls_opt.ftol = (T)prm->ftol; p.ls_opt.wolfe = (T)prm->wolfe;
+        p.trace = trace_host ? s->d_trace : nullptr;
+        p.trace_cap = trace_host ? trace_cap : 0;
+        CU(ctx, cudaMemcpyAsync(p.x, x_inout + (size_t)b * ldx, vb, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    CU(ctx, cudaMemcpyAsync(s->d_state, hs, sizeof(PState<T>) * (size_t)B, cudaMemcpyHostToDevice, ctx->stream));
+    PCtl hc{};
+    hc.nactive = B;
+    hc.epoch = ctx->x_epoch;
+    CU(ctx, cudaMemcpyAsync(s->d_ctl, &hc, sizeof(hc), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemsetAsync(s->d_halo, 0, sizeof(double) * kHaloDoubles * (size_t)B, ctx->stream));
+
+    // ---- one cooperative launch: one CTA per SM (fewer when the vector has fewer tiles than SMs) ----
+    const int64_t ntiles = (s->n + kGramTE - 1) / kGramTE;
+    const int grid = (int)(ntiles < ctx->sm_count ? (ntiles < 1 ? 1 : ntiles) : ctx->sm_count);
+    const size_t smem = (size_t)kGramStages * 4 * kGramTE * sizeof(T);
+    CU(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPThreads, smem));
+    REQUIRE(ctx, per_sm >= 1, "the persistent solve kernel does not fit on an SM of this device");
+    PArgs<T> a{};
+    a.probs = static_cast<PState<T>*>(s->d_state); a.B = B; a.ctl = s->d_ctl; a.partials = s->d_partials; a.pstride = s->pstride;
+    a.n = s->n; a.ld = s->hist[0]->ld; a.xc = ctx->x_active ? ctx->x_comm : nullptr;
+    a.index_offset = index_offset; a.n_global = n_global;
+    void* kargs[] = {&a};
+    CU(ctx, cudaEventRecord(s->ev0, ctx->stream));
+    CU(ctx, cudaLaunchCooperativeKernel(kernel, dim3((unsigned)grid), dim3(kPThreads), kargs, smem, ctx->stream));
+    CU(ctx, cudaEventRecord(s->ev1, ctx->stream));
+    ctx->launches++;
+    CU(ctx, cudaMemcpyAsync(hs, s->d_state, sizeof(PState<T>) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(&hc, s->d_ctl, sizeof(hc), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->x_epoch = hc.epoch;
+    s->last_ctl = hc;
+    CU(ctx, cudaEventElapsedTime(&s->last_kernel_ms, s->ev0, s->ev1));
+    if (hc.abort) return fail(ctx, LBFGS_B200_ERR_CUDA, "the persistent solve gave up waiting at a grid / cross-rank barrier after %llu rounds (watchdog)", hc.rounds);
+
+    // the states tell where the results live after all the pointer rotations
+    for (int b = 0; b < B; b++)
+    {
+        const PState<T>& p = hs[b];
+        CU(ctx, cudaMemcpyAsync(x_inout + (size_t)b * ldx, p.x, vb, cudaMemcpyDeviceToDevice, ctx->stream));
+        s->final_g[b] = p.g;
+        s->final_x[b] = p.x;
+        lbfgs_b200_hist* h = s->hist[b];
+        h->head = p.head; h->ncorr = p.ncorr; h->gram_cur = p.gram_cur; h->pending = -1;
+        outs[b].status = p.status;
+        outs[b].niter = p.niter;
+        outs[b].nfev = p.nfev;
+        outs[b].fx = (double)p.fx;
+        outs[b].gnorm = (double)p.gnorm;
+        outs[b].rounds = p.rounds;
+    }
+    if (trace_host)
+    {
+        const long long cnt = hs[0].nfev < trace_cap ? hs[0].nfev : trace_cap;
+        CU(ctx, cudaMemcpyAsync(trace_host, s->d_trace, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return LBFGS_B200_OK;
+}
+
+extern "C" {
+
+#ifdef LBFGS_B200_PERSIST_F64
+lbfgs_b200_status lbfgs_b200_solver_create_batch(lbfgs_b200_ctx* ctx, int64_t n, int m, int elem_bytes, int batch, lbfgs_b200_solver** out)
+{
+    REQUIRE(ctx, ctx && out, "solver_create: NULL argument");
+    *out = nullptr;
+    REQUIRE(ctx, batch >= 1 && batch <= 4096, "solver_create: 1 <= batch <= 4096 (got %d)", batch);
+    REQUIRE(ctx, n >= 1 && m >= 1 && m <= 64, "solver_create: need n >= 1 and 1 <= m <= 64 (got n=%lld m=%d)", (long long)n, m);
+    REQUIRE(ctx, elem_bytes == 8 || elem_bytes == 4, "solver_create: elem_bytes must be 8 or 4");
+    lbfgs_b200_solver* s = new (std::nothrow) lbfgs_b200_solver();
+    if (!s) return fail(ctx, LBFGS_B200_ERR_ALLOC, "out of host memory");
+    s->ctx = ctx; s->n = n; s->m = m; s->elem = elem_bytes; s->B = batch;
+    s->final_g.assign((size_t)batch, nullptr);
+    s->final_x.assign((size_t)batch, nullptr);
+    lbfgs_b200_status st = LBFGS_B200_OK;
+    for (int b = 0; b < batch && st == LBFGS_B200_OK; b++)
+    {
+        lbfgs_b200_hist* h = nullptr;
+        st = lbfgs_b200_hist_create(ctx, &h, n, m, elem_bytes);
+        if (st == LBFGS_B200_OK) s->hist.push_back(h);
+    }
+    if (st) { lbfgs_b200_solver_destroy(s); return st; }
+    cudaError_t e = cudaSuccess;
+    s->vec_elems = (((size_t)n * elem_bytes + 255) & ~size_t(255)) / elem_bytes;
+    s->pstride = ((m * lb::kGramVals > 8 ? m * lb::kGramVals : 8) + 7) & ~7;
+    const size_t state_bytes = (elem_bytes == 8 ? sizeof(lb::PState<double>) : sizeof(lb::PState<float>)) * (size_t)batch;
+    if (e == cudaSuccess) e = cudaMalloc(&s->vec_slab, (size_t)batch * 7 * s->vec_elems * elem_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_state, state_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_ctl, sizeof(lb::PCtl));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_partials, sizeof(double) * (size_t)batch * s->pstride * ctx->sm_count);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_raw, sizeof(double) * (size_t)batch * s->pstride);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_halo, sizeof(double) * (size_t)batch * lb::kHaloDoubles);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
+    if (e != cudaSuccess)
+    {
+        lbfgs_b200_solver_destroy(s);
+        return fail(ctx, e == cudaErrorMemoryAllocation ? LBFGS_B200_ERR_ALLOC : LBFGS_B200_ERR_CUDA, "solver_create: %s", cudaGetErrorString(e));
+    }
+    *out = s;
+    return LBFGS_B200_OK;
+}
+
+lbfgs_b200_status lbfgs_b200_solver_create(lbfgs_b200_ctx* ctx, int64_t n, int m, int elem_bytes, lbfgs_b200_solver** out)
+{
+    return lbfgs_b200_solver_create_batch(ctx, n, m, elem_bytes, 1, out);
+}
+
+void lbfgs_b200_solver_destroy(lbfgs_b200_solver* s)
+{
+    if (!s) return;
+    if (s->ctx && s->ctx->stream) cudaStreamSynchronize(s->ctx->stream);
+    cudaFree(s->vec_slab);
+    cudaFree(s->d_state);
+    cudaFree(s->d_ctl);
+    cudaFree(s->d_partials);
+    cudaFree(s->d_raw);
+    cudaFree(s->d_halo);
+    cudaFree(s->d_trace);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    for (lbfgs_b200_hist* h : s->hist) lbfgs_b200_hist_destroy(h);
+    delete s;
+}
+
+int lbfgs_b200_solver_batch(const lbfgs_b200_solver* s) { return s ? s->B : 0; }
+lbfgs_b200_status lbfgs_b200_solver_profile(const lbfgs_b200_solver* s, double* kernel_ms, double* ms_by_op8, unsigned long long* rounds_by_op8,
+                                            double* alg_bytes_by_op8, double* sync_ms)
+{
+    if (!s) return LBFGS_B200_ERR_INVALID;
+    const lb::PCtl& c = s->last_ctl;
+    long long total = 0;
+    for (int k = 0; k < 8; k++) total += c.cyc_op[k];
+    const double scale = total > 0 ? (double)s->last_kernel_ms / (double)total : 0.0;   // CTA 0's cycles -> share of the event-timed kernel
+    if (kernel_ms) *kernel_ms = s->last_kernel_ms;
+    for (int k = 0; k < 8; k++)
+    {
+        if (ms_by_op8) ms_by_op8[k] = scale * (double)c.cyc_op[k];
+        if (rounds_by_op8) rounds_by_op8[k] = c.n_op[k];
+        if (alg_bytes_by_op8) alg_bytes_by_op8[k] = c.words_op[k] * (double)s->n * (double)s->elem;
+    }
+    if (sync_ms) *sync_ms = scale * (double)c.cyc_sync;
+    return LBFGS_B200_OK;
+}
+const void* lbfgs_b200_solver_final_grad(const lbfgs_b200_solver* s) { return s ? s->final_g[0] : nullptr; }
+const void* lbfgs_b200_solver_final_grad_of(const lbfgs_b200_solver* s, int b) { return (s && b >= 0 && b < s->B) ? s->final_g[(size_t)b] : nullptr; }
+lbfgs_b200_hist* lbfgs_b200_solver_history(lbfgs_b200_solver* s) { return s ? s->hist[0] : nullptr; }
+lbfgs_b200_hist* lbfgs_b200_solver_history_of(lbfgs_b200_solver* s, int b) { return (s && b >= 0 && b < s->B) ? s->hist[(size_t)b] : nullptr; }
+
+lbfgs_b200_status lbfgs_b200_solver_minimize_f64(lbfgs_b200_solver* s, int objective, const double* data0, const double* data1,
+                                                 const lbfgs_b200_param* prm, int line_search, double* x_inout, double* trace_host,
+                                                 long long trace_cap, lbfgs_b200_outcome* out)
+{
+    if (!s || !s->ctx) return LBFGS_B200_ERR_INVALID;
+    if (s->B != 1) return fail(s->ctx, LBFGS_B200_ERR_INVALID, "solver_minimize: the solver holds a batch of %d problems, use solver_minimize_batch", s->B);
+    return solver_minimize<double>(s, objective, data0, data1, 0, prm, line_search, x_inout, s->n, trace_host, trace_cap, out);
+}
+lbfgs_b200_status lbfgs_b200_solver_minimize_batch_f64(lbfgs_b200_solver* s, int objective, const double* data0, const double* data1, int64_t ldd,
+                                                       const lbfgs_b200_param* prm, int line_search, double* x_inout, int64_t ldx,
+                                                       lbfgs_b200_outcome* outs)
+{
+    if (!s || !s->ctx) return LBFGS_B200_ERR_INVALID;
+    return solver_minimize<double>(s, objective, data0, data1, ldd, prm, line_search, x_inout, ldx, nullptr, 0, outs);
+}
+#endif  // LBFGS_B200_PERSIST_F64
+
+#ifdef LBFGS_B200_PERSIST_F32
+lbfgs_b200_status lbfgs_b200_solver_minimize_f32(lbfgs_b200_solver* s, int objective, const float* data0, const float* data1,
+                                                 const lbfgs_b200_param* prm, int line_search, float* x_inout, double* trace_host,
+                                                 long long trace_cap, lbfgs_b200_outcome* out)
+{
+    if (!s || !s->ctx) return LBFGS_B200_ERR_INVALID;
+    if (s->B != 1) return fail(s->ctx, LBFGS_B200_ERR_INVALID, "solver_minimize: the solver holds a batch of %d problems, use solver_minimize_batch", s->B);
+    return solver_minimize<float>(s, objective, data0, data1, 0, prm, line_search, x_inout, s->n, trace_host, trace_cap, out);
+}
+lbfgs_b200_status lbfgs_b200_solver_minimize_batch_f32(lbfgs_b200_solver* s, int objective, const float* data0, const float* data1, int64_t ldd,
+                                                       const lbfgs_b200_param* prm, int line_search, float* x_inout, int64_t ldx,
+                                                       lbfgs_b200_outcome* outs)
+{
+    if (!s || !s->ctx) return LBFGS_B200_ERR_INVALID;
+    return solver_minimize<float>(s, objective, data0, data1, ldd, prm, line_search, x_inout, ldx, nullptr, 0, outs);
+}
+
+#endif  // LBFGS_B200_PERSIST_F32
+
+}  // extern "C"

@@ -327,6 +327,8 @@ __device__ __forceinline__ void gram_dots_body(const GramDotsArgs<T>& a, double*
             const int nstage = (stage + 1 == kGramStages) ? 0 : stage + 1;
             if (upcoming < ntiles) { wait_tile(upcoming, nstage); form_tile(upcoming, nstage); }
         }
+        // the stage was read (and, when forming, rewritten) through the generic proxy: order that before the bulk copy that re-arms it
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();  // everyone is done with this stage's tile (and the next tile's pair is formed)
         if (next_tile < ntiles) stage_tile(next_tile, stage);
         next_tile += gridDim.x;
@@ -413,6 +415,7 @@ template <class T> struct GramSolveArgs
 // smem layout (T units): SY[c*c] | YY[c*c] | coef[2c+1] | alpha[c] ; everything indexed by AGE (0 = newest).
 inline size_t gram_solve_smem_elems(int c) { return (size_t)2 * c * c + 3 * c + 1; }
 
+// All global reads go through L2 (__ldcg): inside the persistent solve these scalars are rewritten by another CTA between rounds.
 template <class T>
 __device__ void gram_solve_in_smem(const GramSolveArgs<T>& g, T* sm, bool writer)
 {
@@ -426,19 +429,19 @@ __device__ void gram_solve_in_smem(const GramSolveArgs<T>& g, T* sm, bool writer
     {
         const int i = idx / c, j = idx % c;
         const int pi = g.slots[i], pj = g.slots[j];
-        T sy = g.SY_in[pi * M + pj], yy = g.YY_in[pi * M + pj];
+        T sy = __ldcg(g.SY_in + pi * M + pj), yy = __ldcg(g.YY_in + pi * M + pj);
         if (g.new_slot >= 0)
         {
-            if (j == 0) { sy = (T)g.raw[i * kGramVals + 2]; yy = (T)g.raw[i * kGramVals + 3]; }       // s_i'y_new, y_i'y_new
-            else if (i == 0) { sy = (T)g.raw[j * kGramVals + 4]; yy = (T)g.raw[j * kGramVals + 3]; }  // s_new'y_j, y_new'y_j
+            if (j == 0) { sy = (T)__ldcg(g.raw + i * kGramVals + 2); yy = (T)__ldcg(g.raw + i * kGramVals + 3); }       // s_i'y_new, y_i'y_new
+            else if (i == 0) { sy = (T)__ldcg(g.raw + j * kGramVals + 4); yy = (T)__ldcg(g.raw + j * kGramVals + 3); }  // s_new'y_j, y_new'y_j
         }
         sSY[idx] = sy;
         sYY[idx] = yy;
         if (writer && g.new_slot >= 0)
         {
-            T ss = g.SS_in[pi * M + pj];
-            if (j == 0) ss = (T)g.raw[i * kGramVals + 5];        // s_i's_new
-            else if (i == 0) ss = (T)g.raw[j * kGramVals + 5];   // s_new's_j
+            T ss = __ldcg(g.SS_in + pi * M + pj);
+            if (j == 0) ss = (T)__ldcg(g.raw + i * kGramVals + 5);        // s_i's_new
+            else if (i == 0) ss = (T)__ldcg(g.raw + j * kGramVals + 5);   // s_new's_j
             g.SY_out[pi * M + pj] = sy;
             g.YY_out[pi * M + pj] = yy;
             g.SS_out[pi * M + pj] = ss;
@@ -447,12 +450,12 @@ __device__ void gram_solve_in_smem(const GramSolveArgs<T>& g, T* sm, bool writer
     __syncthreads();
     if (tid == 0 && g.with_v)
     {
-        const T theta = g.ov_theta_on ? g.ov_theta : *g.theta;
-        auto ys_of = [&](int i) { return (g.slots[i] == g.ov_slot) ? g.ov_ys : g.ys[g.slots[i]]; };
+        const T theta = g.ov_theta_on ? g.ov_theta : __ldcg(g.theta);
+        auto ys_of = [&](int i) { return (g.slots[i] == g.ov_slot) ? g.ov_ys : __ldcg(g.ys + g.slots[i]); };
         // backward sweep (BFGSMat.h:285-290): alpha_i = s_i'q / ys_i with q = a*v - sum_{newer t} alpha_t y_t
         for (int i = 0; i < c; i++)
         {
-            T sq = g.a * (T)g.raw[i * kGramVals + 0];
+            T sq = g.a * (T)__ldcg(g.raw + i * kGramVals + 0);
             for (int t = 0; t < i; t++) sq -= al[t] * sSY[i * c + t];
             al[i] = sq / ys_of(i);
         }
@@ -460,7 +463,7 @@ __device__ void gram_solve_in_smem(const GramSolveArgs<T>& g, T* sm, bool writer
         T* cs = coef + 1 + c;
         for (int i = c - 1; i >= 0; i--)
         {
-            T yq = g.a * (T)g.raw[i * kGramVals + 1];
+            T yq = g.a * (T)__ldcg(g.raw + i * kGramVals + 1);
             for (int t = 0; t < c; t++) yq -= al[t] * sYY[i * c + t];
             T yr = yq / theta;
             for (int t = c - 1; t > i; t--) yr += cs[t] * sSY[t * c + i];

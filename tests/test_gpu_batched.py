@@ -38,3 +38,52 @@ def test_batch_reports_per_problem_failures():
     X0 = np.zeros((3, 8))
     res, _, _ = lb.solve_batch(lb.OBJ_ROSENBROCK_PAIRED, X0, lb.LBFGSParam(max_linesearch=1), "Backtracking", threads=2)
     assert [r["status"] for r in res] == ["runtime_error"] * 3
+
+
+# ---- the batch as ONE persistent kernel launch (lbfgs_b200_solver_minimize_batch / LBFGSpp::LBFGSBatchSolver) --------------------
+def test_persistent_batch_equals_lone_solves_and_cpu_checker(orc):
+    import pyoracle as po
+    B, n = 10, 4096
+    X0 = np.stack([np.random.default_rng(1000 + b).uniform(-1, 1, n) for b in range(B)])
+    prm = lb.LBFGSParam(m=10)
+    bs = lb.BatchSession(lb.OBJ_ROSENBROCK_PAIRED, X0, prm, "MoreThuente")
+    res, X, _ = bs.solve()
+    res2, X2, _ = bs.solve()          # the session is reusable and repeatable
+    bs.close()
+    cprm = orc.default_param(m=10)
+    for b in range(B):
+        single = lb.LBFGSSolver(prm, "MoreThuente", resident=True).minimize(lb.OBJ_ROSENBROCK_PAIRED, X0[b])
+        assert res[b]["status"] == "ok"
+        assert (res[b]["niter"], res[b]["nfev"], res[b]["fx"]) == (single["niter"], single["nfev"], single["fx"])
+        assert np.array_equal(X[b], single["x"]) and np.array_equal(X2[b], X[b]) and res2[b] == res[b]
+        # against the CPU checker on the batch's own seeds: these are 100+-iteration runs, so the optimum is compared and the
+        # iteration count must lie within what two summation orders of the checker itself give, widened by 25 %
+        c1 = orc.lbfgs(po.OBJ_ROSENBROCK_PAIRED, X0[b], po.LS_MORE_THUENTE, cprm, sum_mode=po.SUM_SEQUENTIAL)
+        c2 = orc.lbfgs(po.OBJ_ROSENBROCK_PAIRED, X0[b], po.LS_MORE_THUENTE, cprm, sum_mode=po.SUM_LANES8)
+        lo, hi = min(c1["niter"], c2["niter"]), max(c1["niter"], c2["niter"])
+        assert 0.75 * lo <= res[b]["niter"] <= 1.25 * hi, (b, res[b]["niter"], c1["niter"], c2["niter"])
+        assert np.max(np.abs(X[b] - 1.0)) <= 3.0 * max(np.max(np.abs(c1["x"] - 1.0)), np.max(np.abs(c2["x"] - 1.0)), 1e-4)
+
+
+def test_persistent_batch_problems_leave_as_they_converge():
+    """Problems of very different length in one batch: an already-optimal start (1 evaluation), x0 = 0 (22 iterations) and random
+    starts (100+): each must report its own counts, and the short ones must not be disturbed by the long ones."""
+    n = 2048
+    X0 = np.stack([np.ones(n), np.zeros(n), np.random.default_rng(7).uniform(-1, 1, n), np.zeros(n)])
+    bs = lb.BatchSession(lb.OBJ_ROSENBROCK_PAIRED, X0, lb.LBFGSParam(m=10), "MoreThuente")
+    res, X, _ = bs.solve()
+    bs.close()
+    assert (res[0]["niter"], res[0]["nfev"]) == (1, 1)
+    lone = lb.LBFGSSolver(lb.LBFGSParam(m=10), "MoreThuente", resident=True).minimize(lb.OBJ_ROSENBROCK_PAIRED, np.zeros(n))
+    for b in (1, 3):
+        assert (res[b]["niter"], res[b]["nfev"], res[b]["fx"]) == (lone["niter"], lone["nfev"], lone["fx"])
+        assert np.array_equal(X[b], lone["x"])
+    assert res[2]["niter"] > res[1]["niter"] and res[2]["rounds"] > res[1]["rounds"]
+
+
+def test_persistent_batch_reports_per_problem_failures():
+    X0 = np.zeros((3, 8))
+    bs = lb.BatchSession(lb.OBJ_ROSENBROCK_PAIRED, X0, lb.LBFGSParam(max_linesearch=1), "Backtracking")
+    res, _, _ = bs.solve()
+    bs.close()
+    assert [r["status"] for r in res] == ["runtime_error"] * 3
