@@ -421,8 +421,8 @@ int lbfgsb200_drv_session_solve(void* handle, int from_host, int to_host, drv_re
 
 const double* lbfgsb200_drv_session_result(void* handle) { return static_cast<Session*>(handle)->pinned_out; }
 
-// accounting of the session's last device-resident solve (lbfgs_b200_solver_profile); returns 1 when the session runs the
-// host-driven loop
+// accounting of the session's last device-resident solve (lbfgs_b200_solver_profile; sync_ms has 2 slots); returns 1 when the
+// session runs the host-driven loop
 int lbfgsb200_drv_session_profile(void* handle, double* kernel_ms, double* ms_by_op8, unsigned long long* rounds_by_op8, double* alg_bytes_by_op8,
                                   double* sync_ms)
 {

@@ -1,6 +1,6 @@
 // persist.cuh -- the device-resident L-BFGS solve: LBFGSSolver::minimize() (reference LBFGS.h:78-173) for built-in objectives as
 // ONE persistent cooperative kernel launch, for one problem or for a batch of B independent problems (BASELINE config 5).
-// Included at the end of lbfgs_b200.cu.
+// Included by persist_f64.cu / persist_f32.cu.
 //
 // The kernel is a "phase machine".  One CTA per SM (768 threads), all co-resident (cooperative launch).  Work proceeds in ROUNDS;
 // in a round every problem that is still running executes the ONE streaming pass its state asks for:
@@ -12,15 +12,21 @@
 //     COMBINE_TRIAL  COMBINE + the first trial of the next line search in the same pass: the reference restarts every search
 //                    at step = 1 (LBFGS.h:168), so x1 = x + d, g1 = grad f(x1) ; {g.d, f1, g1.d, g1.g1, x1.x1}
 //     RESTORE        x = xp, g = gp (a search that never improved on its start point; LineSearchMoreThuente.h:602-614)
-// Every CTA owns the same contiguous chunk [t0, t1) of 2048-element tiles of EVERY vector in EVERY pass, so a CTA only ever reads
-// vector elements it wrote itself (halo coordinates excepted, those are read through L2).  Between rounds there is one grid-wide
-// synchronisation: CTAs deposit their partial sums in fixed slots, CTA 0 adds them in a fixed order (deterministic: no
+// Every CTA owns the same contiguous chunk (256-element granularity) of EVERY vector in EVERY pass, so a CTA only ever reads vector
+// elements it wrote itself (halo coordinates excepted, those are read through L2) and streams long contiguous runs.  Between rounds there is one
+// grid-wide synchronisation: CTAs deposit their partial sums in fixed slots, CTA 0 adds them in a fixed order (deterministic: no
 // floating-point atomics, result independent of which other problems are in flight), exchanges them with the other ranks when
-// n is sharded (ONE exchange per round carrying the sums of all running problems = "one all-reduce of a B-vector per dot"), and
-// runs each problem's scalar logic: line-search state machine (the cores of include/LBFGSpp/LineSearchCore.h, the same code the
-// host front uses), convergence tests (LBFGS.h:137-154), curvature gate (:161), ring bookkeeping (BFGSMat.h:81-97), buffer rotation
-// (pointer swaps).  The host is not involved between launch and completion: 1 launch per minimize(), 2 + (T - 1) rounds per
-// iteration with T line-search trials.
+// n is sharded (ONE exchange per round carrying the sums of all running problems = "one all-reduce of a B-vector per dot"), runs
+// each problem's scalar logic -- line-search state machine (the cores of include/LBFGSpp/LineSearchCore.h, the same code the host
+// front uses), convergence tests (LBFGS.h:137-154), curvature gate (:161), ring bookkeeping (BFGSMat.h:81-97), buffer rotation
+// (pointer swaps) -- and publishes one 128-byte descriptor per problem that tells every CTA what the next round does.  The host is
+// not involved between launch and completion: 1 launch per minimize(), 2 + (T - 1) rounds per iteration with T line-search trials.
+//
+// Data movement: the right-hand vectors of the dots pass and ALL operands of the combination pass (g, x and the 2c history
+// columns, tile by tile) are staged into shared memory by TMA bulk copies (cp.async.bulk + mbarrier) in a multi-stage ring, so the
+// bytes in flight per SM are set by the ring (~90-180 KB), not by registers; the S/Y columns of the dots pass stream into registers
+// with 256-bit evict-first loads (one warp per column pair).  Vectors owned by the solver are padded to whole 256-byte lines, so
+// every tile -- the ragged end of a vector included -- is a legal bulk copy; lanes past n are masked in the arithmetic.
 #pragma once
 
 #include "../../include/LBFGSpp/LineSearchCore.h"
@@ -30,15 +36,19 @@ namespace lb {
 constexpr int kMaxPast = 64;
 constexpr int kPThreads = kGramMaxThreads;   // 768: one CTA per SM
 constexpr int kPWarps = kPThreads / 32;
+constexpr int kPGrain = 256;                 // chunk boundaries are multiples of this many elements
+constexpr int kPStageBytes = kGramStages * 4 * kGramTE * 8;   // dynamic shared memory of the kernel: 196608 bytes
+constexpr int kPMaxStages = 4;
+constexpr int kPCache = 4;                   // problems whose leader-side state is kept in shared memory
 
 enum { POP_IDLE = 0, POP_FIRST = 1, POP_TRIAL = 2, POP_DOTS_FORM = 3, POP_DOTS_PLAIN = 4, POP_COMBINE = 5, POP_COMBINE_TRIAL = 6, POP_RESTORE = 7 };
 
-// ---- per-problem state (device memory; written by the leader CTA only, read by everyone through L2) --------------------------
+// ---- per-problem state (device memory; the leader CTA's working copy) ----------------------------------------------------------
 template <class T> struct PState
 {
     // vectors (rotate by pointer swap)
     T *x, *xp, *g, *gp, *drt, *x_lo, *g_lo;
-    // history storage (fixed)
+    // history storage (fixed for the duration of the kernel: other CTAs read these fields with ordinary loads)
     T *S, *Y, *ys, *alpha, *theta;
     T *SY[2], *YY[2], *SS[2];
     const T *data0, *data1;
@@ -72,10 +82,20 @@ template <class T> struct PState
     long long rounds;           // rounds this problem took part in
 };
 
-struct PCtl
+// what every CTA needs to know about a problem's next round: one 128-byte line, written by the leader, read through L2
+template <class T> struct alignas(128) PRound
 {
-    unsigned arrive;            // grid barrier: arrivals so far (monotonic)
-    unsigned release;           // grid barrier: last round released by the leader
+    T *x, *xp, *g, *gp, *drt;
+    T step;
+    int op, c_round, head, pending, gram_cur, pad;
+};
+
+struct alignas(128) PCtl
+{
+    unsigned arrive;            // grid barrier: arrivals so far (monotonic); a cache line of its own
+    unsigned pad0[31];
+    unsigned release;           // grid barrier: last episode released by the leader; bit 31 = nothing left to do
+    unsigned pad1[31];
     int abort;                  // watchdog tripped (a wait exceeded its budget): everybody leaves
     int nactive;                // problems still running
     unsigned long long epoch;   // cross-rank exchange sequence number (continues the context's)
@@ -85,13 +105,16 @@ struct PCtl
     // CTA + the leader's work), and the algorithmic n-words of the passes (what the design has to move, see words_of)
     long long cyc_op[8];
     long long cyc_sync;
+    long long cyc_wait_all;     // of cyc_sync: from CTA 0's own arrival until the last CTA has arrived
     unsigned long long n_op[8];
     double words_op[8];
 };
+constexpr unsigned kPStopBit = 0x80000000u;
 
 template <class T> struct PArgs
 {
     PState<T>* probs;
+    PRound<T>* rounds;
     int B;
     PCtl* ctl;
     double* partials;           // [B][pstride][G]
@@ -162,22 +185,40 @@ template <class T> struct PObjMaker<T, QuadTridiag<T> >
 // ---- shared memory of the kernel ----------------------------------------------------------------------------------------------
 struct PShared
 {
-    uint64_t full_bar[kGramStages];
+    uint64_t full_bar[kPMaxStages];
     double red[kPWarps][3 * kGramVals];     // block reduction scratch (dots: ROUNDS*6 values per warp)
+    double coef[2 * kMaxM + 2];             // combination coefficients {cv, cy[c], cs[c]} (stored as T)
+    const void* vecs[2 * kMaxM + 2];        // combination pass: the staged vectors {g, (x), y_0.., s_0..} in coefficient order
     unsigned char slots[kMaxM];
-    const void* ycol[kMaxM];
-    const void* scol[kMaxM];
-    int flag;
+    unsigned char ops[4096];                // this round's op of every problem
 };
 
-// this CTA's chunk of tiles: K = min(G, ntiles) CTAs share the tiles as evenly as whole tiles allow
-__device__ __forceinline__ void chunk_of(int64_t ntiles, int cta, int G, int64_t& t0, int64_t& t1)
+// Ownership.  CTA i owns the contiguous chunk [c0, c1) of every vector (boundaries on multiples of kPGrain elements, the chunks
+// differ by at most one grain) in EVERY pass: a CTA only ever reads what it wrote itself, and every CTA streams long contiguous
+// runs of each vector (measured faster than dealing 2048-element blocks round-robin: 14.3 vs 15.1 ms per config-2 solve).
+struct Own
 {
-    const int64_t K = ntiles < G ? ntiles : G;
-    if (cta >= K) { t0 = t1 = 0; return; }
-    t0 = (ntiles * cta) / K;
-    t1 = (ntiles * (cta + 1)) / K;
-}
+    int64_t n;
+    int G, cta, BS;   // BS: largest tile a pass may use
+    int64_t c0, c1;
+    __device__ __forceinline__ Own(int64_t n_, int G_, int cta_) : n(n_), G(G_), cta(cta_), BS(2048)
+    {
+        const int64_t units = (n + kPGrain - 1) / kPGrain;
+        const int64_t K = units < G ? units : G;
+        if (cta >= K) { c0 = c1 = 0; return; }
+        c0 = ((units * cta) / K) * kPGrain;
+        c1 = ((units * (cta + 1)) / K) * kPGrain;
+        if (c1 > n) c1 = n;
+    }
+    // tiles of TE elements: number owned, first element and length of the t-th (the last one may be shorter)
+    __device__ __forceinline__ int64_t ntiles(int TE) const { return (c1 - c0 + TE - 1) / TE; }
+    __device__ __forceinline__ int64_t start(int64_t t, int TE) const { return c0 + t * TE; }
+    __device__ __forceinline__ int len(int64_t t, int TE) const
+    {
+        const int64_t rest = c1 - start(t, TE);
+        return rest <= 0 ? 0 : (rest < TE ? (int)rest : TE);
+    }
+};
 
 // block-wide sums of NV per-thread values -> dst[k * G] (this CTA's slot of value k).  All threads call.
 template <int NV> __device__ __forceinline__ void block_sums(const double (&acc)[NV], PShared& sh, double* dst, int G)
@@ -200,18 +241,26 @@ template <int NV> __device__ __forceinline__ void block_sums(const double (&acc)
     }
 }
 
+template <class T> __device__ __forceinline__ void mask_pack(Pack<T>& p, int cnt)
+{
+#pragma unroll
+    for (int k = 0; k < 4; k++) p.v[k] = (k < cnt) ? p.v[k] : T(0);
+}
+
 // ---- FIRST / TRIAL -------------------------------------------------------------------------------------------------------------
-// MODE 0: FIRST (evaluate at x, write g and d = -g) ; MODE 1: TRIAL (x = xp + step*d, write x and g)
+// MODE 0: FIRST (evaluate at x, write g and d = -g) ; MODE 1: TRIAL (x = xp + step*d, write x and g).  Operands stream through
+// registers with 256-bit loads/stores (a shared-memory staged variant measured slower for this 1:1 read/write pass).
 template <class T, class OBJ, int MODE>
-__device__ __forceinline__ void p_trial(const OBJ& obj, int64_t n, int64_t e0, int64_t e1, const T* __restrict__ xp, const T* __restrict__ d, T step,
+__device__ __forceinline__ void p_trial(const OBJ& obj, const Own& own, const T* __restrict__ xp, const T* __restrict__ d, T step,
                                         T* __restrict__ x, T* __restrict__ g, T* __restrict__ dout, PShared& sh, double* dst, int G)
 {
     T acc[4] = {T(0), T(0), T(0), T(0)};
-    const int64_t p1 = (e1 + 3) >> 2;
+    const int64_t n = own.n;
+    const int64_t p1 = (own.c1 + 3) >> 2;
 #pragma unroll 2
-    for (int64_t p = (e0 >> 2) + threadIdx.x; p < p1; p += kPThreads)
+    for (int64_t q = (own.c0 >> 2) + threadIdx.x; q < p1; q += kPThreads)
     {
-        const int64_t i0 = p << 2;
+        const int64_t i0 = q << 2;
         const int cnt = (n - i0 >= 4) ? 4 : int(n - i0);
         T xv[4], dv[4] = {T(0), T(0), T(0), T(0)}, gv[4];
         T xl = T(0), xr = T(0);
@@ -262,12 +311,13 @@ __device__ __forceinline__ void p_trial(const OBJ& obj, int64_t n, int64_t e0, i
 
 // ---- RESTORE --------------------------------------------------------------------------------------------------------------------
 template <class T>
-__device__ __forceinline__ void p_restore(int64_t n, int64_t e0, int64_t e1, const T* __restrict__ xp, const T* __restrict__ gp, T* __restrict__ x, T* __restrict__ g)
+__device__ __forceinline__ void p_restore(const Own& own, const T* __restrict__ xp, const T* __restrict__ gp, T* __restrict__ x, T* __restrict__ g)
 {
-    const int64_t p1 = (e1 + 3) >> 2;
-    for (int64_t p = (e0 >> 2) + threadIdx.x; p < p1; p += kPThreads)
+    const int64_t n = own.n;
+    const int64_t p1 = (own.c1 + 3) >> 2;
+    for (int64_t q = (own.c0 >> 2) + threadIdx.x; q < p1; q += kPThreads)
     {
-        const int64_t i0 = p << 2;
+        const int64_t i0 = q << 2;
         const int cnt = (n - i0 >= 4) ? 4 : int(n - i0);
         store4<T, Hint::Plain, true>(x, i0, cnt, load4<T, Hint::Stream, true>(xp, i0, cnt));
         store4<T, Hint::Plain, true>(g, i0, cnt, load4<T, Hint::Stream, true>(gp, i0, cnt));
@@ -275,9 +325,11 @@ __device__ __forceinline__ void p_restore(int64_t n, int64_t e0, int64_t e1, con
 }
 
 // ---- DOTS -----------------------------------------------------------------------------------------------------------------------
-// [S Y]'[v s_new y_new] over this CTA's tiles; FORM: the newest pair is formed on the fly from (x, xp, v = g, gp) into ring slot
-// `new_slot` and takes part as the newest column (see k_pair_dots in two_loop_gram.cuh: same tile pipeline, TMA-staged right-hand
-// vectors, S/Y columns streamed into registers).  PLAIN: s.v and y.v only.
+// [S Y]'[v s_new y_new] over this CTA's chunk; FORM: the newest pair is formed on the fly from (x, xp, v = g, gp) into ring slot
+// `new_slot` and takes part as the newest column (same tile pipeline as k_pair_dots in two_loop_gram.cuh: TMA-staged right-hand
+// vectors, S/Y columns streamed into registers, one warp -- or `split` warps -- per column pair).  PLAIN: s.v and y.v only.
+// Tiles are kGramTE elements; the last tile of a chunk may be shorter (a multiple of 32 elements is copied, lanes past its length
+// are masked).
 template <class T> struct PDots
 {
     int64_t n, ld;
@@ -290,74 +342,50 @@ template <class T> struct PDots
 };
 
 template <class T, int ROUNDS, bool FORM>
-__device__ __forceinline__ void p_dots(const PDots<T>& a, int64_t t0, int64_t t1, T* tiles, PShared& sh, unsigned& phase_bits, double* dst, int G)
+__device__ __forceinline__ void p_dots(const PDots<T>& a, const Own& own, T* tiles, PShared& sh, unsigned& phase_bits, double* dst, int G)
 {
     constexpr int NT = 4;                                        // stage stride in vectors (FORM uses all four)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int my_col = warp / a.split, my_part = warp % a.split;
-    const int part_len = kGramTE / a.split;
+    const int DTE = own.BS < kGramTE ? own.BS : kGramTE;          // tile length (the stage stride stays kGramTE)
+    const int part_len = DTE / a.split;                           // >= 256 (the caller bounds `split`)
     uint64_t* full_bar = sh.full_bar;
+    int64_t ntl = own.ntiles(DTE);
+    while (ntl > 0 && own.len(ntl - 1, DTE) == 0) ntl--;          // trailing tiles of the vector's last block may be empty
 
-    auto tile_is_tma = [&](int64_t tile) { return a.n - tile * kGramTE >= kGramTE; };
-    auto stage_tile = [&](int64_t tile, int stage) {
+    auto tile_len = [&](int64_t t) { return own.len(t, DTE); };
+    auto stage_tile = [&](int64_t t, int stage) {
+        if (tid != 0) return;
         T* dstt = tiles + (size_t)stage * NT * kGramTE;
-        const int64_t e0 = tile * kGramTE;
-        const int64_t len = (a.n - e0 < kGramTE) ? (a.n - e0) : kGramTE;
-        if (len == kGramTE)
+        const int64_t e0 = own.start(t, DTE);
+        const unsigned bytes = (unsigned)((tile_len(t) + 31) & ~31) * (unsigned)sizeof(T);   // whole 32-element groups: inside the padding
+        // the stage was last touched through the generic proxy (LDS of the dots, STS of form_tile): order those accesses before the
+        // bulk copy that overwrites it
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if constexpr (FORM)
         {
-            if (tid == 0)
-            {
-                const unsigned bytes = kGramTE * sizeof(T);
-                // the stage was last touched through the generic proxy (LDS of the dots, STS of form_tile): order those accesses
-                // before the bulk copy that overwrites it
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                if constexpr (FORM)
-                {
-                    mbar_expect_tx(&full_bar[stage], bytes * 4);
-                    tma_load_1d(dstt, a.v + e0, bytes, &full_bar[stage]);
-                    tma_load_1d(dstt + kGramTE, a.fx + e0, bytes, &full_bar[stage]);
-                    tma_load_1d(dstt + 2 * kGramTE, a.fgp + e0, bytes, &full_bar[stage]);
-                    tma_load_1d(dstt + 3 * kGramTE, a.fxp + e0, bytes, &full_bar[stage]);
-                }
-                else
-                {
-                    mbar_expect_tx(&full_bar[stage], bytes);
-                    tma_load_1d(dstt, a.v + e0, bytes, &full_bar[stage]);
-                }
-            }
+            mbar_expect_tx(&full_bar[stage], bytes * 4);
+            tma_load_1d(dstt, a.v + e0, bytes, &full_bar[stage]);
+            tma_load_1d(dstt + kGramTE, a.fx + e0, bytes, &full_bar[stage]);
+            tma_load_1d(dstt + 2 * kGramTE, a.fgp + e0, bytes, &full_bar[stage]);
+            tma_load_1d(dstt + 3 * kGramTE, a.fxp + e0, bytes, &full_bar[stage]);
         }
         else
         {
-            for (int i = tid; i < kGramTE; i += kPThreads)
-            {
-                const bool ok = i < len;
-                if constexpr (FORM)
-                {
-                    const T gv = ok ? a.v[e0 + i] : T(0);
-                    const T sv = ok ? a.fx[e0 + i] - a.fxp[e0 + i] : T(0);
-                    const T yv = ok ? gv - a.fgp[e0 + i] : T(0);
-                    dstt[i] = gv;
-                    dstt[kGramTE + i] = sv;
-                    dstt[2 * kGramTE + i] = yv;
-                    if (ok) { a.s_out[e0 + i] = sv; a.y_out[e0 + i] = yv; }
-                }
-                else
-                    dstt[i] = ok ? a.v[e0 + i] : T(0);
-            }
+            mbar_expect_tx(&full_bar[stage], bytes);
+            tma_load_1d(dstt, a.v + e0, bytes, &full_bar[stage]);
         }
     };
-    auto wait_tile = [&](int64_t tile, int st) {
-        if (tile_is_tma(tile))
-        {
-            mbar_wait(&full_bar[st], (phase_bits >> st) & 1u);
-            phase_bits ^= (1u << st);
-        }
+    auto wait_tile = [&](int st) {
+        mbar_wait(&full_bar[st], (phase_bits >> st) & 1u);
+        phase_bits ^= (1u << st);
     };
-    auto form_tile = [&](int64_t tile, int st) {
-        if (!tile_is_tma(tile)) return;
+    // FORM: turn a landed tile {g, x, gp, xp} into {g, s = x - xp, y = g - gp} in place and write s, y to the ring columns
+    auto form_tile = [&](int64_t t, int st) {
         T* tt = tiles + (size_t)st * NT * kGramTE;
-        const int64_t e0f = tile * kGramTE;
-        for (int i = tid * 4; i < kGramTE; i += kPThreads * 4)
+        const int64_t e0f = own.start(t, DTE);
+        const int lim = (tile_len(t) + 31) & ~31;
+        for (int i = tid * 4; i < lim; i += kPThreads * 4)
         {
             Pack<T> ps, py;
 #pragma unroll
@@ -379,29 +407,25 @@ __device__ __forceinline__ void p_dots(const PDots<T>& a, int64_t t0, int64_t t1
 #pragma unroll
         for (int k = 0; k < kGramVals; k++) acc[r][k] = T(0);
 
-    __syncthreads();   // the stages (and sh.slots) are free: every thread has left the previous phase
-    int64_t next_tile = t0;
+    __syncthreads();   // the stages (and sh.slots) are free: every thread has left the previous pass
+    int64_t next_tile = 0;
     for (int s = 0; s < kGramStages; s++, next_tile++)
-        if (next_tile < t1) stage_tile(next_tile, s);
+        if (next_tile < ntl) stage_tile(next_tile, s);
     if constexpr (FORM)
     {
-        if (t0 < t1) { wait_tile(t0, 0); form_tile(t0, 0); }
+        if (ntl > 0) { wait_tile(0); form_tile(0, 0); }
         __syncthreads();
     }
     int stage = 0;
-    for (int64_t tile = t0; tile < t1; tile++)
+    for (int64_t t = 0; t < ntl; t++)
     {
-        if constexpr (!FORM)
-        {
-            if (tile_is_tma(tile)) wait_tile(tile, stage);
-            else __syncthreads();
-        }
+        if constexpr (!FORM) wait_tile(stage);
         const T* vt = tiles + (size_t)stage * NT * kGramTE;
         const T* snt = vt + kGramTE;
         const T* ynt = vt + 2 * kGramTE;
-        const int64_t e0 = tile * kGramTE;
-        const int64_t len = (a.n - e0 < kGramTE) ? (a.n - e0) : kGramTE;
-        const bool full_tile = (len == kGramTE);
+        const int64_t e0 = own.start(t, DTE);
+        const int len = tile_len(t);
+        const bool full_tile = (len == DTE);
 #pragma unroll
         for (int r = 0; r < ROUNDS; r++)
         {
@@ -425,7 +449,7 @@ __device__ __forceinline__ void p_dots(const PDots<T>& a, int64_t t0, int64_t t1
                             ps[u] = lds_pack(snt + off, lane);
                             py[u] = lds_pack(ynt + off, lane);
                         }
-                        else if (full_tile)
+                        else if (full_tile || off + 4 <= len)
                         {
                             ps[u] = ld_pack<Hint::Stream>(scol + off);
                             py[u] = ld_pack<Hint::Stream>(ycol + off);
@@ -445,7 +469,14 @@ __device__ __forceinline__ void p_dots(const PDots<T>& a, int64_t t0, int64_t t1
                     for (int u = 0; u < 2; u++)
                     {
                         const int off = base + u * 128;
-                        const Pack<T> pv = lds_pack(vt + off, lane);
+                        Pack<T> pv = lds_pack(vt + off, lane);
+                        if (!full_tile)
+                        {
+                            const int cnt = len - off;            // lanes past the tile's length: zero on both sides of every product
+                            mask_pack(pv, cnt);
+                            mask_pack(ps[u], cnt);
+                            mask_pack(py[u], cnt);
+                        }
 #pragma unroll
                         for (int k = 0; k < 4; k++)
                         {
@@ -454,7 +485,12 @@ __device__ __forceinline__ void p_dots(const PDots<T>& a, int64_t t0, int64_t t1
                         }
                         if constexpr (FORM)
                         {
-                            const Pack<T> pyn = lds_pack(ynt + off, lane), psn = lds_pack(snt + off, lane);
+                            Pack<T> pyn = lds_pack(ynt + off, lane), psn = lds_pack(snt + off, lane);
+                            if (!full_tile)
+                            {
+                                mask_pack(pyn, len - off);
+                                mask_pack(psn, len - off);
+                            }
 #pragma unroll
                             for (int k = 0; k < 4; k++)
                             {
@@ -470,13 +506,12 @@ __device__ __forceinline__ void p_dots(const PDots<T>& a, int64_t t0, int64_t t1
         }
         if constexpr (FORM)
         {
-            const int64_t upcoming = tile + 1;
             const int nstage = (stage + 1 == kGramStages) ? 0 : stage + 1;
-            if (upcoming < t1) { wait_tile(upcoming, nstage); form_tile(upcoming, nstage); }
+            if (t + 1 < ntl) { wait_tile(nstage); form_tile(t + 1, nstage); }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads / form_tile writes of this stage before its re-arming bulk copy
         __syncthreads();
-        if (next_tile < t1) stage_tile(next_tile, stage);
+        if (next_tile < ntl) stage_tile(next_tile, stage);
         next_tile++;
         stage = (stage + 1 == kGramStages) ? 0 : stage + 1;
     }
@@ -502,70 +537,132 @@ __device__ __forceinline__ void p_dots(const PDots<T>& a, int64_t t0, int64_t t1
     }
 }
 
+// 16-byte units (2 doubles / 4 floats): the granularity of the combination pass
+template <class T> struct alignas(16) Unit { T v[16 / sizeof(T)]; };
+template <class T> __device__ __forceinline__ Unit<T> lds_unit(const T* p)
+{
+    Unit<T> u;
+    *reinterpret_cast<float4*>(u.v) = *reinterpret_cast<const float4*>(p);
+    return u;
+}
+template <class T> __device__ __forceinline__ void st_unit(T* base, int64_t i0, int cnt, const Unit<T>& u)
+{
+    constexpr int EPT = 16 / (int)sizeof(T);
+    if (cnt == EPT) { *reinterpret_cast<float4*>(base + i0) = *reinterpret_cast<const float4*>(u.v); return; }
+#pragma unroll
+    for (int k = 0; k < EPT; k++)
+        if (k < cnt) base[i0 + k] = u.v[k];
+}
+
 // ---- COMBINE (+ first trial) ---------------------------------------------------------------------------------------------------
 // d = cv*v + sum_j cy_j*y_j + cs_j*s_j ; FUSE: x1 = xc + d, g1 = grad f(x1) written to (x1_out, g1_out) and the four trial sums.
+// ALL operands are staged tile by tile through shared memory by bulk copies: NV = 2c + 1 (+1 with FUSE) vectors per tile listed in
+// sh.vecs in coefficient order {v, y_0 .. y_{c-1}, s_0 .. s_{c-1}, (xc)}; the tile length is the largest power of two for which
+// two stages fit the kernel's shared memory (c = 10, fp64: 512 elements = 88 KB per stage).  A thread owns one 4-element pack of
+// the tile and adds the terms in the order the recursion would (y newest -> oldest, then s oldest -> newest).
 template <class T, class OBJ, bool FUSE>
-__device__ __forceinline__ void p_combine(const OBJ& obj, int64_t n, int64_t e0, int64_t e1, int c, const T* s_coef, const T* __restrict__ v,
-                                          const T* __restrict__ xc, T* __restrict__ res, T* __restrict__ x1_out, T* __restrict__ g1_out,
-                                          PShared& sh, double* dst, int G)
+__device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, int c, T* tiles, T* __restrict__ res,
+                                          T* __restrict__ x1_out, T* __restrict__ g1_out, PShared& sh, unsigned& phase_bits, double* dst, int G)
 {
-    const T cv = s_coef[0];
+    constexpr int EPT = 16 / (int)sizeof(T);       // elements per 16-byte unit: 2 doubles / 4 floats
+    const int tid = threadIdx.x;
+    const int NV = 2 * c + 1 + (FUSE ? 1 : 0);
+    int TE = kGramTE;
+    while (TE > 32 && (TE > own.BS || (size_t)2 * NV * TE * sizeof(T) > (size_t)kPStageBytes)) TE >>= 1;
+    int stages = (int)((size_t)kPStageBytes / ((size_t)NV * TE * sizeof(T)));
+    stages = stages > kPMaxStages ? kPMaxStages : stages;
+    int64_t ntl = own.ntiles(TE);
+    while (ntl > 0 && own.len(ntl - 1, TE) == 0) ntl--;
+    const T* s_coef = reinterpret_cast<const T*>(sh.coef);
+    uint64_t* full_bar = sh.full_bar;
+
+    auto tile_len = [&](int64_t t) { return own.len(t, TE); };
+    auto stage_tile = [&](int64_t t, int stage) {
+        if (tid != 0) return;
+        T* dstt = tiles + (size_t)stage * NV * TE;
+        const int64_t e0 = own.start(t, TE);
+        const unsigned bytes = (unsigned)((tile_len(t) + 31) & ~31) * (unsigned)sizeof(T);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&full_bar[stage], bytes * (unsigned)NV);
+        for (int q = 0; q < NV; q++) tma_load_1d(dstt + (size_t)q * TE, static_cast<const T*>(sh.vecs[q]) + e0, bytes, &full_bar[stage]);
+    };
+
     T acc[5] = {T(0), T(0), T(0), T(0), T(0)};
-    const int64_t p1 = (e1 + 3) >> 2;
-    for (int64_t p = (e0 >> 2) + threadIdx.x; p < p1; p += kPThreads)
+    __syncthreads();   // sh.vecs / sh.coef are in place and the tile area is free
+    int64_t next_tile = 0;
+    for (int s = 0; s < stages; s++, next_tile++)
+        if (next_tile < ntl) stage_tile(next_tile, s);
+    const T cv = s_coef[0];
+    int stage = 0;
+    for (int64_t t = 0; t < ntl; t++)
     {
-        const int64_t i0 = p << 2;
-        const int cnt = (n - i0 >= 4) ? 4 : int(n - i0);
-        const Pack<T> pv = load4<T, Hint::Stream, true>(v, i0, cnt);
-        Pack<T> px;
-        if (FUSE) px = load4<T, Hint::Stream, true>(xc, i0, cnt);
-        T r[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) r[k] = cv * pv.v[k];
-        // y terms newest -> oldest, then s terms oldest -> newest (the order the recursion would add them)
-#pragma unroll 4
-        for (int j = 0; j < c; j++)
+        mbar_wait(&full_bar[stage], (phase_bits >> stage) & 1u);
+        phase_bits ^= (1u << stage);
+        const T* base = tiles + (size_t)stage * NV * TE;
+        const int len = tile_len(t);
+        const int64_t e0 = own.start(t, TE);
+        // one 16-byte unit (EPT elements) per thread: up to TE / EPT threads work on a tile, and the operand loads of 8 history
+        // columns are in flight per thread before their multiply-adds retire (the pass is bound by shared-memory latency otherwise)
+        for (int off = tid * EPT; off < len; off += kPThreads * EPT)
         {
-            const Pack<T> py = load4<T, Hint::Stream, true>(static_cast<const T*>(sh.ycol[j]), i0, cnt);
-            const T cy = s_coef[1 + j];
+            const int cnt = (len - off >= EPT) ? EPT : (len - off);
+            const Unit<T> uv = lds_unit<T>(base + off);
+            T r[EPT];
 #pragma unroll
-            for (int k = 0; k < 4; k++) r[k] += cy * py.v[k];
-        }
-#pragma unroll 4
-        for (int j = c - 1; j >= 0; j--)
-        {
-            const Pack<T> ps = load4<T, Hint::Stream, true>(static_cast<const T*>(sh.scol[j]), i0, cnt);
-            const T cs = s_coef[1 + c + j];
-#pragma unroll
-            for (int k = 0; k < 4; k++) r[k] += cs * ps.v[k];
-        }
-        Pack<T> out;
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-        {
-            out.v[k] = r[k];
-            acc[0] += (k < cnt) ? pv.v[k] * r[k] : T(0);
-        }
-        store4<T, Hint::Plain, true>(res, i0, cnt, out);
-        if (FUSE)
-        {
-            T xv[4], gv[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) xv[k] = px.v[k] + T(1) * r[k];
-            acc[1] += obj.eval(i0, cnt, xv, T(0), T(0), gv);
-            Pack<T> pg, po;
-#pragma unroll
-            for (int k = 0; k < 4; k++)
+            for (int k = 0; k < EPT; k++) r[k] = cv * uv.v[k];
+            const T* col = base + TE + off;
+#pragma unroll 8
+            for (int j = 0; j < c; j++)                        // y terms newest -> oldest
             {
-                acc[2] += (k < cnt) ? gv[k] * r[k] : T(0);
-                acc[3] += gv[k] * gv[k];
-                acc[4] += (k < cnt) ? xv[k] * xv[k] : T(0);
-                pg.v[k] = gv[k];
-                po.v[k] = xv[k];
+                const Unit<T> uy = lds_unit<T>(col + (size_t)j * TE);
+                const T cy = s_coef[1 + j];
+#pragma unroll
+                for (int k = 0; k < EPT; k++) r[k] += cy * uy.v[k];
             }
-            store4<T, Hint::Plain, true>(x1_out, i0, cnt, po);
-            store4<T, Hint::Plain, true>(g1_out, i0, cnt, pg);
+            col = base + (size_t)(c + 1) * TE + off;
+#pragma unroll 8
+            for (int j = c - 1; j >= 0; j--)                   // s terms oldest -> newest
+            {
+                const Unit<T> us = lds_unit<T>(col + (size_t)j * TE);
+                const T cs = s_coef[1 + c + j];
+#pragma unroll
+                for (int k = 0; k < EPT; k++) r[k] += cs * us.v[k];
+            }
+            Unit<T> out;
+#pragma unroll
+            for (int k = 0; k < EPT; k++)
+            {
+                out.v[k] = r[k];
+                acc[0] += (k < cnt) ? uv.v[k] * r[k] : T(0);
+            }
+            const int64_t i0 = e0 + off;
+            st_unit<T>(res, i0, cnt, out);
+            if constexpr (FUSE)
+            {
+                const Unit<T> ux = lds_unit<T>(base + (size_t)(2 * c + 1) * TE + off);
+                T xv[4] = {T(0), T(0), T(0), T(0)}, gv[4];
+#pragma unroll
+                for (int k = 0; k < EPT; k++) xv[k] = (k < cnt) ? ux.v[k] + T(1) * r[k] : T(0);
+                acc[1] += obj.eval(i0, cnt, xv, T(0), T(0), gv);
+                Unit<T> ug, uo;
+#pragma unroll
+                for (int k = 0; k < EPT; k++)
+                {
+                    acc[2] += (k < cnt) ? gv[k] * r[k] : T(0);
+                    acc[3] += (k < cnt) ? gv[k] * gv[k] : T(0);
+                    acc[4] += (k < cnt) ? xv[k] * xv[k] : T(0);
+                    ug.v[k] = gv[k];
+                    uo.v[k] = xv[k];
+                }
+                st_unit<T>(x1_out, i0, cnt, uo);
+                st_unit<T>(g1_out, i0, cnt, ug);
+            }
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (next_tile < ntl) stage_tile(next_tile, stage);
+        next_tile++;
+        stage = (stage + 1 == stages) ? 0 : stage + 1;
     }
     if (FUSE)
     {
@@ -782,17 +879,20 @@ __device__ __forceinline__ int nvals_of(int op, int c_round)
     }
 }
 
-// Fixed-order sums of the CTAs' partials of every running problem into raw[], (optional) cross-rank exchange, scalar logic.
-// Called by all threads of CTA 0 once every CTA has arrived.
+// Fixed-order sums of the CTAs' partials of every running problem into raw[], (optional) cross-rank exchange, scalar logic,
+// publication of the next round's descriptors.  Called by all threads of CTA 0 once every CTA has arrived.  Returns (in every
+// thread) the number of problems still running.
 template <class T, bool HALO>
-__device__ void leader_round(const PArgs<T>& a, int G)
+__device__ int leader_round(const PArgs<T>& a, int G, PShared& sh, PState<T>* cache)
 {
     const int tid = threadIdx.x;
+    // the leader's working copies: the first kPCache problems live in shared memory for the duration of the kernel
+    auto state_of = [&](int b) -> PState<T>* { return b < kPCache ? cache + b : a.probs + b; };
     // 1. local sums: 16 threads per value (CTAs s, s+16, ... then a fixed shuffle tree), 48 values per sweep
     for (int b = 0; b < a.B; b++)
     {
-        PState<T>* st = a.probs + b;
-        const int op = st->op;
+        PState<T>* st = state_of(b);
+        const int op = st->op;           // the pass this problem just ran (advance_problem below moves it on)
         if (op == POP_IDLE) continue;
         const int nv = nvals_of(op, st->c_round);
         const double* part = a.partials + (size_t)b * a.pstride * G;
@@ -809,7 +909,6 @@ __device__ void leader_round(const PArgs<T>& a, int G)
             if (v < nv && sub == 0) st->raw[v] = t;
         }
     }
-    __threadfence();
     __syncthreads();
     // 2. n sharded over ranks: ONE exchange for all running problems (sums in rank order: identical bits on every rank)
     if (a.xc != nullptr)
@@ -822,7 +921,7 @@ __device__ void leader_round(const PArgs<T>& a, int G)
         int ofs = 0;
         for (int b = 0; b < a.B; b++)
         {
-            PState<T>* st = a.probs + b;
+            PState<T>* st = state_of(b);
             const int op = st->op;
             if (op == POP_IDLE) continue;
             const int nv = nvals_of(op, st->c_round);
@@ -856,7 +955,7 @@ __device__ void leader_round(const PArgs<T>& a, int G)
         ofs = 0;
         for (int b = 0; b < a.B; b++)
         {
-            PState<T>* st = a.probs + b;
+            PState<T>* st = state_of(b);
             const int op = st->op;
             if (op == POP_IDLE) continue;
             const int nv = nvals_of(op, st->c_round);
@@ -878,27 +977,30 @@ __device__ void leader_round(const PArgs<T>& a, int G)
                 ofs += 4;
             }
         }
-        __threadfence();
         __syncthreads();
         if (tid == 0) a.ctl->epoch = epoch;
     }
-    // 3. scalar logic, one thread per problem
+    // 3. scalar logic, one thread per problem; the outcome goes into the problem's round descriptor
     int still = 0;
     for (int b0 = 0; b0 < a.B; b0 += kPThreads)
     {
         const int b = b0 + tid;
         int running = 0;
-        if (b < a.B)
+        if (b < a.B && state_of(b)->op != POP_IDLE)
         {
-            PState<T>* st = a.probs + b;
-            if (st->op != POP_IDLE) advance_problem(st, st->raw);
+            PState<T>* st = state_of(b);
+            advance_problem(st, st->raw);
+            PRound<T>* rd = a.rounds + b;
+            rd->x = st->x; rd->xp = st->xp; rd->g = st->g; rd->gp = st->gp; rd->drt = st->drt;
+            rd->step = st->step;
+            rd->c_round = st->c_round; rd->head = st->head; rd->pending = st->pending; rd->gram_cur = st->gram_cur;
+            rd->op = st->op;
             running = st->op != POP_IDLE;
         }
         still += __syncthreads_count(running);
     }
     if (tid == 0) { a.ctl->nactive = still; a.ctl->rounds++; }
-    __threadfence();
-    __syncthreads();
+    return still;
 }
 
 // exchange-only prelude for neighbour-coupled objectives under n-sharding: the first evaluation needs the neighbours' boundary
@@ -951,16 +1053,13 @@ template <class T, class OBJ, int ROUNDS>
 __global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
 {
     extern __shared__ __align__(128) unsigned char p_smem[];
-    T* tiles = reinterpret_cast<T*>(p_smem);      // [stage][4][TE] for the dots; the combine passes keep their coefficients here
+    T* tiles = reinterpret_cast<T*>(p_smem);      // the staging ring of the dots / combination passes
     __shared__ PShared sh;
     const int tid = threadIdx.x, G = gridDim.x, cta = blockIdx.x;
-    const int64_t ntiles = (a.n + kGramTE - 1) / kGramTE;
-    int64_t t0, t1;
-    chunk_of(ntiles, cta, G, t0, t1);
-    const int64_t e0 = t0 * kGramTE, e1 = (t1 * kGramTE < a.n) ? t1 * kGramTE : a.n;
+    const Own own(a.n, G, cta);
     if (tid == 0)
     {
-        for (int s = 0; s < kGramStages; s++) mbar_init(&sh.full_bar[s], 1);
+        for (int s = 0; s < kPMaxStages; s++) mbar_init(&sh.full_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -971,14 +1070,26 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
     long long t_last = clock64(), t_arrive = 0;   // CTA 0, thread 0: accounting (PCtl::cyc_*)
     int acct_bucket = 0;
     double acct_words = 0.0;
+    __shared__ unsigned s_release;
+    __shared__ PState<T> s_state[kPCache];     // CTA 0: working copies of the first problems' states (scalar logic at shared-memory latency)
+    const int ncache = a.B < kPCache ? a.B : kPCache;
+    if (cta == 0)
+    {
+        const unsigned* src = reinterpret_cast<const unsigned*>(a.probs);
+        unsigned* dstw = reinterpret_cast<unsigned*>(s_state);
+        for (int w = tid; w < (int)(sizeof(PState<T>) / 4) * ncache; w += kPThreads) dstw[w] = src[w];
+        __syncthreads();
+    }
 
-    // grid-wide barrier; between arrival of the last CTA and the release, CTA 0 runs `leader_work` (all its threads)
-    auto grid_barrier = [&](auto leader_work) {
+    // Grid-wide barrier.  Arrival: the CTA's partial sums are written, bar.sync, thread 0 fences and counts in.  Between the last
+    // arrival and the release CTA 0 runs `leader_work` (all its threads; returns true when nothing is left to do).  Returns that
+    // verdict in every thread of every CTA (it travels in bit 31 of the release word).
+    auto grid_barrier = [&](auto leader_work) -> bool {
         episode++;
         asm volatile("fence.proxy.async;" ::: "memory");   // this round's generic-proxy stores before later bulk (async-proxy) reads
-        __threadfence();
+        if (HALO) __threadfence();                           // boundary coordinates are read by the neighbouring CTA next round
         __syncthreads();
-        if (tid == 0) atomicAdd(&a.ctl->arrive, 1u);
+        if (tid == 0) { __threadfence(); atomicAdd(&a.ctl->arrive, 1u); }
         if (cta == 0)
         {
             if (tid == 0)
@@ -987,11 +1098,10 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
                 t_arrive = t_start;
                 while (ld_acquire_gpu_u32(&a.ctl->arrive) != episode * (unsigned)G)
                     if (clock64() - t_start > kPWaitCycles || ldv(&a.ctl->abort)) { a.ctl->abort = 1; break; }
+                a.ctl->cyc_wait_all += clock64() - t_start;
             }
             __syncthreads();
-            __threadfence();
-            leader_work();
-            __threadfence();
+            const bool stop = leader_work();
             __syncthreads();
             if (tid == 0)
             {
@@ -1001,108 +1111,133 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
                 a.ctl->n_op[acct_bucket] += 1ull;
                 a.ctl->words_op[acct_bucket] += acct_words;
                 t_last = now;
-                st_release_gpu_u32(&a.ctl->release, episode);
+                st_release_gpu_u32(&a.ctl->release, episode | (stop ? kPStopBit : 0u));
             }
         }
         if (tid == 0)
         {
             const long long t_start = clock64();
-            while (ld_acquire_gpu_u32(&a.ctl->release) < episode)
-                if (clock64() - t_start > 6 * kPWaitCycles || ldv(&a.ctl->abort)) { a.ctl->abort = 1; break; }
+            unsigned v;
+            while (((v = ld_acquire_gpu_u32(&a.ctl->release)) & ~kPStopBit) < episode)
+                if (clock64() - t_start > 6 * kPWaitCycles || ldv(&a.ctl->abort)) { a.ctl->abort = 1; v = kPStopBit; break; }
+            s_release = v;
         }
         __syncthreads();
+        return (s_release & kPStopBit) != 0u;
     };
 
-    if (HALO && a.xc != nullptr) grid_barrier([&]() { leader_halo_prelude<T>(a); });
+    if (HALO && a.xc != nullptr)
+        if (grid_barrier([&]() { leader_halo_prelude<T>(a); return ldv(&a.ctl->abort) != 0; })) return;
 
     for (;;)
     {
-        if (ldv(&a.ctl->nactive) == 0 || ldv(&a.ctl->abort)) break;
+        // this round's op of every problem (the descriptors were published before the release that let us through)
+        if (a.B > 1)
+        {
+            for (int b = tid; b < a.B; b += kPThreads) sh.ops[b] = (unsigned char)ldv(&a.rounds[b].op);
+            __syncthreads();
+        }
         acct_bucket = -1;
         acct_words = 0.0;
         for (int b = 0; b < a.B; b++)
         {
-            const PState<T>* st = a.probs + b;
-            const int op = ldv(&st->op);
+            const PRound<T>* rd = a.rounds + b;
+            const int op = (a.B > 1) ? (int)sh.ops[b] : ldv(&rd->op);   // a single problem: the op travels with the rest of the descriptor
             if (op == POP_IDLE) continue;
+            const PState<T>* st = a.probs + b;     // fields that are fixed for the duration of the kernel only
+            T* const vx = ldv(&rd->x); T* const vxp = ldv(&rd->xp); T* const vg = ldv(&rd->g); T* const vgp = ldv(&rd->gp); T* const vd = ldv(&rd->drt);
+            const T step = ldv(&rd->step);
+            const int c_round = ldv(&rd->c_round), head = ldv(&rd->head), pending = ldv(&rd->pending), gram_cur = ldv(&rd->gram_cur);
             acct_bucket = (acct_bucket == -1 || acct_bucket == op) ? op : 0;
-            acct_words += words_of(op, ldv(&st->c_round), kDataVectors);
+            acct_words += words_of(op, c_round, kDataVectors);
             double* dst = a.partials + (size_t)b * a.pstride * G + cta;
-            const OBJ obj = PObjMaker<T, OBJ>::make(a, ldv(&st->data0), ldv(&st->data1), (HALO && a.xc != nullptr) ? ldv(&st->halo) : nullptr);
+            const OBJ obj = PObjMaker<T, OBJ>::make(a, st->data0, st->data1, (HALO && a.xc != nullptr) ? st->halo : nullptr);
             switch (op)
             {
             case POP_FIRST:
-                p_trial<T, OBJ, 0>(obj, a.n, e0, e1, nullptr, nullptr, T(0), ldv(&st->x), ldv(&st->g), ldv(&st->drt), sh, dst, G);
+                p_trial<T, OBJ, 0>(obj, own, nullptr, nullptr, T(0), vx, vg, vd, sh, dst, G);
                 break;
             case POP_TRIAL:
-                p_trial<T, OBJ, 1>(obj, a.n, e0, e1, ldv(&st->xp), ldv(&st->drt), ldv(&st->step), ldv(&st->x), ldv(&st->g), nullptr, sh, dst, G);
+                p_trial<T, OBJ, 1>(obj, own, vxp, vd, step, vx, vg, nullptr, sh, dst, G);
                 break;
             case POP_RESTORE:
-                p_restore<T>(a.n, e0, e1, ldv(&st->xp), ldv(&st->gp), ldv(&st->x), ldv(&st->g));
+                p_restore<T>(own, vxp, vgp, vx, vg);
                 break;
             case POP_DOTS_FORM:
             case POP_DOTS_PLAIN:
             {
                 const bool form = op == POP_DOTS_FORM;
                 PDots<T> d;
-                d.n = a.n; d.ld = a.ld; d.v = ldv(&st->g); d.S = ldv(&st->S); d.Y = ldv(&st->Y);
-                d.c = ldv(&st->c_round);
-                const int head = ldv(&st->head), M = ldv(&st->M);
+                d.n = a.n; d.ld = a.ld; d.v = vg; d.S = st->S; d.Y = st->Y;
+                d.c = c_round;
+                const int M = st->M;
                 d.new_slot = form ? head : -1;
                 int split = 8;
-                while (split > 1 && d.c * split > kGramMaxWarps) split >>= 1;
+                const int dte = own.BS < kGramTE ? own.BS : kGramTE;
+                while (split > 1 && (d.c * split > kGramMaxWarps || dte / split < 256)) split >>= 1;
                 d.split = split;
                 d.cols_per_round = d.c < kGramMaxWarps / split ? d.c : kGramMaxWarps / split;
-                d.fx = ldv(&st->x); d.fxp = ldv(&st->xp); d.fgp = ldv(&st->gp);
-                d.s_out = const_cast<T*>(d.S) + (int64_t)head * a.ld;
-                d.y_out = const_cast<T*>(d.Y) + (int64_t)head * a.ld;
+                d.fx = vx; d.fxp = vxp; d.fgp = vgp;
+                d.s_out = st->S + (int64_t)head * a.ld;
+                d.y_out = st->Y + (int64_t)head * a.ld;
                 __syncthreads();   // sh.slots may still be read by the previous problem's pass
                 if (tid < d.c) sh.slots[tid] = (unsigned char)(form ? (tid == 0 ? head : slot_by_age(head, M, tid - 1)) : slot_by_age(head, M, tid));
-                if (form) p_dots<T, ROUNDS, true>(d, t0, t1, tiles, sh, phase_bits, dst, G);
-                else p_dots<T, ROUNDS, false>(d, t0, t1, tiles, sh, phase_bits, dst, G);
+                if (form) p_dots<T, ROUNDS, true>(d, own, tiles, sh, phase_bits, dst, G);
+                else p_dots<T, ROUNDS, false>(d, own, tiles, sh, phase_bits, dst, G);
                 break;
             }
             case POP_COMBINE:
             case POP_COMBINE_TRIAL:
             {
                 GramSolveArgs<T> g;
-                g.c = ldv(&st->c_round);
-                g.M = ldv(&st->M); g.new_slot = ldv(&st->pending); g.with_v = 1; g.a = T(-1);
-                g.raw = ldv(&st->raw);
-                const int in = ldv(&st->gram_cur), out = (g.new_slot >= 0) ? 1 - in : in;
-                g.SY_in = ldv(&st->SY[in]); g.YY_in = ldv(&st->YY[in]); g.SS_in = ldv(&st->SS[in]);
-                g.SY_out = ldv(&st->SY[out]); g.YY_out = ldv(&st->YY[out]); g.SS_out = ldv(&st->SS[out]);
-                g.ys = ldv(&st->ys); g.alpha = ldv(&st->alpha); g.theta = ldv(&st->theta);
+                g.c = c_round;
+                g.M = st->M; g.new_slot = pending; g.with_v = 1; g.a = T(-1);
+                g.raw = st->raw;
+                const int in = gram_cur, out = (g.new_slot >= 0) ? 1 - in : in;
+                g.SY_in = st->SY[in]; g.YY_in = st->YY[in]; g.SS_in = st->SS[in];
+                g.SY_out = st->SY[out]; g.YY_out = st->YY[out]; g.SS_out = st->SS[out];
+                g.ys = st->ys; g.alpha = st->alpha; g.theta = st->theta;
                 g.ov_slot = -1; g.ov_theta_on = 0;
-                const int head = ldv(&st->head);
                 for (int age = 0; age < g.c; age++) g.slots[age] = (unsigned char)slot_by_age(head, g.M, age);
-                __syncthreads();   // the tile area / pointer tables may still be in use by the previous problem's pass
+                __syncthreads();   // the tile area / tables may still be in use by the previous problem's pass
                 gram_solve_in_smem<T>(g, tiles, cta == 0);
-                const T* S = ldv(&st->S); const T* Y = ldv(&st->Y);
-                for (int j = tid; j < g.c; j += kPThreads)
+                // coefficients out of the tile area (the staging ring is about to overwrite it), operand table in coefficient order
+                const bool fuse = !OBJ::kHalo && op == POP_COMBINE_TRIAL;
                 {
-                    sh.ycol[j] = Y + (int64_t)g.slots[j] * a.ld;
-                    sh.scol[j] = S + (int64_t)g.slots[j] * a.ld;
+                    const T* s_coef = tiles + 2 * g.c * g.c;
+                    T* keep = reinterpret_cast<T*>(sh.coef);
+                    for (int q = tid; q < 2 * g.c + 1; q += kPThreads) keep[q] = s_coef[q];
+                    for (int j = tid; j < g.c; j += kPThreads)
+                    {
+                        sh.vecs[1 + j] = st->Y + (int64_t)g.slots[j] * a.ld;
+                        sh.vecs[1 + g.c + j] = st->S + (int64_t)g.slots[j] * a.ld;
+                    }
+                    if (tid == 0) { sh.vecs[0] = vg; sh.vecs[2 * g.c + 1] = vx; }
                 }
-                __syncthreads();
-                const T* s_coef = tiles + 2 * g.c * g.c;
                 bool done = false;
                 if constexpr (!OBJ::kHalo)
                 {
-                    if (op == POP_COMBINE_TRIAL)
+                    if (fuse)
                     {
-                        p_combine<T, OBJ, true>(obj, a.n, e0, e1, g.c, s_coef, ldv(&st->g), ldv(&st->x), ldv(&st->drt), ldv(&st->xp), ldv(&st->gp), sh, dst, G);
+                        p_combine<T, OBJ, true>(obj, own, g.c, tiles, vd, vxp, vgp, sh, phase_bits, dst, G);
                         done = true;
                     }
                 }
-                if (!done) p_combine<T, OBJ, false>(obj, a.n, e0, e1, g.c, s_coef, ldv(&st->g), nullptr, ldv(&st->drt), nullptr, nullptr, sh, dst, G);
+                if (!done) p_combine<T, OBJ, false>(obj, own, g.c, tiles, vd, nullptr, nullptr, sh, phase_bits, dst, G);
                 break;
             }
             default: break;
             }
         }
         if (acct_bucket < 0) acct_bucket = 0;
-        grid_barrier([&]() { leader_round<T, HALO>(a, G); });
+        if (grid_barrier([&]() { return leader_round<T, HALO>(a, G, sh, s_state) == 0 || ldv(&a.ctl->abort) != 0; })) break;
+    }
+    if (cta == 0)
+    {
+        __syncthreads();
+        const unsigned* src = reinterpret_cast<const unsigned*>(s_state);
+        unsigned* dstw = reinterpret_cast<unsigned*>(a.probs);
+        for (int w = tid; w < (int)(sizeof(PState<T>) / 4) * ncache; w += kPThreads) dstw[w] = src[w];
     }
 }
 

@@ -11,6 +11,7 @@ struct lbfgs_b200_solver
     void* vec_slab = nullptr;             // [B][7][vec_elems] : x, xp, g, gp, drt, x_lo, g_lo
     size_t vec_elems = 0;                 // n rounded up to a whole number of 256-byte lines
     void* d_state = nullptr;              // PState<T>[B]
+    void* d_rounds = nullptr;             // PRound<T>[B]
     lb::PCtl* d_ctl = nullptr;
     double* d_partials = nullptr;         // [B][pstride][sm_count]
     double* d_raw = nullptr;              // [B][pstride]
@@ -20,6 +21,7 @@ struct lbfgs_b200_solver
     long long trace_cap = 0;
     std::vector<void*> final_g, final_x;  // device pointers of each problem's final gradient / point (inside vec_slab)
     std::vector<unsigned char> h_state;   // host copy of the states
+    std::vector<unsigned char> h_rounds;  // host image of the initial round descriptors
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_kernel_ms = 0.f;           // device time of the last solve's kernel (CUDA events around the launch)
     lb::PCtl last_ctl{};                  // its accounting
@@ -116,7 +118,16 @@ static lbfgs_b200_status solver_minimize(lbfgs_b200_solver* s, int objective, co
         p.trace_cap = trace_host ? trace_cap : 0;
         CU(ctx, cudaMemcpyAsync(p.x, x_inout + (size_t)b * ldx, vb, cudaMemcpyDeviceToDevice, ctx->stream));
     }
+    s->h_rounds.assign(sizeof(PRound<T>) * (size_t)B, 0);
+    PRound<T>* hr = reinterpret_cast<PRound<T>*>(s->h_rounds.data());
+    for (int b = 0; b < B; b++)
+    {
+        const PState<T>& p = hs[b];
+        hr[b].x = p.x; hr[b].xp = p.xp; hr[b].g = p.g; hr[b].gp = p.gp; hr[b].drt = p.drt;
+        hr[b].step = T(0); hr[b].op = p.op; hr[b].c_round = 0; hr[b].head = 0; hr[b].pending = -1; hr[b].gram_cur = p.gram_cur;
+    }
     CU(ctx, cudaMemcpyAsync(s->d_state, hs, sizeof(PState<T>) * (size_t)B, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(s->d_rounds, hr, sizeof(PRound<T>) * (size_t)B, cudaMemcpyHostToDevice, ctx->stream));
     PCtl hc{};
     hc.nactive = B;
     hc.epoch = ctx->x_epoch;
@@ -124,15 +135,15 @@ static lbfgs_b200_status solver_minimize(lbfgs_b200_solver* s, int objective, co
     CU(ctx, cudaMemsetAsync(s->d_halo, 0, sizeof(double) * kHaloDoubles * (size_t)B, ctx->stream));
 
     // ---- one cooperative launch: one CTA per SM (fewer when the vector has fewer tiles than SMs) ----
-    const int64_t ntiles = (s->n + kGramTE - 1) / kGramTE;
-    const int grid = (int)(ntiles < ctx->sm_count ? (ntiles < 1 ? 1 : ntiles) : ctx->sm_count);
-    const size_t smem = (size_t)kGramStages * 4 * kGramTE * sizeof(T);
+    const int64_t units = (s->n + kPGrain - 1) / kPGrain;
+    const int grid = (int)(units < ctx->sm_count ? (units < 1 ? 1 : units) : ctx->sm_count);
+    const size_t smem = (size_t)kPStageBytes;
     CU(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPThreads, smem));
     REQUIRE(ctx, per_sm >= 1, "the persistent solve kernel does not fit on an SM of this device");
     PArgs<T> a{};
-    a.probs = static_cast<PState<T>*>(s->d_state); a.B = B; a.ctl = s->d_ctl; a.partials = s->d_partials; a.pstride = s->pstride;
+    a.probs = static_cast<PState<T>*>(s->d_state); a.rounds = static_cast<PRound<T>*>(s->d_rounds); a.B = B; a.ctl = s->d_ctl; a.partials = s->d_partials; a.pstride = s->pstride;
     a.n = s->n; a.ld = s->hist[0]->ld; a.xc = ctx->x_active ? ctx->x_comm : nullptr;
     a.index_offset = index_offset; a.n_global = n_global;
     void* kargs[] = {&a};
@@ -202,6 +213,7 @@ lbfgs_b200_status lbfgs_b200_solver_create_batch(lbfgs_b200_ctx* ctx, int64_t n,
     const size_t state_bytes = (elem_bytes == 8 ? sizeof(lb::PState<double>) : sizeof(lb::PState<float>)) * (size_t)batch;
     if (e == cudaSuccess) e = cudaMalloc(&s->vec_slab, (size_t)batch * 7 * s->vec_elems * elem_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_state, state_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_rounds, (elem_bytes == 8 ? sizeof(lb::PRound<double>) : sizeof(lb::PRound<float>)) * (size_t)batch);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_ctl, sizeof(lb::PCtl));
     if (e == cudaSuccess) e = cudaMalloc(&s->d_partials, sizeof(double) * (size_t)batch * s->pstride * ctx->sm_count);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_raw, sizeof(double) * (size_t)batch * s->pstride);
@@ -228,6 +240,7 @@ void lbfgs_b200_solver_destroy(lbfgs_b200_solver* s)
     if (s->ctx && s->ctx->stream) cudaStreamSynchronize(s->ctx->stream);
     cudaFree(s->vec_slab);
     cudaFree(s->d_state);
+    cudaFree(s->d_rounds);
     cudaFree(s->d_ctl);
     cudaFree(s->d_partials);
     cudaFree(s->d_raw);
@@ -255,7 +268,7 @@ lbfgs_b200_status lbfgs_b200_solver_profile(const lbfgs_b200_solver* s, double* 
         if (rounds_by_op8) rounds_by_op8[k] = c.n_op[k];
         if (alg_bytes_by_op8) alg_bytes_by_op8[k] = c.words_op[k] * (double)s->n * (double)s->elem;
     }
-    if (sync_ms) *sync_ms = scale * (double)c.cyc_sync;
+    if (sync_ms) { sync_ms[0] = scale * (double)c.cyc_sync; sync_ms[1] = scale * (double)c.cyc_wait_all; }
     return LBFGS_B200_OK;
 }
 const void* lbfgs_b200_solver_final_grad(const lbfgs_b200_solver* s) { return s ? s->final_g[0] : nullptr; }

@@ -25,6 +25,13 @@ def show(tag, g, c=None):
 
 
 PERF_ONLY = "--perf" in sys.argv
+if "--one" in sys.argv:   # under ncu: 3 warm solves + 1 at config 2's size, nothing else
+    sess = lb.Session(lb.OBJ_ROSENBROCK_PAIRED, np.zeros(10_000_000), lb.LBFGSParam(m=10), "MoreThuente", resident=True)
+    for _ in range(4):
+        r = sess.solve()
+    print(r, sess.profile())
+    sess.close()
+    sys.exit(0)
 for n in (() if PERF_ONLY else (10, 4098, 100000)):
     for ls in LSN:
         prm = lb.LBFGSParam(m=10 if n > 10 else 6)
@@ -65,7 +72,7 @@ for n in (1_000_000, 10_000_000):
             n, resident, r["niter"], r["nfev"], r["fx"], dt * 1e3, r["niter"] / dt, r["launches"]), flush=True)
         prof = sess.profile()
         if prof:
-            print('   kernel_ms=%.3f sync_ms=%.3f' % (prof['kernel_ms'], prof['sync_ms']))
+            print('   kernel_ms=%.3f sync_ms=%.3f (waiting for the last CTA %.3f)' % (prof['kernel_ms'], prof['sync_ms'], prof['wait_last_cta_ms']))
             for k, v in prof['ops'].items():
                 print('   %-14s rounds=%3d ms=%.3f  %.0f GB/s' % (k, v['rounds'], v['ms'], v['alg_bytes'] / max(v['ms'], 1e-9) / 1e6))
         sess.close()

@@ -7,7 +7,9 @@ Every rank owns a contiguous block of every vector (lbfgspp_b200.sharding.shard_
 run on the FULL vectors:
   1. the fused trial / objective kernels of the neighbour-coupled objectives (chained Rosenbrock, tridiagonal quadratic):
      the block of the gradient and the all-reduced {f, g.d, g.g, x.x} -- this is the halo exchange;
-  2. whole solves (paired Rosenbrock, chained Rosenbrock, tridiagonal quadratic): iterations, evaluations, fx, x block.
+  2. whole solves (paired Rosenbrock, chained Rosenbrock, tridiagonal quadratic), host-driven loop and (p2p) the device-resident
+     persistent kernel incl. its in-kernel halo exchange: iterations, evaluations, fx, x block;
+  3. (p2p) a batch of n-sharded problems in one persistent kernel launch.
 Prints one line 'MULTI_GPU_CHECK PASS ...' on rank 0 when every rank passed."""
 import os
 import sys
@@ -79,10 +81,10 @@ def main():
             expect(abs(f2 - f_ref) <= 1e-11 * max(1.0, abs(f_ref)), "objective f: " + tag)
 
     # ---- 2. solves -------------------------------------------------------------------------------------------------
-    def solve(kind, n, x0, prm, ls, d0=None, d1=None):
+    def solve(kind, n, x0, prm, ls, d0=None, d1=None, resident=False):
         lo, hi = shard_bounds(n, rank, world)
         lb.set_global_extent(local, lo, n)
-        sess = lb.Session(kind, x0[lo:hi], prm, ls, device=local, resident=False,
+        sess = lb.Session(kind, x0[lo:hi], prm, ls, device=local, resident=resident,
                           data0=None if d0 is None else d0[lo:hi], data1=None if d1 is None else d1[lo:hi])
         r = sess.solve(to_host=True)
         r["x"] = sess.result()
@@ -93,31 +95,50 @@ def main():
         p = orc.default_param(m=prm.m, max_iterations=prm.max_iterations)
         return orc.lbfgs(kind, x0, po.__dict__["LS_" + ls], p, data0=d0, data1=d1, sum_mode=po.SUM_LANES8)
 
-    n = 50000 * world
-    prm = lb.LBFGSParam(m=10)
-    g, lo, hi = solve(lb.OBJ_ROSENBROCK_PAIRED, n, np.zeros(n), prm, "MoreThuente")
-    c = cpu(po.OBJ_ROSENBROCK_PAIRED, np.zeros(n), prm, "MORE_THUENTE")
-    expect((g["niter"], g["nfev"]) == (c["niter"], c["nfev"]), "paired solve counts %r vs %r" % ((g["niter"], g["nfev"]), (c["niter"], c["nfev"])))
-    expect(abs(g["fx"] - c["fx"]) <= 1e-10 * max(1.0, abs(c["fx"])), "paired solve fx")
-    expect(np.max(np.abs(g["x"] - c["x"][lo:hi])) <= 1e-7, "paired solve x block")
+    for resident in ((False, True) if mode == "p2p" else (False,)):
+        tag = "[device-resident] " if resident else "[host-driven] "
+        n = 50000 * world
+        prm = lb.LBFGSParam(m=10)
+        g, lo, hi = solve(lb.OBJ_ROSENBROCK_PAIRED, n, np.zeros(n), prm, "MoreThuente", resident=resident)
+        c = cpu(po.OBJ_ROSENBROCK_PAIRED, np.zeros(n), prm, "MORE_THUENTE")
+        expect((g["niter"], g["nfev"]) == (c["niter"], c["nfev"]), tag + "paired solve counts %r vs %r" % ((g["niter"], g["nfev"]), (c["niter"], c["nfev"])))
+        expect(abs(g["fx"] - c["fx"]) <= 1e-10 * max(1.0, abs(c["fx"])), tag + "paired solve fx")
+        expect(np.max(np.abs(g["x"] - c["x"][lo:hi])) <= 1e-7, tag + "paired solve x block")
 
-    n = 10000 * world + 6
-    x0 = np.full(n, 3.0)
-    g, lo, hi = solve(lb.OBJ_ROSENBROCK_CHAINED, n, x0, prm, "MoreThuente")
-    c = cpu(po.OBJ_ROSENBROCK_CHAINED, x0, prm, "MORE_THUENTE")
-    expect((g["niter"], g["nfev"]) == (c["niter"], c["nfev"]), "chained solve counts %r vs %r" % ((g["niter"], g["nfev"]), (c["niter"], c["nfev"])))
-    expect(abs(g["fx"] - c["fx"]) <= 1e-10 * max(1.0, abs(c["fx"])), "chained solve fx %r %r" % (g["fx"], c["fx"]))
-    expect(np.max(np.abs(g["x"] - c["x"][lo:hi])) <= 1e-6, "chained solve x block")
+        n = 10000 * world + 6
+        x0 = np.full(n, 3.0)
+        g, lo, hi = solve(lb.OBJ_ROSENBROCK_CHAINED, n, x0, prm, "MoreThuente", resident=resident)
+        c = cpu(po.OBJ_ROSENBROCK_CHAINED, x0, prm, "MORE_THUENTE")
+        expect((g["niter"], g["nfev"]) == (c["niter"], c["nfev"]), tag + "chained solve counts %r vs %r" % ((g["niter"], g["nfev"]), (c["niter"], c["nfev"])))
+        expect(abs(g["fx"] - c["fx"]) <= 1e-10 * max(1.0, abs(c["fx"])), tag + "chained solve fx %r %r" % (g["fx"], c["fx"]))
+        expect(np.max(np.abs(g["x"] - c["x"][lo:hi])) <= 1e-6, tag + "chained solve x block")
 
-    n = 10000 * world
-    d0, d1, xs = po.quad_tridiag_data(n, kappa=1e3, seed=0)
-    prm20 = lb.LBFGSParam(m=20)
-    g, lo, hi = solve(lb.OBJ_QUAD_TRIDIAG, n, np.zeros(n), prm20, "Bracketing", d0, d1)
-    c = cpu(po.OBJ_QUAD_TRIDIAG, np.zeros(n), prm20, "BRACKETING", d0, d1)
-    expect(c["status"] == "ok", "cpu tridiag status " + c["status"])
-    expect(abs(g["fx"] - c["fx"]) <= 1e-9 * abs(c["fx"]), "tridiag solve fx %r %r" % (g["fx"], c["fx"]))
-    expect(abs(g["niter"] - c["niter"]) <= max(3, c["niter"] // 20), "tridiag solve iterations %d vs %d" % (g["niter"], c["niter"]))
-    expect(np.max(np.abs(g["x"] - xs[lo:hi])) <= 1e-3, "tridiag solve x block")
+        n = 10000 * world
+        d0, d1, xs = po.quad_tridiag_data(n, kappa=1e3, seed=0)
+        prm20 = lb.LBFGSParam(m=20)
+        g, lo, hi = solve(lb.OBJ_QUAD_TRIDIAG, n, np.zeros(n), prm20, "Bracketing", d0, d1, resident=resident)
+        c = cpu(po.OBJ_QUAD_TRIDIAG, np.zeros(n), prm20, "BRACKETING", d0, d1)
+        expect(c["status"] == "ok", tag + "cpu tridiag status " + c["status"])
+        expect(abs(g["fx"] - c["fx"]) <= 1e-9 * abs(c["fx"]), tag + "tridiag solve fx %r %r" % (g["fx"], c["fx"]))
+        expect(abs(g["niter"] - c["niter"]) <= max(3, c["niter"] // 20), tag + "tridiag solve iterations %d vs %d" % (g["niter"], c["niter"]))
+        expect(np.max(np.abs(g["x"] - xs[lo:hi])) <= 1e-3, tag + "tridiag solve x block")
+
+    # ---- 3. a batch of problems, every one n-sharded: ONE exchange per round carries all the running problems' sums ----------
+    if mode == "p2p":
+        n = 20000 * world
+        lo, hi = shard_bounds(n, rank, world)
+        lb.set_global_extent(local, lo, n)
+        starts = [np.zeros(n), np.full(n, 0.5), np.full(n, -0.3), np.zeros(n)]
+        bs = lb.BatchSession(lb.OBJ_ROSENBROCK_PAIRED, np.stack([x[lo:hi] for x in starts]), prm, "MoreThuente", device=local)
+        res, X, _ = bs.solve()
+        bs.close()
+        for b, x0 in enumerate(starts):
+            c = cpu(po.OBJ_ROSENBROCK_PAIRED, x0, prm, "MORE_THUENTE")
+            expect(res[b]["status"] == "ok" and (res[b]["niter"], res[b]["nfev"]) == (c["niter"], c["nfev"]),
+                   "sharded batch problem %d counts %r vs %r" % (b, (res[b]["niter"], res[b]["nfev"]), (c["niter"], c["nfev"])))
+            expect(abs(res[b]["fx"] - c["fx"]) <= 1e-10 * max(1.0, abs(c["fx"])), "sharded batch problem %d fx" % b)
+            expect(np.max(np.abs(X[b] - c["x"][lo:hi])) <= 1e-7, "sharded batch problem %d x block" % b)
+        expect(res[0] == res[3] and np.array_equal(X[0], X[3]), "sharded batch: equal problems must give equal bits")
 
     bad = torch.tensor([len(failures)], dtype=torch.int64, device="cuda")
     dist.all_reduce(bad)

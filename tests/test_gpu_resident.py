@@ -30,8 +30,8 @@ def test_resident_matches_cpu_checker(orc, ls, n):
 
 
 def test_resident_other_objectives(orc):
-    n = 5000
-    d, b, xs = po.quad_tridiag_data(n, seed=1)
+    n = 20000
+    d, b, xs = po.quad_tridiag_data(n, kappa=1e3, seed=0)   # config 3's shape at a size where the reference's run ends normally
     prm = lb.LBFGSParam(m=20)
     g = resident(prm, "Bracketing").minimize(lb.OBJ_QUAD_TRIDIAG, np.zeros(n), data0=d, data1=b)
     c = orc.lbfgs(po.OBJ_QUAD_TRIDIAG, np.zeros(n), LS["Bracketing"], cpu_param(orc, prm), data0=d, data1=b)
