@@ -24,6 +24,7 @@
 #include "LBFGSpp/LineSearchDriver.h"
 #include "LBFGSpp/LineSearchMoreThuente.h"
 #include "LBFGSpp/Param.h"
+#include "LBFGSpp/PhaseClock.h"
 #include "LBFGSpp/SubspaceMin.h"
 
 namespace LBFGSpp {
@@ -102,7 +103,10 @@ public:
             m_gradp.swap(m_grad);
 
             Scalar info[2];
-            dev.check(detail::BoxAbi<Scalar>::dir_info(dev.ctx(), n, m_xp.data(), m_drt.data(), m_gradp.data(), lb.data(), ub.data(), info));
+            {
+                PhaseClock::Scope ph(dev, "dir_info");
+                dev.check(detail::BoxAbi<Scalar>::dir_info(dev.ctx(), n, m_xp.data(), m_drt.data(), m_gradp.data(), lb.data(), ub.data(), info));
+            }
             Scalar dg = info[0], step_max = info[1];
             if (dg >= Scalar(0) || step_max <= m_param.min_step)                    // :188-197
             {
@@ -116,7 +120,10 @@ public:
             step_max = std::min(m_param.max_step, step_max);
             Scalar step = std::min(Scalar(1), step_max);
 
-            run_line_search<typename LineSearch<Scalar>::Machine>(f, m_param, m_xp, m_gradp, m_drt, step_max, step, fx, dg, x, m_grad, m_ws);
+            {
+                PhaseClock::Scope ph(dev, "line_search");
+                run_line_search<typename LineSearch<Scalar>::Machine>(f, m_param, m_xp, m_gradp, m_drt, step_max, step, fx, dg, x, m_grad, m_ws);
+            }
             m_nfev += m_ws.evaluations;
 
             m_projgnorm = proj_grad_norm(dev, x, m_grad, lb, ub);                   // :206
@@ -129,11 +136,17 @@ public:
             }
             if (m_param.max_iterations != 0 && k >= m_param.max_iterations) return k;
 
-            if (m_bfgs.update(x, m_xp, m_grad, m_gradp)) m_bfgs.refresh_middle();   // :235-238 (+ BFGSMat.h:99-146)
+            {
+                PhaseClock::Scope ph(dev, "update+middle_matrix");
+                if (m_bfgs.update(x, m_xp, m_grad, m_gradp)) m_bfgs.refresh_middle();   // :235-238 (+ BFGSMat.h:99-146)
+            }
 
             dev.check(detail::BoxAbi<Scalar>::clamp(dev.ctx(), n, x.data(), lb.data(), ub.data()));   // :240
             cp = Cauchy<Scalar>::get_cauchy_point(m_bfgs, x, m_grad, lb, ub);                          // :241
-            SubspaceMin<Scalar>::subspace_minimize(m_bfgs, x, m_grad, lb, ub, cp, m_param.max_submin, m_drt);   // :249-250
+            {
+                PhaseClock::Scope ph(dev, "subspace_min");
+                SubspaceMin<Scalar>::subspace_minimize(m_bfgs, x, m_grad, lb, ub, cp, m_param.max_submin, m_drt);   // :249-250
+            }
             k++;
         }
         return k;

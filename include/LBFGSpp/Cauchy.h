@@ -17,6 +17,8 @@
 
 #include "BFGSMat.h"
 
+#include "PhaseClock.h"
+
 namespace LBFGSpp {
 
 template <typename Scalar>
@@ -46,7 +48,11 @@ public:
         out.vecc.assign(size_t(2 * c), Scalar(0));
 
         Scalar info[5];
+        PhaseClock::Scope ph_all(dev, "cauchy.total");
+        {
+        PhaseClock::Scope ph(dev, "cauchy.breakpoints");
         dev.check(detail::BoxAbi<Scalar>::cauchy_breaks(box, x0.data(), g.data(), lb.data(), ub.data(), info));
+        }
         const long nfree_inf = long(info[1]), nord = long(info[2]);
         const Scalar dd = info[3], tmin = info[4];
         Scalar counts[2] = {0, 0};
@@ -84,6 +90,7 @@ public:
         else
         {
             std::vector<Scalar> res(size_t(5 + 2 * c));
+            PhaseClock::Scope ph(dev, "cauchy.sort+sweep");
             dev.check(detail::BoxAbi<Scalar>::cauchy_sweep(box, g.data(), c > 0 ? bfgs.Mmat().data() : nullptr, c > 0 ? p0.data() : nullptr,
                                                            theta, dd, nord, nfree_inf, res.data()));
             t_cross = res[0];

@@ -605,6 +605,18 @@ class BatchSession:
             self.h = None
 
 
+def phase_clock(on=True):
+    """Enable / disable (and clear) the wall-clock accounting of the host-driven L-BFGS-B loop's phases (LBFGSpp/PhaseClock.h)."""
+    driver().lbfgsb200_drv_phase_enable(int(on))
+
+
+def phase_report():
+    import json
+    buf = C.create_string_buffer(8192)
+    driver().lbfgsb200_drv_phase_report(buf, 8192)
+    return json.loads(buf.value.decode() or "{}")
+
+
 def driver_ctx(device=0):
     """The lbfgs_b200_ctx* the driver uses for `device` (so that the raw ABI / profiling can address it)."""
     return C.c_void_p(driver().lbfgsb200_drv_ctx(device))

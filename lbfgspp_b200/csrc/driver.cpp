@@ -5,6 +5,7 @@
 // have the same layout as the CPU checker's (oracle/oracle_api.h) so that a parity test calls both sides with the
 // very same objects -- but nothing here includes or links anything from oracle/.
 #include <chrono>
+#include <cstdio>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -776,6 +777,29 @@ extern "C" int lbfgsb200_drv_batch_session_solve(void* handle, drv_batch_item* i
         if (err && errlen > 0) { std::strncpy(err, e.what(), size_t(errlen) - 1); err[errlen - 1] = 0; }
         return -1;
     }
+}
+
+// PhaseClock (include/LBFGSpp/PhaseClock.h): wall-clock accounting of the host-driven L-BFGS-B loop's phases for bench.py / profiles
+extern "C" void lbfgsb200_drv_phase_enable(int on)
+{
+    PhaseClock::get().enabled = on != 0;
+    PhaseClock::get().reset();
+}
+// JSON object {"phase": {"seconds": s, "calls": k}, ...} of everything recorded on this thread since the last enable; returns its length
+extern "C" int lbfgsb200_drv_phase_report(char* buf, int len)
+{
+    std::string out = "{";
+    bool first = true;
+    for (const auto& kv : PhaseClock::get().acc)
+    {
+        char item[256];
+        std::snprintf(item, sizeof(item), "%s\"%s\": {\"seconds\": %.9g, \"calls\": %ld}", first ? "" : ", ", kv.first.c_str(), kv.second.seconds, kv.second.calls);
+        out += item;
+        first = false;
+    }
+    out += "}";
+    if (buf && len > 0) { std::strncpy(buf, out.c_str(), size_t(len) - 1); buf[len - 1] = 0; }
+    return int(out.size());
 }
 
 // dense B or H of an explicit history (test hook for final_approx_hessian / final_approx_inverse_hessian)

@@ -16,6 +16,9 @@ struct lbfgs_b200_box
     unsigned char* cls = nullptr;
     unsigned long long* keys = nullptr;
     unsigned* ord = nullptr;
+    unsigned long long* keys2 = nullptr;   // radix sort: the other side of the ping-pong
+    unsigned* ord2 = nullptr;
+    unsigned* radix_hist = nullptr;        // [256][npad / kSortTile]
     void* block_sums = nullptr;   // [(npad/kScanBlock)][4m+1]
     long long* best = nullptr;
     void* small = nullptr;        // device scratch for small host-supplied arrays: Mmat [2m*2m] | p0 [2m] | coef [2m] | out [5+2m]
@@ -138,7 +141,7 @@ static void box_free(lbfgs_b200_box* b)
 {
     if (!b) return;
     for (void* p : {b->brk, b->dvec, b->xcp, b->vecc, b->vecy, b->lambda, b->mu, b->tmp, b->tmp2, b->yfb, (void*)b->cls,
-                    (void*)b->keys, (void*)b->ord, b->block_sums, (void*)b->best, b->small, (void*)b->mg_partials, (void*)b->mg_result})
+                    (void*)b->keys, (void*)b->ord, (void*)b->keys2, (void*)b->ord2, (void*)b->radix_hist, b->block_sums, (void*)b->best, b->small, (void*)b->mg_partials, (void*)b->mg_result})
         cudaFree(p);
     delete b;
 }
@@ -166,7 +169,7 @@ template <class T> static lbfgs_b200_status sweep_launch(lbfgs_b200_box* b, cons
     return post_launch(ctx, "k_sweep");
 }
 
-// sort the finite positive breakpoints (bitonic network over npad = 2^k pairs)
+// sort the finite positive breakpoints by (breakpoint, index): LSD radix sort, 8 bits per pass (lbfgsb_kernels.cuh)
 template <class T> static lbfgs_b200_status box_sort(lbfgs_b200_box* b)
 {
     lbfgs_b200_ctx* ctx = b->h->ctx;
@@ -176,17 +179,19 @@ template <class T> static lbfgs_b200_status box_sort(lbfgs_b200_box* b)
     else k_sort_fill_f32<<<g, kThreads, 0, ctx->stream>>>(b->n, npad, static_cast<const float*>(b->brk), b->cls, b->keys, b->ord);
     if (auto st = post_launch(ctx, "k_sort_fill")) return st;
     const unsigned tiles = (unsigned)(npad / kSortTile);
-    k_sort_smem<<<tiles, 1024, 0, ctx->stream>>>(b->keys, b->ord, 2ull, (unsigned long long)kSortTile);
-    if (auto st = post_launch(ctx, "k_sort_smem")) return st;
-    for (unsigned long long k = 2ull * kSortTile; k <= (unsigned long long)npad; k <<= 1)
+    unsigned long long* kin = b->keys; unsigned long long* kout = b->keys2;
+    unsigned* iin = b->ord; unsigned* iout = b->ord2;
+    const int passes = (sizeof(T) == 8) ? 8 : 4;          // an even number of passes: the result is back in keys / ord
+    for (int p = 0; p < passes; p++)
     {
-        for (unsigned long long j = k >> 1; j >= (unsigned long long)kSortTile; j >>= 1)
-        {
-            k_sort_global<<<grid_for(ctx, npad * 2, 4), kThreads, 0, ctx->stream>>>(npad, b->keys, b->ord, k, j);
-            if (auto st = post_launch(ctx, "k_sort_global")) return st;
-        }
-        k_sort_smem<<<tiles, 1024, 0, ctx->stream>>>(b->keys, b->ord, k, k);
-        if (auto st = post_launch(ctx, "k_sort_smem")) return st;
+        k_radix_hist<<<tiles, 256, 0, ctx->stream>>>(kin, 8 * p, b->radix_hist, tiles);
+        if (auto st = post_launch(ctx, "k_radix_hist")) return st;
+        k_radix_scan<<<1, 1024, 0, ctx->stream>>>(b->radix_hist, (unsigned)kRadix * tiles);
+        if (auto st = post_launch(ctx, "k_radix_scan")) return st;
+        k_radix_scatter<<<tiles, 256, 0, ctx->stream>>>(kin, iin, kout, iout, 8 * p, b->radix_hist, tiles);
+        if (auto st = post_launch(ctx, "k_radix_scatter")) return st;
+        std::swap(kin, kout);
+        std::swap(iin, iout);
     }
     return LBFGS_B200_OK;
 }
@@ -316,8 +321,7 @@ lbfgs_b200_status lbfgs_b200_box_create(lbfgs_b200_hist* h, lbfgs_b200_box** out
     lbfgs_b200_box* b = new (std::nothrow) lbfgs_b200_box();
     if (!b) return fail(ctx, LBFGS_B200_ERR_ALLOC, "out of host memory");
     b->h = h; b->n = h->n;
-    int64_t npad = kSortTile;
-    while (npad < h->n) npad <<= 1;
+    const int64_t npad = ((h->n + kSortTile - 1) / kSortTile) * kSortTile;   // whole tiles of the radix sort
     b->npad = npad;
     const size_t vb = (size_t)h->ld * h->elem;
     const int m = h->m, w = 2 * m;
@@ -327,6 +331,9 @@ lbfgs_b200_status lbfgs_b200_box_create(lbfgs_b200_hist* h, lbfgs_b200_box** out
     if (e == cudaSuccess) e = cudaMalloc(&b->cls, (size_t)h->ld);
     if (e == cudaSuccess) e = cudaMalloc(&b->keys, sizeof(unsigned long long) * npad);
     if (e == cudaSuccess) e = cudaMalloc(&b->ord, sizeof(unsigned) * npad);
+    if (e == cudaSuccess) e = cudaMalloc(&b->keys2, sizeof(unsigned long long) * npad);
+    if (e == cudaSuccess) e = cudaMalloc(&b->ord2, sizeof(unsigned) * npad);
+    if (e == cudaSuccess) e = cudaMalloc(&b->radix_hist, sizeof(unsigned) * (size_t)kRadix * (npad / kSortTile));
     if (e == cudaSuccess) e = cudaMalloc(&b->block_sums, (size_t)h->elem * (npad / kScanBlock + 1) * (4 * m + 1));
     if (e == cudaSuccess) e = cudaMalloc(&b->best, sizeof(long long));
     if (e == cudaSuccess) e = cudaMalloc(&b->small, (size_t)h->elem * (4 * m * m + 4 * m + 5 + w + 16));

@@ -140,9 +140,14 @@ template <class T> __global__ void __launch_bounds__(kThreads) k_cauchy_breaks(i
     grid_reduce_mixed<5>(acc, rb, 16u);
 }
 
-// ---------------------------------------------------------------- bitonic sort of (key, index) pairs
-// keys: bit patterns of the positive finite breakpoints (order-preserving as unsigned), padded with ~0
-constexpr int kSortTile = 2048;   // pairs per CTA in the shared-memory phases (1024 threads, 2 pairs each)
+// ---------------------------------------------------------------- LSD radix sort of (key, index) pairs
+// Replaces the reference's std::sort of the breakpoints (Cauchy.h:31-50).  Keys: bit patterns of the positive finite breakpoints
+// (order-preserving as unsigned integers), padded with ~0 up to a whole number of tiles; payload: the coordinate index.  8 bits per
+// pass, least significant digit first, every pass stable -- so equal keys end up ordered by index (deterministic; std::sort leaves
+// ties unspecified).  Per pass: digit histogram of every 2048-pair tile -> exclusive scan over (digit, tile) -> stable scatter.
+// The pair arrays (12 bytes per coordinate) stay in L2; fp64 keys take 8 passes, fp32 keys 4.
+constexpr int kSortTile = 2048;   // pairs per CTA (256 threads: 8 warps x 8 rounds x 32 lanes)
+constexpr int kRadix = 256;
 
 __global__ void __launch_bounds__(kThreads) k_sort_fill(int64_t n, int64_t npad, const double* __restrict__ brk, const unsigned char* __restrict__ cls,
                                                        unsigned long long* keys, unsigned* idx)
@@ -167,56 +172,81 @@ __global__ void __launch_bounds__(kThreads) k_sort_fill_f32(int64_t n, int64_t n
     }
 }
 
-__device__ __forceinline__ void cmp_swap(unsigned long long& ka, unsigned& ia, unsigned long long& kb, unsigned& ib, bool up)
+// hist[d * ntiles + tile] = number of keys of the tile whose digit (bits [shift, shift+8)) is d
+__global__ void __launch_bounds__(256) k_radix_hist(const unsigned long long* __restrict__ keys, int shift, unsigned* __restrict__ hist, unsigned ntiles)
 {
-    // total order on (key, index) keeps the network deterministic for equal keys
-    const bool gt = (ka > kb) || (ka == kb && ia > ib);
-    if (gt == up)
-    {
-        const unsigned long long tk = ka; ka = kb; kb = tk;
-        const unsigned ti = ia; ia = ib; ib = ti;
-    }
-}
-
-// all steps j < kSortTile of stages k <= k_hi, starting at stage k_lo (k_lo == k_hi for the merge tail of a big stage)
-__global__ void __launch_bounds__(1024) k_sort_smem(unsigned long long* keys, unsigned* idx, unsigned long long k_lo, unsigned long long k_hi)
-{
-    __shared__ unsigned long long sk[kSortTile];
-    __shared__ unsigned si[kSortTile];
-    const int64_t base = (int64_t)blockIdx.x * kSortTile;
-    for (int t = threadIdx.x; t < kSortTile; t += 1024) { sk[t] = keys[base + t]; si[t] = idx[base + t]; }
+    __shared__ unsigned s_hist[kRadix];
+    s_hist[threadIdx.x] = 0u;
     __syncthreads();
-    for (unsigned long long k = k_lo; k <= k_hi; k <<= 1)
-    {
-        unsigned long long jstart = k >> 1;
-        if (jstart >= (unsigned long long)kSortTile) jstart = kSortTile >> 1;
-        for (unsigned long long j = jstart; j > 0; j >>= 1)
-        {
-            const unsigned t = threadIdx.x;
-            const unsigned lo = 2 * t - (t & (unsigned)(j - 1));      // index with bit j clear
-            const unsigned hi = lo + (unsigned)j;
-            const bool up = (((unsigned long long)(base + lo)) & k) == 0;
-            cmp_swap(sk[lo], si[lo], sk[hi], si[hi], up);
-            __syncthreads();
-        }
-    }
-    for (int t = threadIdx.x; t < kSortTile; t += 1024) { keys[base + t] = sk[t]; idx[base + t] = si[t]; }
+    const int64_t base = (int64_t)blockIdx.x * kSortTile;
+    for (int t = threadIdx.x; t < kSortTile; t += 256) atomicAdd(&s_hist[(unsigned)(keys[base + t] >> shift) & 255u], 1u);
+    __syncthreads();
+    hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = s_hist[threadIdx.x];
 }
 
-// one global step (j >= kSortTile) of stage k
-__global__ void __launch_bounds__(kThreads) k_sort_global(int64_t npad, unsigned long long* keys, unsigned* idx, unsigned long long k, unsigned long long j)
+// exclusive scan of `total` counters in place (one CTA of 1024 threads; digit-major order = the order of the sorted output)
+__global__ void __launch_bounds__(1024) k_radix_scan(unsigned* hist, unsigned total)
 {
-    for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < npad / 2; t += (int64_t)gridDim.x * kThreads)
+    __shared__ unsigned s_part[1024];
+    const unsigned per = (total + 1023u) / 1024u;
+    const unsigned lo = threadIdx.x * per, hi = (lo + per < total) ? lo + per : total;
+    unsigned sum = 0u;
+    for (unsigned i = lo; i < hi; i++) sum += hist[i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (unsigned off = 1; off < 1024u; off <<= 1)          // Hillis-Steele inclusive scan of the per-thread totals
     {
-        const unsigned long long lo = 2ull * t - (t & (j - 1));
-        const unsigned long long hi = lo + j;
-        unsigned long long ka = keys[lo], kb = keys[hi];
-        unsigned ia = idx[lo], ib = idx[hi];
-        const bool up = (lo & k) == 0;
-        const unsigned long long ka0 = ka;
-        const unsigned ia0 = ia;
-        cmp_swap(ka, ia, kb, ib, up);
-        if (ka != ka0 || ia != ia0) { keys[lo] = ka; idx[lo] = ia; keys[hi] = kb; idx[hi] = ib; }
+        const unsigned v = (threadIdx.x >= off) ? s_part[threadIdx.x - off] : 0u;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned run = (threadIdx.x == 0) ? 0u : s_part[threadIdx.x - 1];
+    for (unsigned i = lo; i < hi; i++) { const unsigned c = hist[i]; hist[i] = run; run += c; }
+}
+
+// stable scatter of one tile: position = scanned[digit][tile] + (pairs of this tile with the same digit that come before)
+__global__ void __launch_bounds__(256) k_radix_scatter(const unsigned long long* __restrict__ keys_in, const unsigned* __restrict__ idx_in,
+                                                       unsigned long long* __restrict__ keys_out, unsigned* __restrict__ idx_out, int shift,
+                                                       const unsigned* __restrict__ scanned, unsigned ntiles)
+{
+    __shared__ unsigned s_cnt[8][kRadix];     // per warp: pairs seen so far with each digit; later: exclusive offsets across warps
+    __shared__ unsigned s_base[kRadix];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int t = threadIdx.x; t < 8 * kRadix; t += 256) (&s_cnt[0][0])[t] = 0u;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * kSortTile + warp * 256;   // a warp owns 256 consecutive pairs, 32 per round
+    unsigned long long key[8];
+    unsigned rank[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+    {
+        key[r] = keys_in[base + r * 32 + lane];
+        const unsigned d = (unsigned)(key[r] >> shift) & 255u;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        unsigned old = 0u;
+        if (lane == leader) { old = s_cnt[warp][d]; s_cnt[warp][d] = old + __popc(peers); }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[r] = old + __popc(peers & ((1u << lane) - 1u));
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        const unsigned d = threadIdx.x;
+        unsigned run = 0u;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { const unsigned c = s_cnt[w][d]; s_cnt[w][d] = run; run += c; }
+        s_base[d] = scanned[(size_t)d * ntiles + blockIdx.x];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+    {
+        const unsigned d = (unsigned)(key[r] >> shift) & 255u;
+        const unsigned pos = s_base[d] + s_cnt[warp][d] + rank[r];
+        keys_out[pos] = key[r];
+        idx_out[pos] = idx_in[base + r * 32 + lane];
     }
 }
 

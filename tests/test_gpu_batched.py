@@ -62,7 +62,9 @@ def test_persistent_batch_equals_lone_solves_and_cpu_checker(orc):
         c2 = orc.lbfgs(po.OBJ_ROSENBROCK_PAIRED, X0[b], po.LS_MORE_THUENTE, cprm, sum_mode=po.SUM_LANES8)
         lo, hi = min(c1["niter"], c2["niter"]), max(c1["niter"], c2["niter"])
         assert 0.75 * lo <= res[b]["niter"] <= 1.25 * hi, (b, res[b]["niter"], c1["niter"], c2["niter"])
-        assert np.max(np.abs(X[b] - 1.0)) <= 3.0 * max(np.max(np.abs(c1["x"] - 1.0)), np.max(np.abs(c2["x"] - 1.0)), 1e-4)
+        # where the stop rule gnorm <= 1e-5 |x| catches the run differs between summation orders (factor 50 in |x - 1| on config 5's
+        # seeds, tests/golden/c5_full.json): hold the GPU to the rule itself and to the neighbourhood of x* = 1
+        assert res[b]["gnorm"] <= 1e-5 * np.linalg.norm(X[b]) * (1 + 1e-12) and np.max(np.abs(X[b] - 1.0)) <= 5e-3
 
 
 def test_persistent_batch_problems_leave_as_they_converge():
