@@ -309,8 +309,8 @@ def main():
         return {"kernel": kernel_name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": load_traffic(traffic_key), "peak_source": peak_src,
                 "algorithmic_bytes": "per launch (= one minimize): sum over the kernel's passes of whole vectors read + written, 8 n x "
-                                     "{first 3, trial 4, pair-forming dots 2c+4, combination + first trial 2c+5 (2c+2 without), plain dots 2c+1}, "
-                                     "c = pairs taking part in that pass; one iteration with T trials moves (4c+9) + 4(T-1) words per coordinate "
+                                     "{first 3, trial 4, pair-forming dots 2c+4, combination + first trial 2c+3 (+2 when its x, g are stored), plain dots 2c+1, materialise 4}, "
+                                     "c = pairs taking part in that pass; one iteration with T trials moves (4c+7) + 4(T-1) words per coordinate "
                                      "where SURVEY.md 8d counts (4c+2) + 6 + 8T for the unfused sequence",
                 "launches_timed": len(profs), "ms_per_launch": ms / max(1, len(profs)),
                 "passes": {k: {"ms_per_solve": v["ms"] / len(profs), "rounds_per_solve": v["rounds"] / len(profs),
@@ -434,6 +434,13 @@ def main():
                                   "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                                   "algorithmic_bytes": "lower bound 8n[4 nfev + niter((2c+9) + (4c+8))] (trials; breakpoints/classes/Cauchy build; one "
                                                        "BOXCQP sweep), c = m = 6: the path is launch- and host-latency-bound at n = 1e6, not HBM-bound"}})
+        # per-phase wall clock of the host-driven loop (LBFGSpp/PhaseClock.h: every scope synchronises, so the sum exceeds the untimed run)
+        lb.phase_clock(True)
+        for _ in range(2):
+            solver.minimize(lb.OBJ_ROSENBROCK_PAIRED, x0, 2.0, 4.0, trace_cap=256)
+        rep = lb.phase_report()
+        lb.phase_clock(False)
+        line["phases_ms_per_solve"] = {k: {"ms": 1e3 * v["seconds"] / 2, "calls": v["calls"] / 2} for k, v in rep.items()}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_block(name, r["niter"], r["nfev"], r["fx"])
 

@@ -277,15 +277,15 @@ lbfgs_b200_status lbfgs_b200_solver_create(lbfgs_b200_ctx* ctx, int64_t n, int m
 lbfgs_b200_status lbfgs_b200_solver_create_batch(lbfgs_b200_ctx* ctx, int64_t n, int m, int elem_bytes, int batch, lbfgs_b200_solver** out);
 void lbfgs_b200_solver_destroy(lbfgs_b200_solver* s);
 int lbfgs_b200_solver_batch(const lbfgs_b200_solver* s);
-/* Accounting of the last solve.  kernel_ms: device time of the one kernel (CUDA events around its launch).  The arrays have 8 slots
+/* Accounting of the last solve.  kernel_ms: device time of the one kernel (CUDA events around its launch).  The arrays have 10 slots
  * indexed by the pass a round ran: 0 = rounds in which the problems of a batch ran different passes, 1 FIRST, 2 TRIAL, 3 DOTS_FORM,
- * 4 DOTS_PLAIN, 5 COMBINE, 6 COMBINE_TRIAL, 7 RESTORE.  ms_by_op8: the kernel's time split by round (CTA 0's cycle counter scaled
- * to kernel_ms; includes each round's synchronisation); alg_bytes_by_op8: algorithmic bytes of those passes (whole vectors read and
- * written: FIRST 3n, TRIAL 4n, DOTS_FORM (2c+4)n, DOTS_PLAIN (2c+1)n, COMBINE (2c+2)n, COMBINE_TRIAL (2c+5)n words, + the objective's
+ * 4 DOTS_PLAIN, 5 COMBINE, 6 COMBINE_TRIAL, 7 RESTORE, 8 MATERIALIZE (9 unused).  ms_by_op10: the kernel's time split by round (CTA 0's cycle counter scaled
+ * to kernel_ms; includes each round's synchronisation); alg_bytes_by_op10: algorithmic bytes of those passes (whole vectors read and
+ * written: FIRST 3n, TRIAL 4n, DOTS_FORM (2c+4)n, DOTS_PLAIN (2c+1)n, COMBINE (2c+2)n, COMBINE_TRIAL (2c+3)n words or (2c+5)n when the first trial's x, g are stored, MATERIALIZE 4n words, + the objective's
  * data vectors per evaluation); sync_ms[2]: { the part of kernel_ms between CTA 0's arrival at a grid barrier and its release, the part of that spent waiting for
  * the last CTA to arrive }. */
-lbfgs_b200_status lbfgs_b200_solver_profile(const lbfgs_b200_solver* s, double* kernel_ms, double* ms_by_op8, unsigned long long* rounds_by_op8,
-                                            double* alg_bytes_by_op8, double* sync_ms);
+lbfgs_b200_status lbfgs_b200_solver_profile(const lbfgs_b200_solver* s, double* kernel_ms, double* ms_by_op10, unsigned long long* rounds_by_op10,
+                                            double* alg_bytes_by_op10, double* sync_ms);
 const void* lbfgs_b200_solver_final_grad(const lbfgs_b200_solver* s);   /* device pointer (problem 0), valid until the next minimize */
 const void* lbfgs_b200_solver_final_grad_of(const lbfgs_b200_solver* s, int problem);
 lbfgs_b200_hist* lbfgs_b200_solver_history(lbfgs_b200_solver* s);       /* the S/Y ring of problem 0 as left by the last solve   */

@@ -521,18 +521,18 @@ class Session:
         return dict(niter=res.niter, nfev=res.nfev, fx=res.fx, gnorm=res.gnorm, launches=res.launches,
                     h2d_bytes=res.h2d_bytes, d2h_bytes=res.d2h_bytes)
 
-    OPS = ("mixed", "first", "trial", "dots_form", "dots_plain", "combine", "combine_trial", "restore")
+    OPS = ("mixed", "first", "trial", "dots_form", "dots_plain", "combine", "combine_trial", "restore", "materialize", "-")
 
     def profile(self):
         """Accounting of the last device-resident solve: dict(kernel_ms, sync_ms, ops={name: dict(ms, rounds, alg_bytes)}); None for
         the host-driven loop."""
-        ms, rounds, nbytes = (C.c_double * 8)(), (C.c_ulonglong * 8)(), (C.c_double * 8)()
+        ms, rounds, nbytes = (C.c_double * 10)(), (C.c_ulonglong * 10)(), (C.c_double * 10)()
         kms, sync = C.c_double(0), (C.c_double * 2)()
         self.drv.lbfgsb200_drv_session_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         if self.drv.lbfgsb200_drv_session_profile(self.h, C.byref(kms), ms, rounds, nbytes, sync):
             return None
         return dict(kernel_ms=kms.value, sync_ms=sync[0], wait_last_cta_ms=sync[1],
-                    ops={self.OPS[k]: dict(ms=ms[k], rounds=int(rounds[k]), alg_bytes=nbytes[k]) for k in range(8) if rounds[k]})
+                    ops={self.OPS[k]: dict(ms=ms[k], rounds=int(rounds[k]), alg_bytes=nbytes[k]) for k in range(10) if rounds[k]})
 
     def result(self):
         p = self.drv.lbfgsb200_drv_session_result(self.h)

@@ -424,7 +424,7 @@ const double* lbfgsb200_drv_session_result(void* handle) { return static_cast<Se
 
 // accounting of the session's last device-resident solve (lbfgs_b200_solver_profile; sync_ms has 2 slots); returns 1 when the
 // session runs the host-driven loop
-int lbfgsb200_drv_session_profile(void* handle, double* kernel_ms, double* ms_by_op8, unsigned long long* rounds_by_op8, double* alg_bytes_by_op8,
+int lbfgsb200_drv_session_profile(void* handle, double* kernel_ms, double* ms_by_op10, unsigned long long* rounds_by_op10, double* alg_bytes_by_op10,
                                   double* sync_ms)
 {
     Session* s = static_cast<Session*>(handle);
@@ -437,7 +437,7 @@ int lbfgsb200_drv_session_profile(void* handle, double* kernel_ms, double* ms_by
     default: r = s->s_mt.resident_handle(); break;
     }
     if (!r) return 1;
-    return lbfgs_b200_solver_profile(r, kernel_ms, ms_by_op8, rounds_by_op8, alg_bytes_by_op8, sync_ms) == LBFGS_B200_OK ? 0 : 2;
+    return lbfgs_b200_solver_profile(r, kernel_ms, ms_by_op10, rounds_by_op10, alg_bytes_by_op10, sync_ms) == LBFGS_B200_OK ? 0 : 2;
 }
 
 }  // extern "C"

@@ -12,6 +12,8 @@
 //     COMBINE_TRIAL  COMBINE + the first trial of the next line search in the same pass: the reference restarts every search
 //                    at step = 1 (LBFGS.h:168), so x1 = x + d, g1 = grad f(x1) ; {g.d, f1, g1.d, g1.g1, x1.x1}
 //     RESTORE        x = xp, g = gp (a search that never improved on its start point; LineSearchMoreThuente.h:602-614)
+//     MATERIALIZE    x = xp + step*d, g = grad f(x) for a trial whose sums are already known: optional policy in which the fused first trial
+//                    does not store x1, g1 while first trials keep being rejected (see digest_trial; off by default)
 // Every CTA owns the same contiguous chunk (256-element granularity) of EVERY vector in EVERY pass, so a CTA only ever reads vector
 // elements it wrote itself (halo coordinates excepted, those are read through L2) and streams long contiguous runs.  Between rounds there is one
 // grid-wide synchronisation: CTAs deposit their partial sums in fixed slots, CTA 0 adds them in a fixed order (deterministic: no
@@ -41,7 +43,9 @@ constexpr int kPStageBytes = kGramStages * 4 * kGramTE * 8;   // dynamic shared 
 constexpr int kPMaxStages = 4;
 constexpr int kPCache = 4;                   // problems whose leader-side state is kept in shared memory
 
-enum { POP_IDLE = 0, POP_FIRST = 1, POP_TRIAL = 2, POP_DOTS_FORM = 3, POP_DOTS_PLAIN = 4, POP_COMBINE = 5, POP_COMBINE_TRIAL = 6, POP_RESTORE = 7 };
+enum { POP_IDLE = 0, POP_FIRST = 1, POP_TRIAL = 2, POP_DOTS_FORM = 3, POP_DOTS_PLAIN = 4, POP_COMBINE = 5, POP_COMBINE_TRIAL = 6, POP_RESTORE = 7,
+       POP_MATERIALIZE = 8 };
+constexpr int kPOps = 10;   // accounting slots (ops + the "mixed" bucket 0)
 
 // ---- per-problem state (device memory; the leader CTA's working copy) ----------------------------------------------------------
 template <class T> struct PState
@@ -69,6 +73,12 @@ template <class T> struct PState
     LBFGSpp::MoreThuenteCore<T> mt;
     int have_lo;
     T lo_gg, lo_xx, start_gg, start_xx;
+    // the fused first trial of a search may be "virtual": evaluated and reduced, but x1 / g1 not stored
+    int first_store;            // policy for the next COMBINE_TRIAL pass: 1 = store x1, g1
+    int adaptive_first_store;   // 1: first_store follows the fate of the last first trial (accepted -> store); 0: always store
+    int lo_virtual;             // the best-so-far point (x_lo, g_lo) is the virtual first trial: materialise it at lo_step if needed
+    T lo_step;
+    int after_materialize;      // what MATERIALIZE was for: 1 = the accepted trial, 2 = the best-so-far point
     // iteration scalars
     T fx, dg, gg, xx, gnorm, step;
     int k;
@@ -87,7 +97,7 @@ template <class T> struct alignas(128) PRound
 {
     T *x, *xp, *g, *gp, *drt;
     T step;
-    int op, c_round, head, pending, gram_cur, pad;
+    int op, c_round, head, pending, gram_cur, store_first;
 };
 
 struct alignas(128) PCtl
@@ -103,11 +113,11 @@ struct alignas(128) PCtl
     // accounting by CTA 0 (clock64 cycles of its SM): wall time of the rounds by the op they ran (bucket 0: rounds in which
     // problems ran different ops), the part of it spent between CTA 0's own arrival and the release (waiting for the slowest
     // CTA + the leader's work), and the algorithmic n-words of the passes (what the design has to move, see words_of)
-    long long cyc_op[8];
+    long long cyc_op[kPOps];
     long long cyc_sync;
     long long cyc_wait_all;     // of cyc_sync: from CTA 0's own arrival until the last CTA has arrived
-    unsigned long long n_op[8];
-    double words_op[8];
+    unsigned long long n_op[kPOps];
+    double words_op[kPOps];
 };
 constexpr unsigned kPStopBit = 0x80000000u;
 
@@ -304,6 +314,109 @@ __device__ __forceinline__ void p_trial(const OBJ& obj, const Own& own, const T*
         if (MODE == 1) store4<T, Hint::Plain, true>(x, i0, cnt, po);
         else store4<T, Hint::Plain, true>(dout, i0, cnt, po);
         store4<T, Hint::Plain, true>(g, i0, cnt, pg);
+    }
+    const double dacc[4] = {(double)acc[0], (double)acc[1], (double)acc[2], (double)acc[3]};
+    block_sums<4>(dacc, sh, dst, G);
+}
+
+// Neighbour-coupled objectives (chained Rosenbrock, tridiagonal quadratic): the same pass with its inputs staged tile by tile through
+// shared memory by bulk copies, every tile with one 16-byte granule of margin on either side, so that x_{i-1} and x_{i+1} of a pack
+// come from the tile instead of from single-word L2 loads per pack (3x faster on config 3).  Only the two ends of the GLOBAL vector
+// take their neighbours from the halo record (n-sharding) or as 0.
+constexpr int kTrialTE = 2016;    // 63 x 32 elements: with the margins, six fp64 (xp, d) stages fit the ring
+
+template <class T, class OBJ, int MODE>
+__device__ __forceinline__ void p_trial_halo(const OBJ& obj, const Own& own, const T* __restrict__ xp, const T* __restrict__ d, T step,
+                                             T* __restrict__ x, T* __restrict__ g, T* __restrict__ dout, T* tiles, PShared& sh, unsigned& phase_bits,
+                                             double* dst, int G)
+{
+    constexpr int NVEC = (MODE == 1) ? 2 : 1;
+    constexpr int PAD = 16 / (int)sizeof(T);                         // margin in elements = one 16-byte granule
+    constexpr int TS = kTrialTE + 2 * PAD;                           // staged elements per vector per tile
+    constexpr int STAGES_MAX = kPStageBytes / (NVEC * TS * (int)sizeof(T));
+    constexpr int STAGES = STAGES_MAX > kPMaxStages ? kPMaxStages : STAGES_MAX;
+    const int tid = threadIdx.x, lane = tid & 31;
+    uint64_t* full_bar = sh.full_bar;
+    const T* in0 = (MODE == 1) ? xp : x;
+    const int64_t n = own.n;
+    const int64_t ntl = own.ntiles(kTrialTE);
+    const int64_t n_pad = (n + 31) & ~int64_t(31);                   // the vectors are allocated in whole 256-byte lines
+
+    auto stage_tile = [&](int64_t t, int stage) {
+        if (tid != 0) return;
+        T* dstt = tiles + (size_t)stage * NVEC * TS;
+        const int64_t e0 = own.start(t, kTrialTE);
+        const int64_t lo = e0 >= PAD ? e0 - PAD : 0;                 // first element copied
+        int64_t hi = e0 + ((own.len(t, kTrialTE) + 31) & ~31) + PAD; // one past the last element copied
+        if (hi > n_pad) hi = n_pad;
+        const unsigned bytes = (unsigned)(hi - lo) * (unsigned)sizeof(T);
+        const int shift = (int)(lo - (e0 - PAD));                    // 0, or PAD at the very start of the vector
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&full_bar[stage], bytes * NVEC);
+        tma_load_1d(dstt + shift, in0 + lo, bytes, &full_bar[stage]);
+        if (MODE == 1) tma_load_1d(dstt + TS + shift, d + lo, bytes, &full_bar[stage]);
+    };
+
+    T acc[4] = {T(0), T(0), T(0), T(0)};
+    __syncthreads();   // the tile area is free
+    int64_t next_tile = 0;
+    for (int s = 0; s < STAGES; s++, next_tile++)
+        if (next_tile < ntl) stage_tile(next_tile, s);
+    int stage = 0;
+    for (int64_t t = 0; t < ntl; t++)
+    {
+        mbar_wait(&full_bar[stage], (phase_bits >> stage) & 1u);
+        phase_bits ^= (1u << stage);
+        const T* ta = tiles + (size_t)stage * NVEC * TS + PAD;       // element 0 of the tile
+        const T* tb = ta + TS;
+        const int64_t e0 = own.start(t, kTrialTE);
+        const int len = own.len(t, kTrialTE);
+        for (int off = tid * 4; off < len; off += kPThreads * 4)
+        {
+            const int64_t i0 = e0 + off;
+            const int cnt = (len - off >= 4) ? 4 : (len - off);
+            T xv[4], dv[4] = {T(0), T(0), T(0), T(0)}, gv[4];
+            T xl = T(0), xr = T(0);
+            const Pack<T> pa = lds_pack(ta + off, lane);
+            if (MODE == 1)
+            {
+                const Pack<T> pb = lds_pack(tb + off, lane);
+#pragma unroll
+                for (int k = 0; k < 4; k++) { dv[k] = (k < cnt) ? pb.v[k] : T(0); xv[k] = (k < cnt) ? pa.v[k] + step * pb.v[k] : T(0); }
+                if (i0 > 0) xl = ta[off - 1] + step * tb[off - 1];
+                else if (obj.halo && obj.gofs > 0) xl = T(ldv(obj.halo + kHaloLeftA)) + step * T(ldv(obj.halo + kHaloLeftB));
+                if (i0 + 4 < n) xr = ta[off + 4] + step * tb[off + 4];
+                else if (obj.halo && i0 + 4 == n && obj.gofs + n < obj.n_glob) xr = T(ldv(obj.halo + kHaloRightA)) + step * T(ldv(obj.halo + kHaloRightB));
+            }
+            else
+            {
+#pragma unroll
+                for (int k = 0; k < 4; k++) xv[k] = (k < cnt) ? pa.v[k] : T(0);
+                if (i0 > 0) xl = ta[off - 1];
+                else if (obj.halo && obj.gofs > 0) xl = T(ldv(obj.halo + kHaloLeftA));
+                if (i0 + 4 < n) xr = ta[off + 4];
+                else if (obj.halo && i0 + 4 == n && obj.gofs + n < obj.n_glob) xr = T(ldv(obj.halo + kHaloRightA));
+            }
+            acc[0] += obj.eval(i0, cnt, xv, xl, xr, gv);
+            Pack<T> pg, po;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+                acc[1] += gv[k] * dv[k];
+                acc[2] += gv[k] * gv[k];
+                acc[3] += (k < cnt) ? xv[k] * xv[k] : T(0);
+                pg.v[k] = gv[k];
+                po.v[k] = (MODE == 1) ? xv[k] : T(-1) * gv[k];
+            }
+            if (MODE == 1) store4<T, Hint::Plain, true>(x, i0, cnt, po);
+            else store4<T, Hint::Plain, true>(dout, i0, cnt, po);
+            store4<T, Hint::Plain, true>(g, i0, cnt, pg);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (next_tile < ntl) stage_tile(next_tile, stage);
+        next_tile++;
+        stage = (stage + 1 == STAGES) ? 0 : stage + 1;
     }
     const double dacc[4] = {(double)acc[0], (double)acc[1], (double)acc[2], (double)acc[3]};
     block_sums<4>(dacc, sh, dst, G);
@@ -577,14 +690,20 @@ __device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, int c,
     uint64_t* full_bar = sh.full_bar;
 
     auto tile_len = [&](int64_t t) { return own.len(t, TE); };
+    // one warp issues the NV bulk copies of a tile, a copy per lane (a single thread issuing 22..130 copies back to back costs as
+    // much as half a tile's transfer time); lane 0 posts the byte count first
     auto stage_tile = [&](int64_t t, int stage) {
-        if (tid != 0) return;
+        if (tid >= 32) return;
         T* dstt = tiles + (size_t)stage * NV * TE;
         const int64_t e0 = own.start(t, TE);
         const unsigned bytes = (unsigned)((tile_len(t) + 31) & ~31) * (unsigned)sizeof(T);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&full_bar[stage], bytes * (unsigned)NV);
-        for (int q = 0; q < NV; q++) tma_load_1d(dstt + (size_t)q * TE, static_cast<const T*>(sh.vecs[q]) + e0, bytes, &full_bar[stage]);
+        if (tid == 0)
+        {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&full_bar[stage], bytes * (unsigned)NV);
+        }
+        __syncwarp();
+        for (int q = tid; q < NV; q += 32) tma_load_1d(dstt + (size_t)q * TE, static_cast<const T*>(sh.vecs[q]) + e0, bytes, &full_bar[stage]);
     };
 
     T acc[5] = {T(0), T(0), T(0), T(0), T(0)};
@@ -654,8 +773,11 @@ __device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, int c,
                     ug.v[k] = gv[k];
                     uo.v[k] = xv[k];
                 }
-                st_unit<T>(x1_out, i0, cnt, uo);
-                st_unit<T>(g1_out, i0, cnt, ug);
+                if (x1_out != nullptr)
+                {
+                    st_unit<T>(x1_out, i0, cnt, uo);
+                    st_unit<T>(g1_out, i0, cnt, ug);
+                }
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -674,6 +796,154 @@ __device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, int c,
         const double dacc[1] = {(double)acc[0]};
         block_sums<1>(dacc, sh, dst, G);
     }
+}
+
+// ---- COMBINE + first trial for neighbour-coupled objectives (one GPU) --------------------------------------------------------
+// Same staging as p_combine<FUSE>, but every tile is copied with one 16-byte granule of margin on either side and d, x1 = x + d are
+// also formed for the element just outside each end of the tile (redundantly, with the very arithmetic of the tile that owns it),
+// x1 goes back into the staged x slot, and after a barrier the objective takes x1_{i-1}, x1_{i+1} from shared memory.  A tile has
+// at most kPThreads - 2 units, so a thread keeps its unit's d across the barrier.
+template <class T, class OBJ>
+__device__ __forceinline__ void p_combine_halo(const OBJ& obj, const Own& own, int c, T* tiles, T* __restrict__ res, T* __restrict__ x1_out,
+                                               T* __restrict__ g1_out, PShared& sh, unsigned& phase_bits, double* dst, int G)
+{
+    constexpr int EPT = 16 / (int)sizeof(T);
+    constexpr int PAD = EPT;
+    const int tid = threadIdx.x;
+    const int NV = 2 * c + 2;
+    int TE = 1024;
+    while (TE > 32 && (size_t)2 * NV * (TE + 2 * PAD) * sizeof(T) > (size_t)kPStageBytes) TE >>= 1;
+    const int TS = TE + 2 * PAD;
+    int stages = (int)((size_t)kPStageBytes / ((size_t)NV * TS * sizeof(T)));
+    stages = stages > kPMaxStages ? kPMaxStages : stages;
+    const int64_t n = own.n;
+    const int64_t ntl = own.ntiles(TE);
+    const int64_t n_pad = (n + 31) & ~int64_t(31);
+    const T* s_coef = reinterpret_cast<const T*>(sh.coef);
+    uint64_t* full_bar = sh.full_bar;
+
+    auto stage_tile = [&](int64_t t, int stage) {
+        if (tid >= 32) return;
+        T* dstt = tiles + (size_t)stage * NV * TS;
+        const int64_t e0 = own.start(t, TE);
+        const int64_t lo = e0 >= PAD ? e0 - PAD : 0;
+        int64_t hi = e0 + ((own.len(t, TE) + 31) & ~31) + PAD;
+        if (hi > n_pad) hi = n_pad;
+        const unsigned bytes = (unsigned)(hi - lo) * (unsigned)sizeof(T);
+        const int shift = (int)(lo - (e0 - PAD));
+        if (tid == 0)
+        {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&full_bar[stage], bytes * (unsigned)NV);
+        }
+        __syncwarp();
+        for (int q = tid; q < NV; q += 32) tma_load_1d(dstt + (size_t)q * TS + shift, static_cast<const T*>(sh.vecs[q]) + lo, bytes, &full_bar[stage]);
+    };
+
+    T acc[5] = {T(0), T(0), T(0), T(0), T(0)};
+    __syncthreads();
+    int64_t next_tile = 0;
+    for (int s = 0; s < stages; s++, next_tile++)
+        if (next_tile < ntl) stage_tile(next_tile, s);
+    const T cv = s_coef[0];
+    int stage = 0;
+    for (int64_t t = 0; t < ntl; t++)
+    {
+        mbar_wait(&full_bar[stage], (phase_bits >> stage) & 1u);
+        phase_bits ^= (1u << stage);
+        T* base = tiles + (size_t)stage * NV * TS + PAD;           // element 0 of the tile in vector 0
+        T* x1s = base + (size_t)(2 * c + 1) * TS;                  // the staged x, overwritten by x1
+        const int len = own.len(t, TE);
+        const int64_t e0 = own.start(t, TE);
+        const int nunits = (len + EPT - 1) / EPT;
+        // ---- phase 1: d and x1 for the tile's units and for the unit on either side ----
+        const int u = tid - 1;                                     // unit -1 and unit nunits are the margins
+        const int off = u * EPT;
+        const int64_t i0 = e0 + off;
+        const bool have = tid < nunits + 2 && i0 >= 0 && i0 < n;
+        const bool interior = have && u >= 0 && u < nunits;
+        const int cnt = have ? (int)((n - i0 >= EPT) ? EPT : (n - i0)) : 0;
+        T r[EPT];
+        Unit<T> uv;
+#pragma unroll
+        for (int k = 0; k < EPT; k++) { r[k] = T(0); uv.v[k] = T(0); }
+        if (have)
+        {
+            uv = lds_unit<T>(base + off);
+#pragma unroll
+            for (int k = 0; k < EPT; k++) r[k] = cv * uv.v[k];
+            const T* col = base + TS + off;
+#pragma unroll 8
+            for (int j = 0; j < c; j++)
+            {
+                const Unit<T> uy = lds_unit<T>(col + (size_t)j * TS);
+                const T cy = s_coef[1 + j];
+#pragma unroll
+                for (int k = 0; k < EPT; k++) r[k] += cy * uy.v[k];
+            }
+            col = base + (size_t)(c + 1) * TS + off;
+#pragma unroll 8
+            for (int j = c - 1; j >= 0; j--)
+            {
+                const Unit<T> us = lds_unit<T>(col + (size_t)j * TS);
+                const T cs = s_coef[1 + c + j];
+#pragma unroll
+                for (int k = 0; k < EPT; k++) r[k] += cs * us.v[k];
+            }
+            const Unit<T> ux = lds_unit<T>(x1s + off);
+            Unit<T> u1;
+#pragma unroll
+            for (int k = 0; k < EPT; k++) u1.v[k] = (k < cnt) ? ux.v[k] + T(1) * r[k] : T(0);
+            *reinterpret_cast<float4*>(x1s + off) = *reinterpret_cast<const float4*>(u1.v);
+            if (interior)
+            {
+                Unit<T> out;
+#pragma unroll
+                for (int k = 0; k < EPT; k++)
+                {
+                    out.v[k] = r[k];
+                    acc[0] += (k < cnt) ? uv.v[k] * r[k] : T(0);
+                }
+                st_unit<T>(res, i0, cnt, out);
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: the objective at x1 with its neighbours from shared memory ----
+        if (interior)
+        {
+            T xv[4] = {T(0), T(0), T(0), T(0)}, gv[4];
+            const Unit<T> u1 = lds_unit<T>(x1s + off);
+#pragma unroll
+            for (int k = 0; k < EPT; k++) xv[k] = u1.v[k];
+            const T xl = (i0 > 0) ? x1s[off - 1] : T(0);
+            const T right = (i0 + EPT < n) ? x1s[off + EPT] : T(0);
+            T xr = T(0);
+            if (EPT < 4) xv[EPT < 4 ? EPT : 3] = right; else xr = right;
+            acc[1] += obj.eval(i0, cnt, xv, xl, xr, gv);
+            Unit<T> ug, uo;
+#pragma unroll
+            for (int k = 0; k < EPT; k++)
+            {
+                acc[2] += (k < cnt) ? gv[k] * r[k] : T(0);
+                acc[3] += (k < cnt) ? gv[k] * gv[k] : T(0);
+                acc[4] += (k < cnt) ? xv[k] * xv[k] : T(0);
+                ug.v[k] = gv[k];
+                uo.v[k] = xv[k];
+            }
+            if (x1_out != nullptr)
+            {
+                st_unit<T>(x1_out, i0, cnt, uo);
+                st_unit<T>(g1_out, i0, cnt, ug);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (next_tile < ntl) stage_tile(next_tile, stage);
+        next_tile++;
+        stage = (stage + 1 == stages) ? 0 : stage + 1;
+    }
+    const double dacc[5] = {(double)acc[0], (double)acc[1], (double)acc[2], (double)acc[3], (double)acc[4]};
+    block_sums<5>(dacc, sh, dst, G);
 }
 
 // ---- waits with a watchdog ----------------------------------------------------------------------------------------------------
@@ -725,16 +995,35 @@ template <class T> __device__ __forceinline__ bool converged_after_search(PState
     return false;
 }
 
-// the trial at ls_step_ref(st) has been evaluated: {fx, dg, gg, xx}.  Sets the next op.
-template <class T> __device__ __forceinline__ void digest_trial(PState<T>* st, T fx, T dg, T gg, T xx)
+// after a search has produced its point in (x, g): convergence tests, then on to the pair-forming dots
+template <class T> __device__ __forceinline__ void after_search(PState<T>* st)
+{
+    if (converged_after_search(st)) return;
+    st->op = POP_DOTS_FORM;
+    st->c_round = st->ncorr < st->m ? st->ncorr + 1 : st->m;
+}
+
+// the trial at ls_step_ref(st) has been evaluated: {fx, dg, gg, xx}.  Sets the next op.  `is_virtual`: the fused first trial
+// whose x1 / g1 were not stored (they are x = xp + 1*d and its gradient: a MATERIALIZE pass recomputes them bit for bit if the
+// search turns out to need them).  Adaptive policy (off by default, LBFGS_B200_VIRTUAL_FIRST_TRIAL=1): store the next first trial
+// iff this one was accepted.  Measured on config 2 (3 of 21 first trials accepted): 0.25 ms saved in the combination passes,
+// 0.20 ms spent on the three MATERIALIZE rounds -- a wash at n = 1e7 and a loss at n = 1e6, hence off.
+template <class T> __device__ __forceinline__ void digest_trial(PState<T>* st, T fx, T dg, T gg, T xx, bool is_first, bool is_virtual)
 {
     record_eval(st, fx);
     bool keep = false;
+    const T step_tried = ls_step_ref(st);
     const int rc = ls_advance(st, fx, dg, keep);
+    if (is_first && st->adaptive_first_store) st->first_store = (rc == LBFGSpp::LSC_ACCEPT) ? 1 : 0;
     if (keep)
     {
-        dswap(st->x, st->x_lo);
-        dswap(st->g, st->g_lo);
+        if (is_virtual) { st->lo_virtual = 1; st->lo_step = step_tried; }
+        else
+        {
+            dswap(st->x, st->x_lo);
+            dswap(st->g, st->g_lo);
+            st->lo_virtual = 0;
+        }
         st->have_lo = 1;
         st->lo_gg = gg;
         st->lo_xx = xx;
@@ -743,6 +1032,7 @@ template <class T> __device__ __forceinline__ void digest_trial(PState<T>* st, T
     if (rc == LBFGSpp::LSC_ACCEPT)
     {
         st->fx = fx; st->dg = dg; st->gg = gg; st->xx = xx;
+        if (is_virtual) { st->op = POP_MATERIALIZE; st->step = step_tried; st->after_materialize = 1; return; }
     }
     else if (rc == LBFGSpp::LSC_TAKE_BEST)
     {
@@ -752,10 +1042,11 @@ template <class T> __device__ __forceinline__ void digest_trial(PState<T>* st, T
         st->dg = bd;
         if (st->have_lo)
         {
-            dswap(st->x, st->x_lo);
-            dswap(st->g, st->g_lo);
             st->gg = st->lo_gg;
             st->xx = st->lo_xx;
+            if (st->lo_virtual) { st->op = POP_MATERIALIZE; st->step = st->lo_step; st->after_materialize = 2; return; }
+            dswap(st->x, st->x_lo);
+            dswap(st->g, st->g_lo);
         }
         else
         {
@@ -766,9 +1057,7 @@ template <class T> __device__ __forceinline__ void digest_trial(PState<T>* st, T
         }
     }
     else { finish(st, st->k, rc); return; }
-    if (converged_after_search(st)) return;
-    st->op = POP_DOTS_FORM;
-    st->c_round = st->ncorr < st->m ? st->ncorr + 1 : st->m;
+    after_search(st);
 }
 
 // top of an iteration (LBFGS.h:121-127): the search is armed, the current point becomes the previous one
@@ -781,6 +1070,7 @@ template <class T> __device__ __forceinline__ bool begin_search(PState<T>* st, T
     dswap(st->xp, st->x);
     dswap(st->gp, st->g);
     st->have_lo = 0;
+    st->lo_virtual = 0;
     st->start_gg = st->gg;
     st->start_xx = st->xx;
     st->op = POP_TRIAL;
@@ -808,12 +1098,11 @@ template <class T> __device__ void advance_problem(PState<T>* st, const double* 
         return;
     }
     case POP_TRIAL:
-        digest_trial(st, (T)vals[0], (T)vals[1], (T)vals[2], (T)vals[3]);
+        digest_trial(st, (T)vals[0], (T)vals[1], (T)vals[2], (T)vals[3], false, false);
         return;
     case POP_RESTORE:
-        if (converged_after_search(st)) return;
-        st->op = POP_DOTS_FORM;
-        st->c_round = st->ncorr < st->m ? st->ncorr + 1 : st->m;
+    case POP_MATERIALIZE:       // (x, g) now hold the search's point; its sums were digested before
+        after_search(st);
         return;
     case POP_DOTS_FORM:
     {
@@ -839,12 +1128,13 @@ template <class T> __device__ void advance_problem(PState<T>* st, const double* 
     case POP_COMBINE_TRIAL:
     {
         const bool fused = st->op == POP_COMBINE_TRIAL;
+        const bool stored = st->first_store != 0;      // what this pass was told (the policy flag changes in digest_trial)
         if (st->pending >= 0) { st->gram_cur = 1 - st->gram_cur; st->pending = -1; }
         st->dg = (T)vals[0];                // LBFGS.h:123 for the next pass
         st->k += 1;
         if (!begin_search(st, T(1))) return;   // LBFGS.h:168
         // the pass already evaluated x + 1*d into the buffers that the rotation just made (x, g)
-        if (fused && ls_step_ref(st) == T(1)) digest_trial(st, (T)vals[1], (T)vals[2], (T)vals[3], (T)vals[4]);
+        if (fused && ls_step_ref(st) == T(1)) digest_trial(st, (T)vals[1], (T)vals[2], (T)vals[3], (T)vals[4], true, !stored);
         return;
     }
     default: return;
@@ -852,17 +1142,17 @@ template <class T> __device__ void advance_problem(PState<T>* st, const double* 
 }
 
 // n-words a pass has to move (reads + writes of whole vectors): the roofline numerator of the persistent kernel
-__device__ __forceinline__ double words_of(int op, int c, int data_vectors)
+__device__ __forceinline__ double words_of(int op, int c, int data_vectors, int store_first)
 {
     switch (op)
     {
     case POP_FIRST: return 3.0 + data_vectors;              // R x ; W g, d
-    case POP_TRIAL: return 4.0 + data_vectors;              // R xp, d ; W x, g
+    case POP_TRIAL: case POP_MATERIALIZE: return 4.0 + data_vectors;   // R xp, d ; W x, g
     case POP_RESTORE: return 4.0;                           // R xp, gp ; W x, g
     case POP_DOTS_FORM: return 2.0 * c + 4.0;               // R x, xp, g, gp, 2(c-1) columns ; W s, y
     case POP_DOTS_PLAIN: return 2.0 * c + 1.0;              // R g, 2c columns
     case POP_COMBINE: return 2.0 * c + 2.0;                 // R g, 2c columns ; W d
-    case POP_COMBINE_TRIAL: return 2.0 * c + 5.0 + data_vectors;   // R g, x, 2c columns ; W d, x1, g1
+    case POP_COMBINE_TRIAL: return 2.0 * c + 3.0 + (store_first ? 2.0 : 0.0) + data_vectors;   // R g, x, 2c columns ; W d (, x1, g1)
     default: return 0.0;
     }
 }
@@ -871,7 +1161,7 @@ __device__ __forceinline__ int nvals_of(int op, int c_round)
 {
     switch (op)
     {
-    case POP_FIRST: case POP_TRIAL: return 4;
+    case POP_FIRST: case POP_TRIAL: case POP_MATERIALIZE: return 4;
     case POP_DOTS_FORM: case POP_DOTS_PLAIN: return c_round * kGramVals;
     case POP_COMBINE: return 1;
     case POP_COMBINE_TRIAL: return 5;
@@ -994,6 +1284,7 @@ __device__ int leader_round(const PArgs<T>& a, int G, PShared& sh, PState<T>* ca
             rd->x = st->x; rd->xp = st->xp; rd->g = st->g; rd->gp = st->gp; rd->drt = st->drt;
             rd->step = st->step;
             rd->c_round = st->c_round; rd->head = st->head; rd->pending = st->pending; rd->gram_cur = st->gram_cur;
+            rd->store_first = st->first_store;
             rd->op = st->op;
             running = st->op != POP_IDLE;
         }
@@ -1148,17 +1439,21 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
             T* const vx = ldv(&rd->x); T* const vxp = ldv(&rd->xp); T* const vg = ldv(&rd->g); T* const vgp = ldv(&rd->gp); T* const vd = ldv(&rd->drt);
             const T step = ldv(&rd->step);
             const int c_round = ldv(&rd->c_round), head = ldv(&rd->head), pending = ldv(&rd->pending), gram_cur = ldv(&rd->gram_cur);
+            const int store_first = ldv(&rd->store_first);
             acct_bucket = (acct_bucket == -1 || acct_bucket == op) ? op : 0;
-            acct_words += words_of(op, c_round, kDataVectors);
+            acct_words += words_of(op, c_round, kDataVectors, store_first);
             double* dst = a.partials + (size_t)b * a.pstride * G + cta;
             const OBJ obj = PObjMaker<T, OBJ>::make(a, st->data0, st->data1, (HALO && a.xc != nullptr) ? st->halo : nullptr);
             switch (op)
             {
             case POP_FIRST:
-                p_trial<T, OBJ, 0>(obj, own, nullptr, nullptr, T(0), vx, vg, vd, sh, dst, G);
+                if constexpr (HALO) p_trial_halo<T, OBJ, 0>(obj, own, nullptr, nullptr, T(0), vx, vg, vd, tiles, sh, phase_bits, dst, G);
+                else p_trial<T, OBJ, 0>(obj, own, nullptr, nullptr, T(0), vx, vg, vd, sh, dst, G);
                 break;
             case POP_TRIAL:
-                p_trial<T, OBJ, 1>(obj, own, vxp, vd, step, vx, vg, nullptr, sh, dst, G);
+            case POP_MATERIALIZE:
+                if constexpr (HALO) p_trial_halo<T, OBJ, 1>(obj, own, vxp, vd, step, vx, vg, nullptr, tiles, sh, phase_bits, dst, G);
+                else p_trial<T, OBJ, 1>(obj, own, vxp, vd, step, vx, vg, nullptr, sh, dst, G);
                 break;
             case POP_RESTORE:
                 p_restore<T>(own, vxp, vgp, vx, vg);
@@ -1202,7 +1497,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
                 __syncthreads();   // the tile area / tables may still be in use by the previous problem's pass
                 gram_solve_in_smem<T>(g, tiles, cta == 0);
                 // coefficients out of the tile area (the staging ring is about to overwrite it), operand table in coefficient order
-                const bool fuse = !OBJ::kHalo && op == POP_COMBINE_TRIAL;
+                const bool fuse = op == POP_COMBINE_TRIAL;
                 {
                     const T* s_coef = tiles + 2 * g.c * g.c;
                     T* keep = reinterpret_cast<T*>(sh.coef);
@@ -1214,16 +1509,12 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
                     }
                     if (tid == 0) { sh.vecs[0] = vg; sh.vecs[2 * g.c + 1] = vx; }
                 }
-                bool done = false;
-                if constexpr (!OBJ::kHalo)
+                if (fuse)
                 {
-                    if (fuse)
-                    {
-                        p_combine<T, OBJ, true>(obj, own, g.c, tiles, vd, vxp, vgp, sh, phase_bits, dst, G);
-                        done = true;
-                    }
+                    if constexpr (OBJ::kHalo) p_combine_halo<T, OBJ>(obj, own, g.c, tiles, vd, store_first ? vxp : nullptr, store_first ? vgp : nullptr, sh, phase_bits, dst, G);
+                    else p_combine<T, OBJ, true>(obj, own, g.c, tiles, vd, store_first ? vxp : nullptr, store_first ? vgp : nullptr, sh, phase_bits, dst, G);
                 }
-                if (!done) p_combine<T, OBJ, false>(obj, own, g.c, tiles, vd, nullptr, nullptr, sh, phase_bits, dst, G);
+                else p_combine<T, OBJ, false>(obj, own, g.c, tiles, vd, nullptr, nullptr, sh, phase_bits, dst, G);
                 break;
             }
             default: break;

@@ -110,7 +110,11 @@ static lbfgs_b200_status solver_minimize(lbfgs_b200_solver* s, int objective, co
         p.epsilon = (T)prm->epsilon; p.epsilon_rel = (T)prm->epsilon_rel; p.delta = (T)prm->delta; p.max_step = (T)prm->max_step;
         p.eps_gate = std::numeric_limits<T>::epsilon();
         p.past = prm->past; p.max_iterations = prm->max_iterations; p.ls_kind = ls_kind;
-        p.fuse_first_trial = coupled ? 0 : 1;
+        // the first trial of every search rides on the combination pass; a neighbour-coupled objective needs its neighbours' x + d,
+        // which only exist on this rank when n is not sharded
+        p.fuse_first_trial = (coupled && ctx->nranks > 1) ? 0 : 1;
+        p.adaptive_first_store = (getenv("LBFGS_B200_VIRTUAL_FIRST_TRIAL") && atoi(getenv("LBFGS_B200_VIRTUAL_FIRST_TRIAL")) != 0) ? 1 : 0;
+        p.first_store = p.adaptive_first_store ? 0 : 1;
         p.ls_opt.linesearch = (ls_kind == 3) ? 3 : prm->linesearch;
         p.ls_opt.max_linesearch = prm->max_linesearch;
         p.ls_opt.min_step = (T)prm->min_step; p.ls_opt.max_step = (T)prm->max_step; p.ls_opt.ftol = (T)prm->ftol; p.ls_opt.wolfe = (T)prm->wolfe;
@@ -124,7 +128,7 @@ static lbfgs_b200_status solver_minimize(lbfgs_b200_solver* s, int objective, co
     {
         const PState<T>& p = hs[b];
         hr[b].x = p.x; hr[b].xp = p.xp; hr[b].g = p.g; hr[b].gp = p.gp; hr[b].drt = p.drt;
-        hr[b].step = T(0); hr[b].op = p.op; hr[b].c_round = 0; hr[b].head = 0; hr[b].pending = -1; hr[b].gram_cur = p.gram_cur;
+        hr[b].step = T(0); hr[b].op = p.op; hr[b].c_round = 0; hr[b].head = 0; hr[b].pending = -1; hr[b].gram_cur = p.gram_cur; hr[b].store_first = p.first_store;
     }
     CU(ctx, cudaMemcpyAsync(s->d_state, hs, sizeof(PState<T>) * (size_t)B, cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaMemcpyAsync(s->d_rounds, hr, sizeof(PRound<T>) * (size_t)B, cudaMemcpyHostToDevice, ctx->stream));
@@ -253,20 +257,20 @@ void lbfgs_b200_solver_destroy(lbfgs_b200_solver* s)
 }
 
 int lbfgs_b200_solver_batch(const lbfgs_b200_solver* s) { return s ? s->B : 0; }
-lbfgs_b200_status lbfgs_b200_solver_profile(const lbfgs_b200_solver* s, double* kernel_ms, double* ms_by_op8, unsigned long long* rounds_by_op8,
-                                            double* alg_bytes_by_op8, double* sync_ms)
+lbfgs_b200_status lbfgs_b200_solver_profile(const lbfgs_b200_solver* s, double* kernel_ms, double* ms_by_op10, unsigned long long* rounds_by_op10,
+                                            double* alg_bytes_by_op10, double* sync_ms)
 {
     if (!s) return LBFGS_B200_ERR_INVALID;
     const lb::PCtl& c = s->last_ctl;
     long long total = 0;
-    for (int k = 0; k < 8; k++) total += c.cyc_op[k];
+    for (int k = 0; k < lb::kPOps; k++) total += c.cyc_op[k];
     const double scale = total > 0 ? (double)s->last_kernel_ms / (double)total : 0.0;   // CTA 0's cycles -> share of the event-timed kernel
     if (kernel_ms) *kernel_ms = s->last_kernel_ms;
-    for (int k = 0; k < 8; k++)
+    for (int k = 0; k < lb::kPOps; k++)
     {
-        if (ms_by_op8) ms_by_op8[k] = scale * (double)c.cyc_op[k];
-        if (rounds_by_op8) rounds_by_op8[k] = c.n_op[k];
-        if (alg_bytes_by_op8) alg_bytes_by_op8[k] = c.words_op[k] * (double)s->n * (double)s->elem;
+        if (ms_by_op10) ms_by_op10[k] = scale * (double)c.cyc_op[k];
+        if (rounds_by_op10) rounds_by_op10[k] = c.n_op[k];
+        if (alg_bytes_by_op10) alg_bytes_by_op10[k] = c.words_op[k] * (double)s->n * (double)s->elem;
     }
     if (sync_ms) { sync_ms[0] = scale * (double)c.cyc_sync; sync_ms[1] = scale * (double)c.cyc_wait_all; }
     return LBFGS_B200_OK;

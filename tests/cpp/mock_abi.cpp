@@ -603,7 +603,16 @@ MOCK_BOX(float, f32)
 
 // ---- device-resident solve: not provided by the test double ------------------------------------------------------------------------
 lbfgs_b200_status lbfgs_b200_solver_create(lbfgs_b200_ctx* c, int64_t, int, int, lbfgs_b200_solver**) { return unsupported(c, "the device-resident solve"); }
+lbfgs_b200_status lbfgs_b200_solver_create_batch(lbfgs_b200_ctx* c, int64_t, int, int, int, lbfgs_b200_solver**) { return unsupported(c, "the device-resident solve"); }
 void lbfgs_b200_solver_destroy(lbfgs_b200_solver*) {}
+int lbfgs_b200_solver_batch(const lbfgs_b200_solver*) { return 0; }
+const void* lbfgs_b200_solver_final_grad_of(const lbfgs_b200_solver*, int) { return nullptr; }
+lbfgs_b200_hist* lbfgs_b200_solver_history_of(lbfgs_b200_solver*, int) { return nullptr; }
+lbfgs_b200_status lbfgs_b200_solver_profile(const lbfgs_b200_solver*, double*, double*, unsigned long long*, double*, double*) { return LBFGS_B200_ERR_INVALID; }
+lbfgs_b200_status lbfgs_b200_solver_minimize_batch_f64(lbfgs_b200_solver*, int, const double*, const double*, int64_t, const lbfgs_b200_param*, int, double*,
+                                                       int64_t, lbfgs_b200_outcome*) { return unsupported(nullptr, "the device-resident solve"); }
+lbfgs_b200_status lbfgs_b200_solver_minimize_batch_f32(lbfgs_b200_solver*, int, const float*, const float*, int64_t, const lbfgs_b200_param*, int, float*,
+                                                       int64_t, lbfgs_b200_outcome*) { return unsupported(nullptr, "the device-resident solve"); }
 const void* lbfgs_b200_solver_final_grad(const lbfgs_b200_solver*) { return nullptr; }
 lbfgs_b200_hist* lbfgs_b200_solver_history(lbfgs_b200_solver*) { return nullptr; }
 lbfgs_b200_status lbfgs_b200_solver_minimize_f64(lbfgs_b200_solver*, int, const double*, const double*, const lbfgs_b200_param*, int, double*,
