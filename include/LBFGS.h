@@ -124,6 +124,7 @@ private:
     Device* m_rdev;
     std::ptrdiff_t m_rn;
     int m_rm;
+    bool m_resident_last;   // the last minimize() ran on the device-resident solver: its ring (not m_bfgs's) holds the final approximation
     double* m_trace;
     long m_trace_cap;
 
@@ -149,7 +150,7 @@ private:
         lbfgs_b200_outcome out;
         dev.check(detail::resident_abi<Scalar>::minimize(m_rsolver, f.builtin_kind(), f.builtin_data0(), f.builtin_data1(), &p,
                                                          detail::line_search_id<LineSearch>::value, x.data(), m_trace, m_trace_cap, &out));
-        m_bfgs.borrow(dev, lbfgs_b200_solver_history(m_rsolver), n, m_param.m);   // final_approx_hessian() describes this solve
+        m_resident_last = true;   // final_approx_hessian() asks the solver for this solve's ring on demand
         f.add_calls(long(out.nfev));
         m_nfev = long(out.nfev);
         if (!m_grad.is_bound_to(dev)) m_grad = Vector(dev);
@@ -184,7 +185,7 @@ private:
 
 public:
     LBFGSSolver(const LBFGSParam<Scalar>& param) :
-        m_param(param), m_gnorm(0), m_nfev(0), m_resident(-1), m_rsolver(nullptr), m_rdev(nullptr), m_rn(0), m_rm(0), m_trace(nullptr),
+        m_param(param), m_gnorm(0), m_nfev(0), m_resident(-1), m_rsolver(nullptr), m_rdev(nullptr), m_rn(0), m_rm(0), m_resident_last(false), m_trace(nullptr),
         m_trace_cap(0)
     {
         m_param.check_param();
@@ -218,6 +219,7 @@ public:
             if (try_resident(f, x, fx, niter_resident)) return niter_resident;
         }
 
+        m_resident_last = false;
         m_bfgs.reset(dev, n, m_param.m);
         for (Vector* v : {&m_xp, &m_grad, &m_gradp, &m_drt, &m_ws.x_lo, &m_ws.grad_lo})
         {
@@ -296,8 +298,20 @@ public:
     Scalar final_grad_norm() const { return m_gnorm; }
     // final_approx_hessian() / final_approx_inverse_hessian() of the reference (LBFGS.h:192-197 -> BFGSMat.h:150-271): explicit
     // n x n matrices, only sensible for small n; returned row-major on the host.
-    SmallMatrix<Scalar> final_approx_hessian() { return m_bfgs.dense(false); }
-    SmallMatrix<Scalar> final_approx_inverse_hessian() { return m_bfgs.dense(true); }
+    SmallMatrix<Scalar> final_approx_hessian() { sync_history(); return m_bfgs.dense(false); }
+    SmallMatrix<Scalar> final_approx_inverse_hessian() { sync_history(); return m_bfgs.dense(true); }
+
+private:
+    // after a device-resident solve the S/Y ring lives in the solver (tiled layout): fetch a column-major copy and let m_bfgs look at it
+    void sync_history()
+    {
+        if (!m_resident_last || !m_rsolver) return;
+        lbfgs_b200_hist* h = lbfgs_b200_solver_history(m_rsolver);
+        if (!h) m_rdev->check(LBFGS_B200_ERR_CUDA);
+        m_bfgs.borrow(*m_rdev, h, m_rn, m_rm);
+    }
+
+public:
     // number of objective evaluations of the last minimize() call (not in the reference; used by tests/bench)
     long num_evaluations() const { return m_nfev; }
 };

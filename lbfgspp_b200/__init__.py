@@ -605,6 +605,26 @@ class BatchSession:
             self.h = None
 
 
+def solve_dense(objective, x0, param=None, linesearch="NocedalWright", resident=True, device=0):
+    """minimize() then final_approx_hessian() / final_approx_inverse_hessian() (small n).  Returns (niter, x, B, H)."""
+    drv = driver()
+    x = np.array(x0, dtype=np.float64, order="C").copy()
+    n = x.size
+    param = param if param is not None else LBFGSParam()
+    p = param._c()
+    ls = LINE_SEARCHES[linesearch] if isinstance(linesearch, str) else int(linesearch)
+    Bm, Hm = np.zeros((n, n)), np.zeros((n, n))
+    niter = C.c_int(0)
+    err = C.create_string_buffer(256)
+    dp = C.POINTER(C.c_double)
+    drv.lbfgsb200_drv_solve_dense_f64.argtypes = [C.c_int, C.c_int, C.c_long, C.c_int, C.POINTER(_DrvParam), C.c_int, dp, dp, dp,
+                                                  C.POINTER(C.c_int), C.c_char_p, C.c_int]
+    if drv.lbfgsb200_drv_solve_dense_f64(device, objective, n, ls, C.byref(p), int(resident), x.ctypes.data_as(dp), Bm.ctypes.data_as(dp),
+                                         Hm.ctypes.data_as(dp), C.byref(niter), err, 256):
+        raise RuntimeError("solve_dense failed: " + err.value.decode())
+    return niter.value, x, Bm, Hm
+
+
 def phase_clock(on=True):
     """Enable / disable (and clear) the wall-clock accounting of the host-driven L-BFGS-B loop's phases (LBFGSpp/PhaseClock.h)."""
     driver().lbfgsb200_drv_phase_enable(int(on))

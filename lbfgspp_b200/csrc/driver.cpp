@@ -779,6 +779,46 @@ extern "C" int lbfgsb200_drv_batch_session_solve(void* handle, drv_batch_item* i
     }
 }
 
+// minimize() followed by final_approx_hessian() / final_approx_inverse_hessian() (reference LBFGS.h:192-197) on a built-in objective;
+// resident = 1: the device-resident solve (the matrices then come from the solver's own ring), 0: the host-driven loop.
+extern "C" int lbfgsb200_drv_solve_dense_f64(int device_ordinal, int objective, long n, int ls, const drv_param* q, int resident, double* x_host,
+                                             double* B_out /* n*n */, double* H_out /* n*n */, int* niter_out, char* err, int errlen)
+{
+    try
+    {
+        Device& dev = device(device_ordinal);
+        const LBFGSParam<double> prm = to_param<double>(q);
+        BuiltinObjective<double> obj(objective);
+        DeviceVector<double> x(dev);
+        x.copy_from_host(x_host, n);
+        double fx = 0;
+        SmallMatrix<double> Bm, Hm;
+        int niter = 0;
+        auto run = [&](auto& solver) {
+            solver.set_device_resident(resident != 0);
+            niter = solver.minimize(obj, x, fx);
+            Bm = solver.final_approx_hessian();
+            Hm = solver.final_approx_inverse_hessian();
+        };
+        switch (ls)
+        {
+        case DRV_LS_BACKTRACKING: { LBFGSSolver<double, LineSearchBacktracking> s(prm); run(s); break; }
+        case DRV_LS_BRACKETING: { LBFGSSolver<double, LineSearchBracketing> s(prm); run(s); break; }
+        case DRV_LS_NOCEDAL_WRIGHT: { LBFGSSolver<double, LineSearchNocedalWright> s(prm); run(s); break; }
+        default: { LBFGSSolver<double, LineSearchMoreThuente> s(prm); run(s); break; }
+        }
+        x.copy_to_host(x_host);
+        for (long i = 0; i < n * n; i++) { B_out[i] = Bm.data()[i]; H_out[i] = Hm.data()[i]; }
+        if (niter_out) *niter_out = niter;
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        if (err && errlen > 0) { std::strncpy(err, e.what(), size_t(errlen) - 1); err[errlen - 1] = 0; }
+        return 1;
+    }
+}
+
 // PhaseClock (include/LBFGSpp/PhaseClock.h): wall-clock accounting of the host-driven L-BFGS-B loop's phases for bench.py / profiles
 extern "C" void lbfgsb200_drv_phase_enable(int on)
 {

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <limits>
 #include <new>
+#include <algorithm>
 #include <atomic>
 #include <string>
 #include <vector>

@@ -47,13 +47,30 @@ enum { POP_IDLE = 0, POP_FIRST = 1, POP_TRIAL = 2, POP_DOTS_FORM = 3, POP_DOTS_P
        POP_MATERIALIZE = 8 };
 constexpr int kPOps = 10;   // accounting slots (ops + the "mixed" bucket 0)
 
+// ---- the S/Y history of the solve: tiled layout ---------------------------------------------------------------------------------
+// H[block][slot][S|Y][BT]: all ring slots of one block of BT coordinates lie next to each other (BT = the largest power of two for
+// which two stages of 2m+4 rows fit the kernel's shared memory: 512 for fp64 m = 10).  A pass over a tile then needs the right-hand
+// vectors plus ONE or TWO bulk copies of 8..90 KB for all history columns (the live slots form a cyclic range of the ring), instead
+// of one 4 KB copy per column: measured, the per-copy cost of 22 separate copies was ~15 % of the combination pass, and 42 copies of
+// 2 KB at m = 20 made it 2.8x slower per byte.  The new pair of an iteration is written as one 2*BT run per block.
+template <class T> struct PHist
+{
+    T* H;
+    int bt_log, M;
+    int64_t bstride;      // elements per block: M * 2 * BT
+    __device__ __forceinline__ int BT() const { return 1 << bt_log; }
+    __device__ __forceinline__ T* s_at(int slot, int64_t i) const { return H + (i >> bt_log) * bstride + ((int64_t)slot << (bt_log + 1)) + (i & (BT() - 1)); }
+    __device__ __forceinline__ T* y_at(int slot, int64_t i) const { return s_at(slot, i) + BT(); }
+};
+
 // ---- per-problem state (device memory; the leader CTA's working copy) ----------------------------------------------------------
 template <class T> struct PState
 {
     // vectors (rotate by pointer swap)
     T *x, *xp, *g, *gp, *drt, *x_lo, *g_lo;
     // history storage (fixed for the duration of the kernel: other CTAs read these fields with ordinary loads)
-    T *S, *Y, *ys, *alpha, *theta;
+    PHist<T> hist;              // the S/Y ring, tiled (see PHist)
+    T *ys, *alpha, *theta;
     T *SY[2], *YY[2], *SS[2];
     const T *data0, *data1;
     double* raw;               // [pstride] reduced values of the last round
@@ -129,7 +146,8 @@ template <class T> struct PArgs
     PCtl* ctl;
     double* partials;           // [B][pstride][G]
     int pstride;
-    int64_t n, ld;
+    int64_t n;
+    int grain;                  // chunk boundaries are multiples of this many elements (= the history's block length)
     const XComm* xc;
     int64_t index_offset, n_global;
 };
@@ -199,25 +217,27 @@ struct PShared
     double red[kPWarps][3 * kGramVals];     // block reduction scratch (dots: ROUNDS*6 values per warp)
     double coef[2 * kMaxM + 2];             // combination coefficients {cv, cy[c], cs[c]} (stored as T)
     const void* vecs[2 * kMaxM + 2];        // combination pass: the staged vectors {g, (x), y_0.., s_0..} in coefficient order
-    unsigned char slots[kMaxM];
+    unsigned char slots[kMaxM];             // by age: packed row of the column in the staged history block
+    unsigned char slotid[kMaxM];            // by age: physical ring slot
+    double margin[2][2 * kMaxM + 2];        // neighbour-coupled combination pass: operands of the element on either side of a tile
     unsigned char ops[4096];                // this round's op of every problem
 };
 
-// Ownership.  CTA i owns the contiguous chunk [c0, c1) of every vector (boundaries on multiples of kPGrain elements, the chunks
-// differ by at most one grain) in EVERY pass: a CTA only ever reads what it wrote itself, and every CTA streams long contiguous
+// Ownership.  CTA i owns the contiguous chunk [c0, c1) of every vector (boundaries on multiples of the history's block length, the
+// chunks differ by at most one block) in EVERY pass: a CTA only ever reads what it wrote itself, and every CTA streams long contiguous
 // runs of each vector (measured faster than dealing 2048-element blocks round-robin: 14.3 vs 15.1 ms per config-2 solve).
 struct Own
 {
     int64_t n;
-    int G, cta, BS;   // BS: largest tile a pass may use
+    int G, cta;
     int64_t c0, c1;
-    __device__ __forceinline__ Own(int64_t n_, int G_, int cta_) : n(n_), G(G_), cta(cta_), BS(2048)
+    __device__ __forceinline__ Own(int64_t n_, int G_, int cta_, int grain) : n(n_), G(G_), cta(cta_)
     {
-        const int64_t units = (n + kPGrain - 1) / kPGrain;
+        const int64_t units = (n + grain - 1) / grain;
         const int64_t K = units < G ? units : G;
         if (cta >= K) { c0 = c1 = 0; return; }
-        c0 = ((units * cta) / K) * kPGrain;
-        c1 = ((units * (cta + 1)) / K) * kPGrain;
+        c0 = ((units * cta) / K) * grain;
+        c1 = ((units * (cta + 1)) / K) * grain;
         if (c1 > n) c1 = n;
     }
     // tiles of TE elements: number owned, first element and length of the t-th (the last one may be shorter)
@@ -437,82 +457,92 @@ __device__ __forceinline__ void p_restore(const Own& own, const T* __restrict__ 
     }
 }
 
+// the `cnt` slots of the ring that end just below `end` (cyclically), as <= 2 ascending runs of slots; packed row of a slot
+struct SlotRuns
+{
+    int a0, a1, b0, b1;   // run A = [a0, a1), run B = [b0, b1) (empty when b0 == b1); rows: A first, then B
+    __device__ __forceinline__ SlotRuns(int end, int cnt, int M)
+    {
+        if (cnt <= end) { a0 = end - cnt; a1 = end; b0 = b1 = 0; }
+        else { a0 = 0; a1 = end; b0 = M - (cnt - end); b1 = M; }
+    }
+    __device__ __forceinline__ int row_of(int slot) const { return (slot >= a0 && slot < a1) ? slot - a0 : (a1 - a0) + (slot - b0); }
+};
+
+// 16-byte units (2 doubles / 4 floats): the granularity of the staged passes
+template <class T> struct alignas(16) Unit { T v[16 / sizeof(T)]; };
+template <class T> __device__ __forceinline__ Unit<T> lds_unit(const T* p)
+{
+    Unit<T> u;
+    *reinterpret_cast<float4*>(u.v) = *reinterpret_cast<const float4*>(p);
+    return u;
+}
+template <class T> __device__ __forceinline__ void st_unit(T* base, int64_t i0, int cnt, const Unit<T>& u)
+{
+    constexpr int EPT = 16 / (int)sizeof(T);
+    if (cnt >= EPT) { *reinterpret_cast<float4*>(base + i0) = *reinterpret_cast<const float4*>(u.v); return; }
+#pragma unroll
+    for (int k = 0; k < EPT; k++)
+        if (k < cnt) base[i0 + k] = u.v[k];
+}
+template <class T> __device__ __forceinline__ void mask_unit(Unit<T>& u, int cnt)
+{
+#pragma unroll
+    for (int k = 0; k < 16 / (int)sizeof(T); k++) u.v[k] = (k < cnt) ? u.v[k] : T(0);
+}
+
+// copies of one tile: `nrhs` right-hand vectors (sh.vecs[0..nrhs), round_up(len, 32) elements each) + the history runs of block
+// `blk`; one lane per copy.  Returns nothing; the stage's barrier has been told the byte count.
+template <class T>
+__device__ __forceinline__ void stage_tiled(T* dstt, int TE, int nrhs, int64_t e0, int len, const PHist<T>& h, const SlotRuns& runs, PShared& sh,
+                                            uint64_t* bar)
+{
+    const int tid = threadIdx.x;
+    if (tid >= 32) return;
+    const unsigned rbytes = (unsigned)((len + 31) & ~31) * (unsigned)sizeof(T);
+    const unsigned abytes = (unsigned)(runs.a1 - runs.a0) * 2u * (unsigned)TE * (unsigned)sizeof(T);
+    const unsigned bbytes = (unsigned)(runs.b1 - runs.b0) * 2u * (unsigned)TE * (unsigned)sizeof(T);
+    if (tid == 0)
+    {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy accesses of this stage before the copies that overwrite it
+        mbar_expect_tx(bar, rbytes * (unsigned)nrhs + abytes + bbytes);
+    }
+    __syncwarp();
+    const T* blk = h.H + (e0 >> h.bt_log) * h.bstride;
+    if (tid < nrhs) tma_load_1d(dstt + (size_t)tid * TE, static_cast<const T*>(sh.vecs[tid]) + e0, rbytes, bar);
+    else if (tid == nrhs && abytes) tma_load_1d(dstt + (size_t)nrhs * TE, blk + (size_t)runs.a0 * 2 * TE, abytes, bar);
+    else if (tid == nrhs + 1 && bbytes) tma_load_1d(dstt + (size_t)(nrhs + 2 * (runs.a1 - runs.a0)) * TE, blk + (size_t)runs.b0 * 2 * TE, bbytes, bar);
+}
+
 // ---- DOTS -----------------------------------------------------------------------------------------------------------------------
-// [S Y]'[v s_new y_new] over this CTA's chunk; FORM: the newest pair is formed on the fly from (x, xp, v = g, gp) into ring slot
-// `new_slot` and takes part as the newest column (same tile pipeline as k_pair_dots in two_loop_gram.cuh: TMA-staged right-hand
-// vectors, S/Y columns streamed into registers, one warp -- or `split` warps -- per column pair).  PLAIN: s.v and y.v only.
-// Tiles are kGramTE elements; the last tile of a chunk may be shorter (a multiple of 32 elements is copied, lanes past its length
-// are masked).
+// [S Y]'[v s_new y_new] over this CTA's chunk, one block (tile) at a time, everything staged by bulk copies.  FORM: the newest pair
+// is formed on the fly from (x, xp, v = g, gp) -- s = x - xp, y = g - gp, identical in every warp that needs them -- takes part as
+// column 0 and is written to ring slot `new_slot` by the warps that own column 0.  Column j (by age) belongs to warp group j, whose
+// `split` warps share the tile's units.  PLAIN: s.v and y.v over the old history only.
 template <class T> struct PDots
 {
-    int64_t n, ld;
-    const T* v;
-    const T* S;
-    const T* Y;
-    int c, new_slot, split, cols_per_round;
-    const T *fx, *fxp, *fgp;
-    T *s_out, *y_out;
+    int64_t n;
+    PHist<T> h;
+    int c;               // columns taking part (FORM: including the new pair)
+    int end, cnt_old;    // the old columns: the cnt_old slots below `end`
+    int new_slot, split, cols_per_round;
 };
 
 template <class T, int ROUNDS, bool FORM>
 __device__ __forceinline__ void p_dots(const PDots<T>& a, const Own& own, T* tiles, PShared& sh, unsigned& phase_bits, double* dst, int G)
 {
-    constexpr int NT = 4;                                        // stage stride in vectors (FORM uses all four)
+    constexpr int EPT = 16 / (int)sizeof(T);
+    constexpr int NRHS = FORM ? 4 : 1;                           // staged right-hand vectors: g (, x, gp, xp)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int TE = a.h.BT();
     const int my_col = warp / a.split, my_part = warp % a.split;
-    const int DTE = own.BS < kGramTE ? own.BS : kGramTE;          // tile length (the stage stride stays kGramTE)
-    const int part_len = DTE / a.split;                           // >= 256 (the caller bounds `split`)
+    const int upp = (TE / EPT) / a.split;                        // units of a tile per warp of a column group
+    const SlotRuns runs(a.end, a.cnt_old, a.h.M);
+    const int nrows = NRHS + 2 * a.cnt_old;
+    int stages = (int)((size_t)kPStageBytes / ((size_t)nrows * TE * sizeof(T)));
+    stages = stages > kPMaxStages ? kPMaxStages : stages;
+    const int64_t ntl = own.ntiles(TE);
     uint64_t* full_bar = sh.full_bar;
-    int64_t ntl = own.ntiles(DTE);
-    while (ntl > 0 && own.len(ntl - 1, DTE) == 0) ntl--;          // trailing tiles of the vector's last block may be empty
-
-    auto tile_len = [&](int64_t t) { return own.len(t, DTE); };
-    auto stage_tile = [&](int64_t t, int stage) {
-        if (tid != 0) return;
-        T* dstt = tiles + (size_t)stage * NT * kGramTE;
-        const int64_t e0 = own.start(t, DTE);
-        const unsigned bytes = (unsigned)((tile_len(t) + 31) & ~31) * (unsigned)sizeof(T);   // whole 32-element groups: inside the padding
-        // the stage was last touched through the generic proxy (LDS of the dots, STS of form_tile): order those accesses before the
-        // bulk copy that overwrites it
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if constexpr (FORM)
-        {
-            mbar_expect_tx(&full_bar[stage], bytes * 4);
-            tma_load_1d(dstt, a.v + e0, bytes, &full_bar[stage]);
-            tma_load_1d(dstt + kGramTE, a.fx + e0, bytes, &full_bar[stage]);
-            tma_load_1d(dstt + 2 * kGramTE, a.fgp + e0, bytes, &full_bar[stage]);
-            tma_load_1d(dstt + 3 * kGramTE, a.fxp + e0, bytes, &full_bar[stage]);
-        }
-        else
-        {
-            mbar_expect_tx(&full_bar[stage], bytes);
-            tma_load_1d(dstt, a.v + e0, bytes, &full_bar[stage]);
-        }
-    };
-    auto wait_tile = [&](int st) {
-        mbar_wait(&full_bar[st], (phase_bits >> st) & 1u);
-        phase_bits ^= (1u << st);
-    };
-    // FORM: turn a landed tile {g, x, gp, xp} into {g, s = x - xp, y = g - gp} in place and write s, y to the ring columns
-    auto form_tile = [&](int64_t t, int st) {
-        T* tt = tiles + (size_t)st * NT * kGramTE;
-        const int64_t e0f = own.start(t, DTE);
-        const int lim = (tile_len(t) + 31) & ~31;
-        for (int i = tid * 4; i < lim; i += kPThreads * 4)
-        {
-            Pack<T> ps, py;
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-            {
-                ps.v[k] = tt[kGramTE + i + k] - tt[3 * kGramTE + i + k];
-                py.v[k] = tt[i + k] - tt[2 * kGramTE + i + k];
-            }
-#pragma unroll
-            for (int k = 0; k < 4; k++) { tt[kGramTE + i + k] = ps.v[k]; tt[2 * kGramTE + i + k] = py.v[k]; }
-            st_pack<Hint::Plain>(a.s_out + e0f + i, ps);
-            st_pack<Hint::Plain>(a.y_out + e0f + i, py);
-        }
-    };
 
     T acc[ROUNDS][kGramVals];
 #pragma unroll
@@ -520,113 +550,80 @@ __device__ __forceinline__ void p_dots(const PDots<T>& a, const Own& own, T* til
 #pragma unroll
         for (int k = 0; k < kGramVals; k++) acc[r][k] = T(0);
 
-    __syncthreads();   // the stages (and sh.slots) are free: every thread has left the previous pass
+    __syncthreads();   // sh.vecs / sh.slots are in place and the staging ring is free
     int64_t next_tile = 0;
-    for (int s = 0; s < kGramStages; s++, next_tile++)
-        if (next_tile < ntl) stage_tile(next_tile, s);
-    if constexpr (FORM)
-    {
-        if (ntl > 0) { wait_tile(0); form_tile(0, 0); }
-        __syncthreads();
-    }
+    for (int s = 0; s < stages; s++, next_tile++)
+        if (next_tile < ntl) stage_tiled<T>(tiles + (size_t)s * nrows * TE, TE, NRHS, own.start(next_tile, TE), own.len(next_tile, TE), a.h, runs, sh, &full_bar[s]);
     int stage = 0;
     for (int64_t t = 0; t < ntl; t++)
     {
-        if constexpr (!FORM) wait_tile(stage);
-        const T* vt = tiles + (size_t)stage * NT * kGramTE;
-        const T* snt = vt + kGramTE;
-        const T* ynt = vt + 2 * kGramTE;
-        const int64_t e0 = own.start(t, DTE);
-        const int len = tile_len(t);
-        const bool full_tile = (len == DTE);
+        mbar_wait(&full_bar[stage], (phase_bits >> stage) & 1u);
+        phase_bits ^= (1u << stage);
+        const T* base = tiles + (size_t)stage * nrows * TE;
+        const T* hist = base + (size_t)NRHS * TE;
+        const int64_t e0 = own.start(t, TE);
+        const int len = own.len(t, TE);
 #pragma unroll
         for (int r = 0; r < ROUNDS; r++)
         {
             const int j = r * a.cols_per_round + my_col;
             if (my_col < a.cols_per_round && j < a.c)
             {
-                const int slot = sh.slots[j];
-                const bool is_new = FORM && slot == a.new_slot;
-                const T* scol = a.S + (int64_t)slot * a.ld + e0;
-                const T* ycol = a.Y + (int64_t)slot * a.ld + e0;
-#pragma unroll 2
-                for (int base = my_part * part_len + lane * 4; base < (my_part + 1) * part_len; base += 256)
+                const bool is_new = FORM && j == 0;
+                const T* srow = hist + (size_t)2 * (is_new ? 0 : sh.slots[j]) * TE;     // sh.slots[j]: packed row of the column of age j
+                const T* yrow = srow + TE;
+                T* s_new = a.h.s_at(a.new_slot < 0 ? 0 : a.new_slot, e0);
+                for (int u = my_part * upp + lane; u < (my_part + 1) * upp; u += 32)
                 {
-                    Pack<T> ps[2], py[2];
-#pragma unroll
-                    for (int u = 0; u < 2; u++)
+                    const int off = u * EPT;
+                    const int cnt = len - off;
+                    if (cnt <= 0) break;
+                    Unit<T> ug = lds_unit<T>(base + off), us, uy, usn, uyn;
+                    if constexpr (FORM)
                     {
-                        const int off = base + u * 128;
+                        const Unit<T> ux = lds_unit<T>(base + TE + off), ugp = lds_unit<T>(base + 2 * TE + off), uxp = lds_unit<T>(base + 3 * TE + off);
+#pragma unroll
+                        for (int k = 0; k < EPT; k++) { usn.v[k] = ux.v[k] - uxp.v[k]; uyn.v[k] = ug.v[k] - ugp.v[k]; }
+                        if (cnt < EPT) { mask_unit(usn, cnt); mask_unit(uyn, cnt); }
+                    }
+                    bool loaded = false;
+                    if constexpr (FORM)
+                    {
                         if (is_new)
                         {
-                            ps[u] = lds_pack(snt + off, lane);
-                            py[u] = lds_pack(ynt + off, lane);
-                        }
-                        else if (full_tile || off + 4 <= len)
-                        {
-                            ps[u] = ld_pack<Hint::Stream>(scol + off);
-                            py[u] = ld_pack<Hint::Stream>(ycol + off);
-                        }
-                        else
-                        {
-#pragma unroll
-                            for (int k = 0; k < 4; k++)
-                            {
-                                const bool ok = off + k < len;
-                                ps[u].v[k] = ok ? scol[off + k] : T(0);
-                                py[u].v[k] = ok ? ycol[off + k] : T(0);
-                            }
+                            us = usn; uy = uyn;
+                            st_unit<T>(s_new, off, cnt, usn);
+                            st_unit<T>(s_new + TE, off, cnt, uyn);
+                            loaded = true;
                         }
                     }
+                    if (!loaded) { us = lds_unit<T>(srow + off); uy = lds_unit<T>(yrow + off); }
+                    if (cnt < EPT) { mask_unit(ug, cnt); mask_unit(us, cnt); mask_unit(uy, cnt); }
 #pragma unroll
-                    for (int u = 0; u < 2; u++)
+                    for (int k = 0; k < EPT; k++)
                     {
-                        const int off = base + u * 128;
-                        Pack<T> pv = lds_pack(vt + off, lane);
-                        if (!full_tile)
-                        {
-                            const int cnt = len - off;            // lanes past the tile's length: zero on both sides of every product
-                            mask_pack(pv, cnt);
-                            mask_pack(ps[u], cnt);
-                            mask_pack(py[u], cnt);
-                        }
+                        acc[r][0] += us.v[k] * ug.v[k];
+                        acc[r][1] += uy.v[k] * ug.v[k];
+                    }
+                    if constexpr (FORM)
+                    {
 #pragma unroll
-                        for (int k = 0; k < 4; k++)
+                        for (int k = 0; k < EPT; k++)
                         {
-                            acc[r][0] += ps[u].v[k] * pv.v[k];
-                            acc[r][1] += py[u].v[k] * pv.v[k];
-                        }
-                        if constexpr (FORM)
-                        {
-                            Pack<T> pyn = lds_pack(ynt + off, lane), psn = lds_pack(snt + off, lane);
-                            if (!full_tile)
-                            {
-                                mask_pack(pyn, len - off);
-                                mask_pack(psn, len - off);
-                            }
-#pragma unroll
-                            for (int k = 0; k < 4; k++)
-                            {
-                                acc[r][2] += ps[u].v[k] * pyn.v[k];
-                                acc[r][3] += py[u].v[k] * pyn.v[k];
-                                acc[r][4] += py[u].v[k] * psn.v[k];
-                                acc[r][5] += ps[u].v[k] * psn.v[k];
-                            }
+                            acc[r][2] += us.v[k] * uyn.v[k];
+                            acc[r][3] += uy.v[k] * uyn.v[k];
+                            acc[r][4] += uy.v[k] * usn.v[k];
+                            acc[r][5] += us.v[k] * usn.v[k];
                         }
                     }
                 }
             }
         }
-        if constexpr (FORM)
-        {
-            const int nstage = (stage + 1 == kGramStages) ? 0 : stage + 1;
-            if (t + 1 < ntl) { wait_tile(nstage); form_tile(t + 1, nstage); }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads / form_tile writes of this stage before its re-arming bulk copy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        if (next_tile < ntl) stage_tile(next_tile, stage);
+        if (next_tile < ntl) stage_tiled<T>(tiles + (size_t)stage * nrows * TE, TE, NRHS, own.start(next_tile, TE), own.len(next_tile, TE), a.h, runs, sh, &full_bar[stage]);
         next_tile++;
-        stage = (stage + 1 == kGramStages) ? 0 : stage + 1;
+        stage = (stage + 1 == stages) ? 0 : stage + 1;
     }
 
     // block reduction: lanes -> warp, then the `split` warps of a column; value (j, k) -> dst[(j*6 + k) * G]
@@ -650,119 +647,205 @@ __device__ __forceinline__ void p_dots(const PDots<T>& a, const Own& own, T* til
     }
 }
 
-// 16-byte units (2 doubles / 4 floats): the granularity of the combination pass
-template <class T> struct alignas(16) Unit { T v[16 / sizeof(T)]; };
-template <class T> __device__ __forceinline__ Unit<T> lds_unit(const T* p)
-{
-    Unit<T> u;
-    *reinterpret_cast<float4*>(u.v) = *reinterpret_cast<const float4*>(p);
-    return u;
-}
-template <class T> __device__ __forceinline__ void st_unit(T* base, int64_t i0, int cnt, const Unit<T>& u)
-{
-    constexpr int EPT = 16 / (int)sizeof(T);
-    if (cnt == EPT) { *reinterpret_cast<float4*>(base + i0) = *reinterpret_cast<const float4*>(u.v); return; }
-#pragma unroll
-    for (int k = 0; k < EPT; k++)
-        if (k < cnt) base[i0 + k] = u.v[k];
-}
-
 // ---- COMBINE (+ first trial) ---------------------------------------------------------------------------------------------------
 // d = cv*v + sum_j cy_j*y_j + cs_j*s_j ; FUSE: x1 = xc + d, g1 = grad f(x1) written to (x1_out, g1_out) and the four trial sums.
-// ALL operands are staged tile by tile through shared memory by bulk copies: NV = 2c + 1 (+1 with FUSE) vectors per tile listed in
-// sh.vecs in coefficient order {v, y_0 .. y_{c-1}, s_0 .. s_{c-1}, (xc)}; the tile length is the largest power of two for which
-// two stages fit the kernel's shared memory (c = 10, fp64: 512 elements = 88 KB per stage).  A thread owns one 4-element pack of
-// the tile and adds the terms in the order the recursion would (y newest -> oldest, then s oldest -> newest).
-template <class T, class OBJ, bool FUSE>
-__device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, int c, T* tiles, T* __restrict__ res,
+// Staged rows of a tile: v, (xc,) then the history block's live slots; sh.slots[j] = packed row of the pair of age j.  A thread owns
+// one 16-byte unit of the tile and adds the terms in the order the recursion would (y newest -> oldest, then s oldest -> newest), with
+// the operand loads of 8 columns in flight before their multiply-adds retire (the pass is bound by shared-memory latency otherwise).
+// HALO (neighbour-coupled objectives, one GPU): x1 goes back into the staged x row, two spare warps form d and x1 of the element on
+// either side of the tile from global memory with the very arithmetic of the tile that owns it, and after a barrier the objective
+// takes x1_{i-1}, x1_{i+1} from shared memory.
+template <class T, class OBJ, bool FUSE, bool HALO>
+__device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, const PHist<T>& h, int c, int end, T* tiles, T* __restrict__ res,
                                           T* __restrict__ x1_out, T* __restrict__ g1_out, PShared& sh, unsigned& phase_bits, double* dst, int G)
 {
-    constexpr int EPT = 16 / (int)sizeof(T);       // elements per 16-byte unit: 2 doubles / 4 floats
-    const int tid = threadIdx.x;
-    const int NV = 2 * c + 1 + (FUSE ? 1 : 0);
-    int TE = kGramTE;
-    while (TE > 32 && (TE > own.BS || (size_t)2 * NV * TE * sizeof(T) > (size_t)kPStageBytes)) TE >>= 1;
-    int stages = (int)((size_t)kPStageBytes / ((size_t)NV * TE * sizeof(T)));
+    constexpr int EPT = 16 / (int)sizeof(T);
+    constexpr int NRHS = FUSE ? 2 : 1;                            // v (, xc)
+    constexpr int PAD = EPT;                                      // HALO: room for x1 of the neighbouring element on either side of the x row
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int TE = h.BT();
+    const SlotRuns runs(end, c, h.M);
+    const int nrows = NRHS + 2 * c;
+    const size_t stage_elems = (size_t)nrows * TE + (HALO ? 2 * PAD : 0);
+    int stages = (int)((size_t)kPStageBytes / (stage_elems * sizeof(T)));
     stages = stages > kPMaxStages ? kPMaxStages : stages;
-    int64_t ntl = own.ntiles(TE);
-    while (ntl > 0 && own.len(ntl - 1, TE) == 0) ntl--;
+    const int64_t n = own.n;
+    const int64_t ntl = own.ntiles(TE);
     const T* s_coef = reinterpret_cast<const T*>(sh.coef);
     uint64_t* full_bar = sh.full_bar;
-
-    auto tile_len = [&](int64_t t) { return own.len(t, TE); };
-    // one warp issues the NV bulk copies of a tile, a copy per lane (a single thread issuing 22..130 copies back to back costs as
-    // much as half a tile's transfer time); lane 0 posts the byte count first
-    auto stage_tile = [&](int64_t t, int stage) {
+    // HALO: the x row is staged one granule into the stage (row 1 starts at TE + PAD), everything after it shifts by 2*PAD
+    auto stage_one = [&](int64_t t, int s) {
+        T* dstt = tiles + (size_t)s * stage_elems;
+        if (!HALO) { stage_tiled<T>(dstt, TE, NRHS, own.start(t, TE), own.len(t, TE), h, runs, sh, &full_bar[s]); return; }
         if (tid >= 32) return;
-        T* dstt = tiles + (size_t)stage * NV * TE;
         const int64_t e0 = own.start(t, TE);
-        const unsigned bytes = (unsigned)((tile_len(t) + 31) & ~31) * (unsigned)sizeof(T);
+        const int len = own.len(t, TE);
+        const unsigned rbytes = (unsigned)((len + 31) & ~31) * (unsigned)sizeof(T);
+        const unsigned abytes = (unsigned)(runs.a1 - runs.a0) * 2u * (unsigned)TE * (unsigned)sizeof(T);
+        const unsigned bbytes = (unsigned)(runs.b1 - runs.b0) * 2u * (unsigned)TE * (unsigned)sizeof(T);
         if (tid == 0)
         {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(&full_bar[stage], bytes * (unsigned)NV);
+            mbar_expect_tx(&full_bar[s], rbytes * 2u + abytes + bbytes);
         }
         __syncwarp();
-        for (int q = tid; q < NV; q += 32) tma_load_1d(dstt + (size_t)q * TE, static_cast<const T*>(sh.vecs[q]) + e0, bytes, &full_bar[stage]);
+        const T* blk = h.H + (e0 >> h.bt_log) * h.bstride;
+        T* hist = dstt + 2 * (size_t)TE + 2 * PAD;
+        if (tid == 0) tma_load_1d(dstt, static_cast<const T*>(sh.vecs[0]) + e0, rbytes, &full_bar[s]);
+        else if (tid == 1) tma_load_1d(dstt + TE + PAD, static_cast<const T*>(sh.vecs[1]) + e0, rbytes, &full_bar[s]);
+        else if (tid == 2 && abytes) tma_load_1d(hist, blk + (size_t)runs.a0 * 2 * TE, abytes, &full_bar[s]);
+        else if (tid == 3 && bbytes) tma_load_1d(hist + (size_t)2 * (runs.a1 - runs.a0) * TE, blk + (size_t)runs.b0 * 2 * TE, bbytes, &full_bar[s]);
     };
 
     T acc[5] = {T(0), T(0), T(0), T(0), T(0)};
-    __syncthreads();   // sh.vecs / sh.coef are in place and the tile area is free
+    __syncthreads();   // sh.vecs / sh.coef / sh.slots are in place and the staging ring is free
     int64_t next_tile = 0;
     for (int s = 0; s < stages; s++, next_tile++)
-        if (next_tile < ntl) stage_tile(next_tile, s);
+        if (next_tile < ntl) stage_one(next_tile, s);
     const T cv = s_coef[0];
     int stage = 0;
     for (int64_t t = 0; t < ntl; t++)
     {
         mbar_wait(&full_bar[stage], (phase_bits >> stage) & 1u);
         phase_bits ^= (1u << stage);
-        const T* base = tiles + (size_t)stage * NV * TE;
-        const int len = tile_len(t);
+        T* base = tiles + (size_t)stage * stage_elems;                          // row 0: v
+        T* xrow = base + TE + (HALO ? PAD : 0);                                   // row 1: xc (FUSE)
+        const T* hist = base + (size_t)NRHS * TE + (HALO ? 2 * PAD : 0);
+        const int len = own.len(t, TE);
         const int64_t e0 = own.start(t, TE);
-        // one 16-byte unit (EPT elements) per thread: up to TE / EPT threads work on a tile, and the operand loads of 8 history
-        // columns are in flight per thread before their multiply-adds retire (the pass is bound by shared-memory latency otherwise)
-        for (int off = tid * EPT; off < len; off += kPThreads * EPT)
-        {
-            const int cnt = (len - off >= EPT) ? EPT : (len - off);
-            const Unit<T> uv = lds_unit<T>(base + off);
-            T r[EPT];
+        // d of one unit: the arithmetic every owner of an element uses
+        auto direction = [&](int off, T (&r)[EPT], Unit<T>& uv) {
+            uv = lds_unit<T>(base + off);
 #pragma unroll
             for (int k = 0; k < EPT; k++) r[k] = cv * uv.v[k];
-            const T* col = base + TE + off;
 #pragma unroll 8
             for (int j = 0; j < c; j++)                        // y terms newest -> oldest
             {
-                const Unit<T> uy = lds_unit<T>(col + (size_t)j * TE);
+                const Unit<T> uy = lds_unit<T>(hist + ((size_t)2 * sh.slots[j] + 1) * TE + off);
                 const T cy = s_coef[1 + j];
 #pragma unroll
                 for (int k = 0; k < EPT; k++) r[k] += cy * uy.v[k];
             }
-            col = base + (size_t)(c + 1) * TE + off;
 #pragma unroll 8
             for (int j = c - 1; j >= 0; j--)                   // s terms oldest -> newest
             {
-                const Unit<T> us = lds_unit<T>(col + (size_t)j * TE);
+                const Unit<T> us = lds_unit<T>(hist + (size_t)2 * sh.slots[j] * TE + off);
                 const T cs = s_coef[1 + c + j];
 #pragma unroll
                 for (int k = 0; k < EPT; k++) r[k] += cs * us.v[k];
             }
-            Unit<T> out;
-#pragma unroll
-            for (int k = 0; k < EPT; k++)
+        };
+        if constexpr (!HALO)
+        {
+            for (int off = tid * EPT; off < len; off += kPThreads * EPT)
             {
-                out.v[k] = r[k];
-                acc[0] += (k < cnt) ? uv.v[k] * r[k] : T(0);
+                const int cnt = (len - off >= EPT) ? EPT : (len - off);
+                T r[EPT];
+                Unit<T> uv;
+                direction(off, r, uv);
+                Unit<T> out;
+#pragma unroll
+                for (int k = 0; k < EPT; k++)
+                {
+                    out.v[k] = r[k];
+                    acc[0] += (k < cnt) ? uv.v[k] * r[k] : T(0);
+                }
+                const int64_t i0 = e0 + off;
+                st_unit<T>(res, i0, cnt, out);
+                if constexpr (FUSE)
+                {
+                    const Unit<T> ux = lds_unit<T>(xrow + off);
+                    T xv[4] = {T(0), T(0), T(0), T(0)}, gv[4];
+#pragma unroll
+                    for (int k = 0; k < EPT; k++) xv[k] = (k < cnt) ? ux.v[k] + T(1) * r[k] : T(0);
+                    acc[1] += obj.eval(i0, cnt, xv, T(0), T(0), gv);
+                    Unit<T> ug, uo;
+#pragma unroll
+                    for (int k = 0; k < EPT; k++)
+                    {
+                        acc[2] += (k < cnt) ? gv[k] * r[k] : T(0);
+                        acc[3] += (k < cnt) ? gv[k] * gv[k] : T(0);
+                        acc[4] += (k < cnt) ? xv[k] * xv[k] : T(0);
+                        ug.v[k] = gv[k];
+                        uo.v[k] = xv[k];
+                    }
+                    if (x1_out != nullptr)
+                    {
+                        st_unit<T>(x1_out, i0, cnt, uo);
+                        st_unit<T>(g1_out, i0, cnt, ug);
+                    }
+                }
             }
+        }
+        else
+        {
+            // ---- phase 1: d and x1 of the tile's units (one per thread: a tile has at most 512 units) ----
+            const int off = tid * EPT;
+            const bool mine = off < len;
             const int64_t i0 = e0 + off;
-            st_unit<T>(res, i0, cnt, out);
-            if constexpr (FUSE)
-            {
-                const Unit<T> ux = lds_unit<T>(base + (size_t)(2 * c + 1) * TE + off);
-                T xv[4] = {T(0), T(0), T(0), T(0)}, gv[4];
+            const int cnt = mine ? ((len - off >= EPT) ? EPT : (len - off)) : 0;
+            T r[EPT];
 #pragma unroll
-                for (int k = 0; k < EPT; k++) xv[k] = (k < cnt) ? ux.v[k] + T(1) * r[k] : T(0);
-                acc[1] += obj.eval(i0, cnt, xv, T(0), T(0), gv);
+            for (int k = 0; k < EPT; k++) r[k] = T(0);
+            if (mine)
+            {
+                Unit<T> uv;
+                direction(off, r, uv);
+                Unit<T> out;
+#pragma unroll
+                for (int k = 0; k < EPT; k++)
+                {
+                    out.v[k] = r[k];
+                    acc[0] += (k < cnt) ? uv.v[k] * r[k] : T(0);
+                }
+                st_unit<T>(res, i0, cnt, out);
+                const Unit<T> ux = lds_unit<T>(xrow + off);
+                Unit<T> u1;
+#pragma unroll
+                for (int k = 0; k < EPT; k++) u1.v[k] = (k < cnt) ? ux.v[k] + T(1) * r[k] : T(0);
+                *reinterpret_cast<float4*>(xrow + off) = *reinterpret_cast<const float4*>(u1.v);
+            }
+            // the element on either side of the tile: warp kPWarps-2 (left) and kPWarps-1 (right) gather its operands from global
+            // memory (through L2: other CTAs wrote them in earlier rounds), lane 0 repeats the owner's arithmetic
+            if (warp >= kPWarps - 2)
+            {
+                const bool left = warp == kPWarps - 2;
+                const int64_t im = left ? e0 - 1 : e0 + len;
+                if (im >= 0 && im < n)
+                {
+                    T* scratch = reinterpret_cast<T*>(sh.margin[left ? 0 : 1]);
+                    for (int q = lane; q < 2 * c + 2; q += 32)
+                    {
+                        T val;
+                        if (q == 0) val = __ldcg(static_cast<const T*>(sh.vecs[0]) + im);
+                        else if (q == 1) val = __ldcg(static_cast<const T*>(sh.vecs[1]) + im);
+                        else if (q < 2 + c) val = __ldcg(h.y_at(sh.slotid[q - 2], im));            // y of age q-2
+                        else val = __ldcg(h.s_at(sh.slotid[q - 2 - c], im));                        // s of age q-2-c
+                        scratch[q] = val;
+                    }
+                    __syncwarp();
+                    if (lane == 0)
+                    {
+                        T rm = cv * scratch[0];
+                        for (int j = 0; j < c; j++) rm += s_coef[1 + j] * scratch[2 + j];
+                        for (int j = c - 1; j >= 0; j--) rm += s_coef[1 + c + j] * scratch[2 + c + j];
+                        xrow[left ? -1 : len] = scratch[1] + T(1) * rm;
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- phase 2: the objective at x1 with its neighbours from shared memory ----
+            if (mine)
+            {
+                T xv[4] = {T(0), T(0), T(0), T(0)}, gv[4];
+                const Unit<T> u1 = lds_unit<T>(xrow + off);
+#pragma unroll
+                for (int k = 0; k < EPT; k++) xv[k] = u1.v[k];
+                const T xl = (i0 > 0) ? xrow[off - 1] : T(0);
+                const T right = (i0 + EPT < n) ? xrow[off + EPT] : T(0);
+                T xr = T(0);
+                if (EPT < 4) xv[EPT < 4 ? EPT : 3] = right; else xr = right;
+                acc[1] += obj.eval(i0, cnt, xv, xl, xr, gv);
                 Unit<T> ug, uo;
 #pragma unroll
                 for (int k = 0; k < EPT; k++)
@@ -782,7 +865,7 @@ __device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, int c,
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        if (next_tile < ntl) stage_tile(next_tile, stage);
+        if (next_tile < ntl) stage_one(next_tile, stage);
         next_tile++;
         stage = (stage + 1 == stages) ? 0 : stage + 1;
     }
@@ -796,154 +879,6 @@ __device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, int c,
         const double dacc[1] = {(double)acc[0]};
         block_sums<1>(dacc, sh, dst, G);
     }
-}
-
-// ---- COMBINE + first trial for neighbour-coupled objectives (one GPU) --------------------------------------------------------
-// Same staging as p_combine<FUSE>, but every tile is copied with one 16-byte granule of margin on either side and d, x1 = x + d are
-// also formed for the element just outside each end of the tile (redundantly, with the very arithmetic of the tile that owns it),
-// x1 goes back into the staged x slot, and after a barrier the objective takes x1_{i-1}, x1_{i+1} from shared memory.  A tile has
-// at most kPThreads - 2 units, so a thread keeps its unit's d across the barrier.
-template <class T, class OBJ>
-__device__ __forceinline__ void p_combine_halo(const OBJ& obj, const Own& own, int c, T* tiles, T* __restrict__ res, T* __restrict__ x1_out,
-                                               T* __restrict__ g1_out, PShared& sh, unsigned& phase_bits, double* dst, int G)
-{
-    constexpr int EPT = 16 / (int)sizeof(T);
-    constexpr int PAD = EPT;
-    const int tid = threadIdx.x;
-    const int NV = 2 * c + 2;
-    int TE = 1024;
-    while (TE > 32 && (size_t)2 * NV * (TE + 2 * PAD) * sizeof(T) > (size_t)kPStageBytes) TE >>= 1;
-    const int TS = TE + 2 * PAD;
-    int stages = (int)((size_t)kPStageBytes / ((size_t)NV * TS * sizeof(T)));
-    stages = stages > kPMaxStages ? kPMaxStages : stages;
-    const int64_t n = own.n;
-    const int64_t ntl = own.ntiles(TE);
-    const int64_t n_pad = (n + 31) & ~int64_t(31);
-    const T* s_coef = reinterpret_cast<const T*>(sh.coef);
-    uint64_t* full_bar = sh.full_bar;
-
-    auto stage_tile = [&](int64_t t, int stage) {
-        if (tid >= 32) return;
-        T* dstt = tiles + (size_t)stage * NV * TS;
-        const int64_t e0 = own.start(t, TE);
-        const int64_t lo = e0 >= PAD ? e0 - PAD : 0;
-        int64_t hi = e0 + ((own.len(t, TE) + 31) & ~31) + PAD;
-        if (hi > n_pad) hi = n_pad;
-        const unsigned bytes = (unsigned)(hi - lo) * (unsigned)sizeof(T);
-        const int shift = (int)(lo - (e0 - PAD));
-        if (tid == 0)
-        {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(&full_bar[stage], bytes * (unsigned)NV);
-        }
-        __syncwarp();
-        for (int q = tid; q < NV; q += 32) tma_load_1d(dstt + (size_t)q * TS + shift, static_cast<const T*>(sh.vecs[q]) + lo, bytes, &full_bar[stage]);
-    };
-
-    T acc[5] = {T(0), T(0), T(0), T(0), T(0)};
-    __syncthreads();
-    int64_t next_tile = 0;
-    for (int s = 0; s < stages; s++, next_tile++)
-        if (next_tile < ntl) stage_tile(next_tile, s);
-    const T cv = s_coef[0];
-    int stage = 0;
-    for (int64_t t = 0; t < ntl; t++)
-    {
-        mbar_wait(&full_bar[stage], (phase_bits >> stage) & 1u);
-        phase_bits ^= (1u << stage);
-        T* base = tiles + (size_t)stage * NV * TS + PAD;           // element 0 of the tile in vector 0
-        T* x1s = base + (size_t)(2 * c + 1) * TS;                  // the staged x, overwritten by x1
-        const int len = own.len(t, TE);
-        const int64_t e0 = own.start(t, TE);
-        const int nunits = (len + EPT - 1) / EPT;
-        // ---- phase 1: d and x1 for the tile's units and for the unit on either side ----
-        const int u = tid - 1;                                     // unit -1 and unit nunits are the margins
-        const int off = u * EPT;
-        const int64_t i0 = e0 + off;
-        const bool have = tid < nunits + 2 && i0 >= 0 && i0 < n;
-        const bool interior = have && u >= 0 && u < nunits;
-        const int cnt = have ? (int)((n - i0 >= EPT) ? EPT : (n - i0)) : 0;
-        T r[EPT];
-        Unit<T> uv;
-#pragma unroll
-        for (int k = 0; k < EPT; k++) { r[k] = T(0); uv.v[k] = T(0); }
-        if (have)
-        {
-            uv = lds_unit<T>(base + off);
-#pragma unroll
-            for (int k = 0; k < EPT; k++) r[k] = cv * uv.v[k];
-            const T* col = base + TS + off;
-#pragma unroll 8
-            for (int j = 0; j < c; j++)
-            {
-                const Unit<T> uy = lds_unit<T>(col + (size_t)j * TS);
-                const T cy = s_coef[1 + j];
-#pragma unroll
-                for (int k = 0; k < EPT; k++) r[k] += cy * uy.v[k];
-            }
-            col = base + (size_t)(c + 1) * TS + off;
-#pragma unroll 8
-            for (int j = c - 1; j >= 0; j--)
-            {
-                const Unit<T> us = lds_unit<T>(col + (size_t)j * TS);
-                const T cs = s_coef[1 + c + j];
-#pragma unroll
-                for (int k = 0; k < EPT; k++) r[k] += cs * us.v[k];
-            }
-            const Unit<T> ux = lds_unit<T>(x1s + off);
-            Unit<T> u1;
-#pragma unroll
-            for (int k = 0; k < EPT; k++) u1.v[k] = (k < cnt) ? ux.v[k] + T(1) * r[k] : T(0);
-            *reinterpret_cast<float4*>(x1s + off) = *reinterpret_cast<const float4*>(u1.v);
-            if (interior)
-            {
-                Unit<T> out;
-#pragma unroll
-                for (int k = 0; k < EPT; k++)
-                {
-                    out.v[k] = r[k];
-                    acc[0] += (k < cnt) ? uv.v[k] * r[k] : T(0);
-                }
-                st_unit<T>(res, i0, cnt, out);
-            }
-        }
-        __syncthreads();
-        // ---- phase 2: the objective at x1 with its neighbours from shared memory ----
-        if (interior)
-        {
-            T xv[4] = {T(0), T(0), T(0), T(0)}, gv[4];
-            const Unit<T> u1 = lds_unit<T>(x1s + off);
-#pragma unroll
-            for (int k = 0; k < EPT; k++) xv[k] = u1.v[k];
-            const T xl = (i0 > 0) ? x1s[off - 1] : T(0);
-            const T right = (i0 + EPT < n) ? x1s[off + EPT] : T(0);
-            T xr = T(0);
-            if (EPT < 4) xv[EPT < 4 ? EPT : 3] = right; else xr = right;
-            acc[1] += obj.eval(i0, cnt, xv, xl, xr, gv);
-            Unit<T> ug, uo;
-#pragma unroll
-            for (int k = 0; k < EPT; k++)
-            {
-                acc[2] += (k < cnt) ? gv[k] * r[k] : T(0);
-                acc[3] += (k < cnt) ? gv[k] * gv[k] : T(0);
-                acc[4] += (k < cnt) ? xv[k] * xv[k] : T(0);
-                ug.v[k] = gv[k];
-                uo.v[k] = xv[k];
-            }
-            if (x1_out != nullptr)
-            {
-                st_unit<T>(x1_out, i0, cnt, uo);
-                st_unit<T>(g1_out, i0, cnt, ug);
-            }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (next_tile < ntl) stage_tile(next_tile, stage);
-        next_tile++;
-        stage = (stage + 1 == stages) ? 0 : stage + 1;
-    }
-    const double dacc[5] = {(double)acc[0], (double)acc[1], (double)acc[2], (double)acc[3], (double)acc[4]};
-    block_sums<5>(dacc, sh, dst, G);
 }
 
 // ---- waits with a watchdog ----------------------------------------------------------------------------------------------------
@@ -1347,7 +1282,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
     T* tiles = reinterpret_cast<T*>(p_smem);      // the staging ring of the dots / combination passes
     __shared__ PShared sh;
     const int tid = threadIdx.x, G = gridDim.x, cta = blockIdx.x;
-    const Own own(a.n, G, cta);
+    const Own own(a.n, G, cta, a.grain);
     if (tid == 0)
     {
         for (int s = 0; s < kPMaxStages; s++) mbar_init(&sh.full_bar[s], 1);
@@ -1463,20 +1398,23 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
             {
                 const bool form = op == POP_DOTS_FORM;
                 PDots<T> d;
-                d.n = a.n; d.ld = a.ld; d.v = vg; d.S = st->S; d.Y = st->Y;
-                d.c = c_round;
-                const int M = st->M;
+                d.n = a.n; d.h = st->hist; d.c = c_round;
+                d.end = head;                                   // the old columns: the slots below the free slot `head`
+                d.cnt_old = form ? c_round - 1 : c_round;
                 d.new_slot = form ? head : -1;
+                const int units = d.h.BT() / (16 / (int)sizeof(T));
                 int split = 8;
-                const int dte = own.BS < kGramTE ? own.BS : kGramTE;
-                while (split > 1 && (d.c * split > kGramMaxWarps || dte / split < 256)) split >>= 1;
+                while (split > 1 && (d.c * split > kGramMaxWarps || units / split < 32)) split >>= 1;
                 d.split = split;
                 d.cols_per_round = d.c < kGramMaxWarps / split ? d.c : kGramMaxWarps / split;
-                d.fx = vx; d.fxp = vxp; d.fgp = vgp;
-                d.s_out = st->S + (int64_t)head * a.ld;
-                d.y_out = st->Y + (int64_t)head * a.ld;
-                __syncthreads();   // sh.slots may still be read by the previous problem's pass
-                if (tid < d.c) sh.slots[tid] = (unsigned char)(form ? (tid == 0 ? head : slot_by_age(head, M, tid - 1)) : slot_by_age(head, M, tid));
+                __syncthreads();   // sh.slots / sh.vecs may still be read by the previous problem's pass
+                {
+                    const SlotRuns runs(d.end, d.cnt_old, d.h.M);
+                    // age j (FORM: j >= 1) -> packed row of its slot in the staged block
+                    if (tid < d.c && !(form && tid == 0))
+                        sh.slots[tid] = (unsigned char)runs.row_of(slot_by_age(head, d.h.M, form ? tid - 1 : tid));
+                    if (tid == 0) { sh.vecs[0] = vg; sh.vecs[1] = vx; sh.vecs[2] = vgp; sh.vecs[3] = vxp; }
+                }
                 if (form) p_dots<T, ROUNDS, true>(d, own, tiles, sh, phase_bits, dst, G);
                 else p_dots<T, ROUNDS, false>(d, own, tiles, sh, phase_bits, dst, G);
                 break;
@@ -1486,7 +1424,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
             {
                 GramSolveArgs<T> g;
                 g.c = c_round;
-                g.M = st->M; g.new_slot = pending; g.with_v = 1; g.a = T(-1);
+                g.M = st->hist.M; g.new_slot = pending; g.with_v = 1; g.a = T(-1);
                 g.raw = st->raw;
                 const int in = gram_cur, out = (g.new_slot >= 0) ? 1 - in : in;
                 g.SY_in = st->SY[in]; g.YY_in = st->YY[in]; g.SS_in = st->SS[in];
@@ -1496,25 +1434,26 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
                 for (int age = 0; age < g.c; age++) g.slots[age] = (unsigned char)slot_by_age(head, g.M, age);
                 __syncthreads();   // the tile area / tables may still be in use by the previous problem's pass
                 gram_solve_in_smem<T>(g, tiles, cta == 0);
-                // coefficients out of the tile area (the staging ring is about to overwrite it), operand table in coefficient order
+                // coefficients out of the tile area (the staging ring is about to overwrite it); per age: packed row and ring slot
                 const bool fuse = op == POP_COMBINE_TRIAL;
                 {
                     const T* s_coef = tiles + 2 * g.c * g.c;
                     T* keep = reinterpret_cast<T*>(sh.coef);
                     for (int q = tid; q < 2 * g.c + 1; q += kPThreads) keep[q] = s_coef[q];
+                    const SlotRuns runs(head, g.c, g.M);
                     for (int j = tid; j < g.c; j += kPThreads)
                     {
-                        sh.vecs[1 + j] = st->Y + (int64_t)g.slots[j] * a.ld;
-                        sh.vecs[1 + g.c + j] = st->S + (int64_t)g.slots[j] * a.ld;
+                        sh.slots[j] = (unsigned char)runs.row_of(g.slots[j]);
+                        sh.slotid[j] = g.slots[j];
                     }
-                    if (tid == 0) { sh.vecs[0] = vg; sh.vecs[2 * g.c + 1] = vx; }
+                    if (tid == 0) { sh.vecs[0] = vg; sh.vecs[1] = vx; }
                 }
                 if (fuse)
                 {
-                    if constexpr (OBJ::kHalo) p_combine_halo<T, OBJ>(obj, own, g.c, tiles, vd, store_first ? vxp : nullptr, store_first ? vgp : nullptr, sh, phase_bits, dst, G);
-                    else p_combine<T, OBJ, true>(obj, own, g.c, tiles, vd, store_first ? vxp : nullptr, store_first ? vgp : nullptr, sh, phase_bits, dst, G);
+                    if constexpr (OBJ::kHalo) p_combine<T, OBJ, true, true>(obj, own, st->hist, g.c, head, tiles, vd, store_first ? vxp : nullptr, store_first ? vgp : nullptr, sh, phase_bits, dst, G);
+                    else p_combine<T, OBJ, true, false>(obj, own, st->hist, g.c, head, tiles, vd, store_first ? vxp : nullptr, store_first ? vgp : nullptr, sh, phase_bits, dst, G);
                 }
-                else p_combine<T, OBJ, false>(obj, own, g.c, tiles, vd, nullptr, nullptr, sh, phase_bits, dst, G);
+                else p_combine<T, OBJ, false, false>(obj, own, st->hist, g.c, head, tiles, vd, nullptr, nullptr, sh, phase_bits, dst, G);
                 break;
             }
             default: break;

@@ -7,7 +7,15 @@ struct lbfgs_b200_solver
     lbfgs_b200_ctx* ctx = nullptr;
     int64_t n = 0;
     int m = 0, elem = 8, B = 1;
-    std::vector<lbfgs_b200_hist*> hist;   // one S/Y ring per problem
+    // the S/Y rings, tiled: H[problem][block][slot][S|Y][BT] (lb::PHist); small per-problem arrays in one slab each
+    void* d_hist = nullptr;
+    int bt_log = 9, M = 0;
+    size_t hist_elems = 0;                // elements of one problem's tiled ring
+    void* d_small = nullptr;              // [B][ ys M | alpha M | theta 1 (padded to 4) | SY,YY,SS x2: 6 M^2 ]
+    size_t small_elems = 0;
+    std::vector<int> ring_head, ring_ncorr, ring_gram_cur;   // ring state after the last solve (for the export below)
+    std::vector<lbfgs_b200_hist*> exported;                   // column-major copies made on request (lbfgs_b200_solver_history_of)
+    std::vector<char> export_fresh;
     void* vec_slab = nullptr;             // [B][7][vec_elems] : x, xp, g, gp, drt, x_lo, g_lo
     size_t vec_elems = 0;                 // n rounded up to a whole number of 256-byte lines
     void* d_state = nullptr;              // PState<T>[B]
@@ -72,9 +80,7 @@ static lbfgs_b200_status solver_minimize(lbfgs_b200_solver* s, int objective, co
     }
     else if (coupled) index_offset = 0;
     if (ctx->x_active) REQUIRE(ctx, (size_t)B * (s->pstride + 4) <= (size_t)kXMaxVals, "batch of %d problems with m = %d exceeds the exchange buffer", B, s->m);
-    const int split_m = [&] { int sp = 8; while (sp > 1 && s->m * sp > kGramMaxWarps) sp >>= 1; return sp; }();
-    const int per_round = s->m < kGramMaxWarps / split_m ? s->m : kGramMaxWarps / split_m;
-    const int rounds = (s->m + per_round - 1) / per_round;
+    const int rounds = (s->m + kGramMaxWarps - 1) / kGramMaxWarps;   // column pairs per round of the dots pass: at most one per warp
     void* kernel = persist_kernel_for<T>(objective, rounds);
     if (!kernel) return fail(ctx, LBFGS_B200_ERR_INVALID, "unknown objective id %d", objective);
 
@@ -92,20 +98,21 @@ static lbfgs_b200_status solver_minimize(lbfgs_b200_solver* s, int objective, co
     const size_t vb = sizeof(T) * (size_t)s->n;
     for (int b = 0; b < B; b++)
     {
-        lbfgs_b200_hist* h = s->hist[b];
-        if (auto st = lbfgs_b200_hist_reset(h)) return st;
         PState<T>& p = hs[b];
         T* base = static_cast<T*>(s->vec_slab) + (size_t)b * 7 * s->vec_elems;
         p.x = base; p.xp = base + s->vec_elems; p.g = base + 2 * s->vec_elems; p.gp = base + 3 * s->vec_elems;
         p.drt = base + 4 * s->vec_elems; p.x_lo = base + 5 * s->vec_elems; p.g_lo = base + 6 * s->vec_elems;
-        p.S = static_cast<T*>(h->S); p.Y = static_cast<T*>(h->Y); p.ys = static_cast<T*>(h->ys);
-        p.alpha = static_cast<T*>(h->alpha); p.theta = static_cast<T*>(h->theta);
-        for (int k = 0; k < 2; k++) { p.SY[k] = static_cast<T*>(h->SY[k]); p.YY[k] = static_cast<T*>(h->YY[k]); p.SS[k] = static_cast<T*>(h->SS[k]); }
+        p.hist.H = static_cast<T*>(s->d_hist) + (size_t)b * s->hist_elems;
+        p.hist.bt_log = s->bt_log; p.hist.M = s->M; p.hist.bstride = (int64_t)s->M * 2 * ((int64_t)1 << s->bt_log);
+        T* small = static_cast<T*>(s->d_small) + (size_t)b * s->small_elems;
+        const size_t mm = (size_t)s->M * s->M;
+        p.ys = small; p.alpha = small + s->M; p.theta = small + 2 * s->M;
+        for (int k = 0; k < 2; k++) { p.SY[k] = small + 2 * s->M + 4 + (3 * k + 0) * mm; p.YY[k] = small + 2 * s->M + 4 + (3 * k + 1) * mm; p.SS[k] = small + 2 * s->M + 4 + (3 * k + 2) * mm; }
         p.data0 = data0 ? data0 + (size_t)b * ldd : nullptr;
         p.data1 = data1 ? data1 + (size_t)b * ldd : nullptr;
         p.raw = s->d_raw + (size_t)b * s->pstride;
         p.halo = s->d_halo + (size_t)b * kHaloDoubles;
-        p.head = 0; p.ncorr = 0; p.M = h->M; p.m = h->m; p.gram_cur = h->gram_cur; p.pending = -1;
+        p.head = 0; p.ncorr = 0; p.M = s->M; p.m = s->m; p.gram_cur = 0; p.pending = -1;
         p.op = POP_FIRST; p.c_round = 0;
         p.epsilon = (T)prm->epsilon; p.epsilon_rel = (T)prm->epsilon_rel; p.delta = (T)prm->delta; p.max_step = (T)prm->max_step;
         p.eps_gate = std::numeric_limits<T>::epsilon();
@@ -130,6 +137,12 @@ static lbfgs_b200_status solver_minimize(lbfgs_b200_solver* s, int objective, co
         hr[b].x = p.x; hr[b].xp = p.xp; hr[b].g = p.g; hr[b].gp = p.gp; hr[b].drt = p.drt;
         hr[b].step = T(0); hr[b].op = p.op; hr[b].c_round = 0; hr[b].head = 0; hr[b].pending = -1; hr[b].gram_cur = p.gram_cur; hr[b].store_first = p.first_store;
     }
+    // BFGSMat::reset (BFGSMat.h:61-78): no pairs, theta = 1, Gram matrices cleared
+    CU(ctx, cudaMemsetAsync(s->d_small, 0, sizeof(T) * s->small_elems * (size_t)B, ctx->stream));
+    {
+        static const T one = T(1);
+        for (int b = 0; b < B; b++) CU(ctx, cudaMemcpyAsync(hs[b].theta, &one, sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    }
     CU(ctx, cudaMemcpyAsync(s->d_state, hs, sizeof(PState<T>) * (size_t)B, cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaMemcpyAsync(s->d_rounds, hr, sizeof(PRound<T>) * (size_t)B, cudaMemcpyHostToDevice, ctx->stream));
     PCtl hc{};
@@ -139,7 +152,7 @@ static lbfgs_b200_status solver_minimize(lbfgs_b200_solver* s, int objective, co
     CU(ctx, cudaMemsetAsync(s->d_halo, 0, sizeof(double) * kHaloDoubles * (size_t)B, ctx->stream));
 
     // ---- one cooperative launch: one CTA per SM (fewer when the vector has fewer tiles than SMs) ----
-    const int64_t units = (s->n + kPGrain - 1) / kPGrain;
+    const int64_t units = (s->n + ((int64_t)1 << s->bt_log) - 1) >> s->bt_log;
     const int grid = (int)(units < ctx->sm_count ? (units < 1 ? 1 : units) : ctx->sm_count);
     const size_t smem = (size_t)kPStageBytes;
     CU(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -148,7 +161,7 @@ static lbfgs_b200_status solver_minimize(lbfgs_b200_solver* s, int objective, co
     REQUIRE(ctx, per_sm >= 1, "the persistent solve kernel does not fit on an SM of this device");
     PArgs<T> a{};
     a.probs = static_cast<PState<T>*>(s->d_state); a.rounds = static_cast<PRound<T>*>(s->d_rounds); a.B = B; a.ctl = s->d_ctl; a.partials = s->d_partials; a.pstride = s->pstride;
-    a.n = s->n; a.ld = s->hist[0]->ld; a.xc = ctx->x_active ? ctx->x_comm : nullptr;
+    a.n = s->n; a.grain = 1 << s->bt_log; a.xc = ctx->x_active ? ctx->x_comm : nullptr;
     a.index_offset = index_offset; a.n_global = n_global;
     void* kargs[] = {&a};
     CU(ctx, cudaEventRecord(s->ev0, ctx->stream));
@@ -170,8 +183,8 @@ static lbfgs_b200_status solver_minimize(lbfgs_b200_solver* s, int objective, co
         CU(ctx, cudaMemcpyAsync(x_inout + (size_t)b * ldx, p.x, vb, cudaMemcpyDeviceToDevice, ctx->stream));
         s->final_g[b] = p.g;
         s->final_x[b] = p.x;
-        lbfgs_b200_hist* h = s->hist[b];
-        h->head = p.head; h->ncorr = p.ncorr; h->gram_cur = p.gram_cur; h->pending = -1;
+        s->ring_head[b] = p.head; s->ring_ncorr[b] = p.ncorr; s->ring_gram_cur[b] = p.gram_cur;
+        s->export_fresh[b] = 0;
         outs[b].status = p.status;
         outs[b].niter = p.niter;
         outs[b].nfev = p.nfev;
@@ -188,6 +201,47 @@ static lbfgs_b200_status solver_minimize(lbfgs_b200_solver* s, int objective, co
     return LBFGS_B200_OK;
 }
 
+// The ring of problem b as an ordinary (column-major) lbfgs_b200_hist, for final_approx_hessian() and inspection: made on request,
+// refreshed after every solve.  nullptr on failure (the context holds the message).
+template <class T> __global__ void k_untile_history(lb::PHist<T> h, int64_t n, int64_t ld, T* __restrict__ S, T* __restrict__ Y)
+{
+    const int slot = blockIdx.y;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    {
+        S[(int64_t)slot * ld + i] = *h.s_at(slot, i);
+        Y[(int64_t)slot * ld + i] = *h.y_at(slot, i);
+    }
+}
+#if defined(LBFGS_B200_PERSIST_F64)
+template <class T> static lbfgs_b200_hist* export_history(lbfgs_b200_solver* s, int b)
+{
+    lbfgs_b200_ctx* ctx = s->ctx;
+    lbfgs_b200_hist*& h = s->exported[(size_t)b];
+    if (h && s->export_fresh[(size_t)b]) return h;
+    if (!h && lbfgs_b200_hist_create(ctx, &h, s->n, s->m, s->elem) != LBFGS_B200_OK) return nullptr;
+    lb::PHist<T> ph;
+    ph.H = static_cast<T*>(s->d_hist) + (size_t)b * s->hist_elems;
+    ph.bt_log = s->bt_log; ph.M = s->M; ph.bstride = (int64_t)s->M * 2 * ((int64_t)1 << s->bt_log);
+    const dim3 grid((unsigned)std::min<int64_t>((s->n + 255) / 256, 4 * ctx->sm_count), (unsigned)s->M);
+    k_untile_history<T><<<grid, 256, 0, ctx->stream>>>(ph, s->n, h->ld, static_cast<T*>(h->S), static_cast<T*>(h->Y));
+    const T* small = static_cast<const T*>(s->d_small) + (size_t)b * s->small_elems;
+    const size_t mm = (size_t)s->M * s->M;
+    cudaMemcpyAsync(h->ys, small, sizeof(T) * s->M, cudaMemcpyDeviceToDevice, ctx->stream);
+    cudaMemcpyAsync(h->alpha, small + s->M, sizeof(T) * s->M, cudaMemcpyDeviceToDevice, ctx->stream);
+    cudaMemcpyAsync(h->theta, small + 2 * s->M, sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream);
+    for (int k = 0; k < 2; k++)
+    {
+        cudaMemcpyAsync(h->SY[k], small + 2 * s->M + 4 + (3 * k + 0) * mm, sizeof(T) * mm, cudaMemcpyDeviceToDevice, ctx->stream);
+        cudaMemcpyAsync(h->YY[k], small + 2 * s->M + 4 + (3 * k + 1) * mm, sizeof(T) * mm, cudaMemcpyDeviceToDevice, ctx->stream);
+        cudaMemcpyAsync(h->SS[k], small + 2 * s->M + 4 + (3 * k + 2) * mm, sizeof(T) * mm, cudaMemcpyDeviceToDevice, ctx->stream);
+    }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) { fail(ctx, LBFGS_B200_ERR_CUDA, "exporting the solver's history failed"); return nullptr; }
+    h->head = s->ring_head[(size_t)b]; h->ncorr = s->ring_ncorr[(size_t)b]; h->gram_cur = s->ring_gram_cur[(size_t)b]; h->pending = -1;
+    s->export_fresh[(size_t)b] = 1;
+    return h;
+}
+#endif
+
 extern "C" {
 
 #ifdef LBFGS_B200_PERSIST_F64
@@ -203,19 +257,26 @@ lbfgs_b200_status lbfgs_b200_solver_create_batch(lbfgs_b200_ctx* ctx, int64_t n,
     s->ctx = ctx; s->n = n; s->m = m; s->elem = elem_bytes; s->B = batch;
     s->final_g.assign((size_t)batch, nullptr);
     s->final_x.assign((size_t)batch, nullptr);
-    lbfgs_b200_status st = LBFGS_B200_OK;
-    for (int b = 0; b < batch && st == LBFGS_B200_OK; b++)
+    s->M = m + 1;
+    // block length of the tiled history: the largest power of two for which two stages of 2m+4 rows fit the kernel's staging ring
     {
-        lbfgs_b200_hist* h = nullptr;
-        st = lbfgs_b200_hist_create(ctx, &h, n, m, elem_bytes);
-        if (st == LBFGS_B200_OK) s->hist.push_back(h);
+        int bt = 1024;
+        while (bt > 32 && (size_t)2 * (2 * m + 4) * bt * elem_bytes > (size_t)lb::kPStageBytes) bt >>= 1;
+        s->bt_log = 0;
+        while ((1 << s->bt_log) < bt) s->bt_log++;
     }
-    if (st) { lbfgs_b200_solver_destroy(s); return st; }
+    const int64_t nblocks = (n + ((int64_t)1 << s->bt_log) - 1) >> s->bt_log;
+    s->hist_elems = (size_t)nblocks * s->M * 2 * ((size_t)1 << s->bt_log);
+    s->small_elems = (size_t)2 * s->M + 4 + 6 * (size_t)s->M * s->M;
+    s->ring_head.assign((size_t)batch, 0); s->ring_ncorr.assign((size_t)batch, 0); s->ring_gram_cur.assign((size_t)batch, 0);
+    s->exported.assign((size_t)batch, nullptr); s->export_fresh.assign((size_t)batch, 0);
     cudaError_t e = cudaSuccess;
     s->vec_elems = (((size_t)n * elem_bytes + 255) & ~size_t(255)) / elem_bytes;
     s->pstride = ((m * lb::kGramVals > 8 ? m * lb::kGramVals : 8) + 7) & ~7;
     const size_t state_bytes = (elem_bytes == 8 ? sizeof(lb::PState<double>) : sizeof(lb::PState<float>)) * (size_t)batch;
     if (e == cudaSuccess) e = cudaMalloc(&s->vec_slab, (size_t)batch * 7 * s->vec_elems * elem_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_hist, (size_t)batch * s->hist_elems * elem_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_small, (size_t)batch * s->small_elems * elem_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_state, state_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_rounds, (elem_bytes == 8 ? sizeof(lb::PRound<double>) : sizeof(lb::PRound<float>)) * (size_t)batch);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_ctl, sizeof(lb::PCtl));
@@ -252,7 +313,9 @@ void lbfgs_b200_solver_destroy(lbfgs_b200_solver* s)
     cudaFree(s->d_trace);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
-    for (lbfgs_b200_hist* h : s->hist) lbfgs_b200_hist_destroy(h);
+    cudaFree(s->d_hist);
+    cudaFree(s->d_small);
+    for (lbfgs_b200_hist* h : s->exported) lbfgs_b200_hist_destroy(h);
     delete s;
 }
 
@@ -277,8 +340,13 @@ lbfgs_b200_status lbfgs_b200_solver_profile(const lbfgs_b200_solver* s, double* 
 }
 const void* lbfgs_b200_solver_final_grad(const lbfgs_b200_solver* s) { return s ? s->final_g[0] : nullptr; }
 const void* lbfgs_b200_solver_final_grad_of(const lbfgs_b200_solver* s, int b) { return (s && b >= 0 && b < s->B) ? s->final_g[(size_t)b] : nullptr; }
-lbfgs_b200_hist* lbfgs_b200_solver_history(lbfgs_b200_solver* s) { return s ? s->hist[0] : nullptr; }
-lbfgs_b200_hist* lbfgs_b200_solver_history_of(lbfgs_b200_solver* s, int b) { return (s && b >= 0 && b < s->B) ? s->hist[(size_t)b] : nullptr; }
+lbfgs_b200_hist* lbfgs_b200_solver_history_of(lbfgs_b200_solver* s, int b)
+{
+    if (!s || b < 0 || b >= s->B) return nullptr;
+    if (s->elem == 8) return export_history<double>(s, b);
+    return export_history<float>(s, b);
+}
+lbfgs_b200_hist* lbfgs_b200_solver_history(lbfgs_b200_solver* s) { return lbfgs_b200_solver_history_of(s, 0); }
 
 lbfgs_b200_status lbfgs_b200_solver_minimize_f64(lbfgs_b200_solver* s, int objective, const double* data0, const double* data1,
                                                  const lbfgs_b200_param* prm, int line_search, double* x_inout, double* trace_host,

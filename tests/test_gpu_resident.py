@@ -117,3 +117,19 @@ def test_resident_solve_is_bitwise_repeatable():
     b = resident(lb.LBFGSParam(m=10), "MoreThuente").minimize(lb.OBJ_ROSENBROCK_PAIRED, x0)
     assert (a["niter"], a["nfev"], a["fx"]) == (b["niter"], b["nfev"], b["fx"])
     assert np.array_equal(a["x"], b["x"]) and np.array_equal(a["trace"], b["trace"])
+
+
+def test_final_approx_hessian_after_resident_solve():
+    """final_approx_hessian() / final_approx_inverse_hessian() (reference LBFGS.h:192-197) must describe the solve that just ran, also
+    when that solve was device-resident (its S/Y ring lives in the solver, tiled; the front fetches a column-major copy on demand)."""
+    x0 = np.zeros(10)
+    it_r, x_r, B_r, H_r = lb.solve_dense(lb.OBJ_ROSENBROCK_PAIRED, x0, lb.LBFGSParam(), "NocedalWright", resident=True)
+    it_h, x_h, B_h, H_h = lb.solve_dense(lb.OBJ_ROSENBROCK_PAIRED, x0, lb.LBFGSParam(), "NocedalWright", resident=False)
+    assert it_r == it_h and np.max(np.abs(x_r - x_h)) <= 1e-8
+    scale = np.max(np.abs(B_h))
+    assert np.max(np.abs(B_r - B_h)) <= 1e-6 * scale and np.max(np.abs(H_r - H_h)) <= 1e-6 * np.max(np.abs(H_h))
+    assert np.max(np.abs(B_r - B_r.T)) <= 1e-9 * scale                      # symmetric
+    assert np.max(np.abs(B_r @ H_r - np.eye(10))) <= 1e-6                   # H = inv(B)
+    # a second solve on the same solver type from another start must refresh the matrices
+    it2, _, B2, _ = lb.solve_dense(lb.OBJ_ROSENBROCK_PAIRED, np.full(10, 0.5), lb.LBFGSParam(), "NocedalWright", resident=True)
+    assert it2 > 1 and np.max(np.abs(B2 - B_r)) > 0
