@@ -247,7 +247,7 @@ static lbfgs_b200_status do_box_cauchy_sweep(lbfgs_b200_box* b, const T* g, cons
     a.block_sums = static_cast<T*>(b->block_sums); a.best = b->best; a.out = d_out;
     const int64_t nblocks = (nord + kScanBlock - 1) / kScanBlock;
     if (auto st = sweep_launch<T>(b, a, 0, 0, nblocks)) return st;
-    k_sweep_scan_blocks<T><<<1, 128, 0, ctx->stream>>>(static_cast<T*>(b->block_sums), nblocks, 4 * c + 1);
+    k_sweep_scan_blocks<T><<<1, 1024, 0, ctx->stream>>>(static_cast<T*>(b->block_sums), nblocks, 4 * c + 1);
     if (auto st = post_launch(ctx, "k_sweep_scan_blocks")) return st;
     if (auto st = sweep_launch<T>(b, a, 1, 0, nblocks)) return st;
     long long best = 0;

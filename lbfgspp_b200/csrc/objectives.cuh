@@ -74,6 +74,7 @@ template <class T> struct RosenbrockChained
 {
     static constexpr bool kHalo = true;
     static constexpr int kDataVectors = 0;
+    __device__ __forceinline__ RosenbrockChained staged(const T*, const T*, int64_t) const { return *this; }
     int64_t n;             // local length
     int64_t gofs, n_glob;  // global index of local element 0, global length (gofs = 0, n_glob = n unsharded)
     const double* halo;
@@ -114,6 +115,14 @@ template <class T> struct QuadTridiag
     const T* rhs;   // b
     int64_t gofs, n_glob;
     const double* halo;
+    // the same objective reading its two data vectors from a staged tile: `d_tile[0]` / `b_tile[0]` hold element `e0`
+    __device__ __forceinline__ QuadTridiag staged(const T* d_tile, const T* b_tile, int64_t e0) const
+    {
+        QuadTridiag o = *this;
+        o.diag = d_tile - e0;
+        o.rhs = b_tile - e0;
+        return o;
+    }
     __device__ __forceinline__ T eval(int64_t i0, int cnt, const T (&x)[4], T xl, T xr, T (&g)[4]) const
     {
         T f = T(0);

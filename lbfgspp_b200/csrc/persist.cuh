@@ -38,7 +38,6 @@ namespace lb {
 constexpr int kMaxPast = 64;
 constexpr int kPThreads = kGramMaxThreads;   // 768: one CTA per SM
 constexpr int kPWarps = kPThreads / 32;
-constexpr int kPGrain = 256;                 // chunk boundaries are multiples of this many elements
 constexpr int kPStageBytes = kGramStages * 4 * kGramTE * 8;   // dynamic shared memory of the kernel: 196608 bytes
 constexpr int kPMaxStages = 4;
 constexpr int kPCache = 4;                   // problems whose leader-side state is kept in shared memory
@@ -219,7 +218,8 @@ struct PShared
     const void* vecs[2 * kMaxM + 2];        // combination pass: the staged vectors {g, (x), y_0.., s_0..} in coefficient order
     unsigned char slots[kMaxM];             // by age: packed row of the column in the staged history block
     unsigned char slotid[kMaxM];            // by age: physical ring slot
-    double margin[2][2 * kMaxM + 2];        // neighbour-coupled combination pass: operands of the element on either side of a tile
+    double margin[2][2 * kMaxM + 2];        // neighbour-coupled combination pass: products of the element on either side of a tile
+    double carry[2];                        // ... and x1 of the last element of the previous tile (two slots, alternating)
     unsigned char ops[4096];                // this round's op of every problem
 };
 
@@ -269,12 +269,6 @@ template <int NV> __device__ __forceinline__ void block_sums(const double (&acc)
         for (int w = 0; w < kPWarps; w++) t += sh.red[w][threadIdx.x];
         dst[(size_t)threadIdx.x * G] = t;
     }
-}
-
-template <class T> __device__ __forceinline__ void mask_pack(Pack<T>& p, int cnt)
-{
-#pragma unroll
-    for (int k = 0; k < 4; k++) p.v[k] = (k < cnt) ? p.v[k] : T(0);
 }
 
 // ---- FIRST / TRIAL -------------------------------------------------------------------------------------------------------------
@@ -350,7 +344,9 @@ __device__ __forceinline__ void p_trial_halo(const OBJ& obj, const Own& own, con
                                              T* __restrict__ x, T* __restrict__ g, T* __restrict__ dout, T* tiles, PShared& sh, unsigned& phase_bits,
                                              double* dst, int G)
 {
-    constexpr int NVEC = (MODE == 1) ? 2 : 1;
+    constexpr int NIN = (MODE == 1) ? 2 : 1;                         // xp, d  /  x
+    constexpr int DV = OBJ::kDataVectors;                            // the objective's data vectors are staged with them
+    constexpr int NVEC = NIN + DV;
     constexpr int PAD = 16 / (int)sizeof(T);                         // margin in elements = one 16-byte granule
     constexpr int TS = kTrialTE + 2 * PAD;                           // staged elements per vector per tile
     constexpr int STAGES_MAX = kPStageBytes / (NVEC * TS * (int)sizeof(T));
@@ -375,6 +371,11 @@ __device__ __forceinline__ void p_trial_halo(const OBJ& obj, const Own& own, con
         mbar_expect_tx(&full_bar[stage], bytes * NVEC);
         tma_load_1d(dstt + shift, in0 + lo, bytes, &full_bar[stage]);
         if (MODE == 1) tma_load_1d(dstt + TS + shift, d + lo, bytes, &full_bar[stage]);
+        if constexpr (DV == 2)
+        {
+            tma_load_1d(dstt + (size_t)NIN * TS + shift, obj.diag + lo, bytes, &full_bar[stage]);
+            tma_load_1d(dstt + (size_t)(NIN + 1) * TS + shift, obj.rhs + lo, bytes, &full_bar[stage]);
+        }
     };
 
     T acc[4] = {T(0), T(0), T(0), T(0)};
@@ -417,7 +418,8 @@ __device__ __forceinline__ void p_trial_halo(const OBJ& obj, const Own& own, con
                 if (i0 + 4 < n) xr = ta[off + 4];
                 else if (obj.halo && i0 + 4 == n && obj.gofs + n < obj.n_glob) xr = T(ldv(obj.halo + kHaloRightA));
             }
-            acc[0] += obj.eval(i0, cnt, xv, xl, xr, gv);
+            if constexpr (DV == 2) acc[0] += obj.staged(ta + (size_t)NIN * TS, ta + (size_t)(NIN + 1) * TS, e0).eval(i0, cnt, xv, xl, xr, gv);
+            else acc[0] += obj.eval(i0, cnt, xv, xl, xr, gv);
             Pack<T> pg, po;
 #pragma unroll
             for (int k = 0; k < 4; k++)
@@ -660,7 +662,8 @@ __device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, const 
                                           T* __restrict__ x1_out, T* __restrict__ g1_out, PShared& sh, unsigned& phase_bits, double* dst, int G)
 {
     constexpr int EPT = 16 / (int)sizeof(T);
-    constexpr int NRHS = FUSE ? 2 : 1;                            // v (, xc)
+    constexpr int DV = HALO ? OBJ::kDataVectors : 0;              // HALO: the objective's data vectors ride in the stage as well
+    constexpr int NRHS = (FUSE ? 2 : 1) + DV;                     // v (, xc) (, data0, data1)
     constexpr int PAD = EPT;                                      // HALO: room for x1 of the neighbouring element on either side of the x row
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int TE = h.BT();
@@ -686,18 +689,20 @@ __device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, const 
         if (tid == 0)
         {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(&full_bar[s], rbytes * 2u + abytes + bbytes);
+            mbar_expect_tx(&full_bar[s], rbytes * (unsigned)NRHS + abytes + bbytes);
         }
         __syncwarp();
         const T* blk = h.H + (e0 >> h.bt_log) * h.bstride;
-        T* hist = dstt + 2 * (size_t)TE + 2 * PAD;
+        T* hist = dstt + (size_t)NRHS * TE + 2 * PAD;
         if (tid == 0) tma_load_1d(dstt, static_cast<const T*>(sh.vecs[0]) + e0, rbytes, &full_bar[s]);
         else if (tid == 1) tma_load_1d(dstt + TE + PAD, static_cast<const T*>(sh.vecs[1]) + e0, rbytes, &full_bar[s]);
         else if (tid == 2 && abytes) tma_load_1d(hist, blk + (size_t)runs.a0 * 2 * TE, abytes, &full_bar[s]);
         else if (tid == 3 && bbytes) tma_load_1d(hist + (size_t)2 * (runs.a1 - runs.a0) * TE, blk + (size_t)runs.b0 * 2 * TE, bbytes, &full_bar[s]);
+        else if (tid >= 4 && tid < 4 + DV) tma_load_1d(dstt + (size_t)(tid - 2) * TE + 2 * PAD, static_cast<const T*>(sh.vecs[tid - 2]) + e0, rbytes, &full_bar[s]);
     };
 
     T acc[5] = {T(0), T(0), T(0), T(0), T(0)};
+    T pre[5] = {T(0), T(0), T(0), T(0), T(0)};   // HALO, right-margin warp: operands of the element after the current tile
     __syncthreads();   // sh.vecs / sh.coef / sh.slots are in place and the staging ring is free
     int64_t next_tile = 0;
     for (int s = 0; s < stages; s++, next_tile++)
@@ -805,34 +810,54 @@ __device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, const 
                 for (int k = 0; k < EPT; k++) u1.v[k] = (k < cnt) ? ux.v[k] + T(1) * r[k] : T(0);
                 *reinterpret_cast<float4*>(xrow + off) = *reinterpret_cast<const float4*>(u1.v);
             }
-            // the element on either side of the tile: warp kPWarps-2 (left) and kPWarps-1 (right) gather its operands from global
-            // memory (through L2: other CTAs wrote them in earlier rounds), lane 0 repeats the owner's arithmetic
-            if (warp >= kPWarps - 2)
+            // the element on either side of the tile.  Left: the previous tile of this chunk left its last x1 in sh.carry (only a chunk's
+            // first tile asks global memory).  Right: warp kPWarps-1 holds the operands of the element after the tile (fetched through
+            // L2 one tile ahead: other CTAs wrote them in earlier rounds), multiplies them by their coefficients in parallel and lane 0
+            // adds the products in the owner's order -- the owner's arithmetic, bit for bit.
+            if (warp == kPWarps - 2 && lane == 0 && t > 0) xrow[-1] = *reinterpret_cast<const T*>(&sh.carry[(t - 1) & 1]);
+            if (warp >= kPWarps - 2 && (warp == kPWarps - 1 || t == 0))
             {
                 const bool left = warp == kPWarps - 2;
                 const int64_t im = left ? e0 - 1 : e0 + len;
+                T* scratch = reinterpret_cast<T*>(sh.margin[left ? 0 : 1]);
+                auto fetch = [&](int64_t i, T (&dstv)[5]) {
+#pragma unroll
+                    for (int w = 0; w < 5; w++)
+                    {
+                        const int q = lane + 32 * w;
+                        T val = T(0);
+                        if (i >= 0 && i < n && q < 2 * c + 2)
+                        {
+                            if (q == 0) val = __ldcg(static_cast<const T*>(sh.vecs[0]) + i);
+                            else if (q == 1) val = __ldcg(static_cast<const T*>(sh.vecs[1]) + i);
+                            else if (q < 2 + c) val = __ldcg(h.y_at(sh.slotid[q - 2], i));          // y of age q-2
+                            else val = __ldcg(h.s_at(sh.slotid[q - 2 - c], i));                      // s of age q-2-c
+                        }
+                        dstv[w] = val;
+                    }
+                };
+                if (left || t == 0) fetch(im, pre);        // (the right-margin warp fetched this tile's element during the previous tile)
                 if (im >= 0 && im < n)
                 {
-                    T* scratch = reinterpret_cast<T*>(sh.margin[left ? 0 : 1]);
-                    for (int q = lane; q < 2 * c + 2; q += 32)
+#pragma unroll
+                    for (int w = 0; w < 5; w++)
                     {
-                        T val;
-                        if (q == 0) val = __ldcg(static_cast<const T*>(sh.vecs[0]) + im);
-                        else if (q == 1) val = __ldcg(static_cast<const T*>(sh.vecs[1]) + im);
-                        else if (q < 2 + c) val = __ldcg(h.y_at(sh.slotid[q - 2], im));            // y of age q-2
-                        else val = __ldcg(h.s_at(sh.slotid[q - 2 - c], im));                        // s of age q-2-c
-                        scratch[q] = val;
+                        const int q = lane + 32 * w;
+                        if (q < 2 * c + 2)
+                            scratch[q] = (q == 0) ? cv * pre[w] : (q == 1) ? pre[w] : (q < 2 + c) ? s_coef[1 + (q - 2)] * pre[w] : s_coef[1 + c + (q - 2 - c)] * pre[w];
                     }
                     __syncwarp();
                     if (lane == 0)
                     {
-                        T rm = cv * scratch[0];
-                        for (int j = 0; j < c; j++) rm += s_coef[1 + j] * scratch[2 + j];
-                        for (int j = c - 1; j >= 0; j--) rm += s_coef[1 + c + j] * scratch[2 + c + j];
+                        T rm = scratch[0];
+                        for (int j = 0; j < c; j++) rm += scratch[2 + j];
+                        for (int j = c - 1; j >= 0; j--) rm += scratch[2 + c + j];
                         xrow[left ? -1 : len] = scratch[1] + T(1) * rm;
                     }
                 }
+                if (!left && t + 1 < ntl) fetch(own.start(t + 1, TE) + own.len(t + 1, TE), pre);   // next tile's right neighbour, in flight meanwhile
             }
+            if (mine && off + EPT >= len) *reinterpret_cast<T*>(&sh.carry[t & 1]) = xrow[len - 1];   // (this thread wrote it above; two slots: the next tile reads the other one)
             __syncthreads();
             // ---- phase 2: the objective at x1 with its neighbours from shared memory ----
             if (mine)
@@ -845,7 +870,8 @@ __device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, const 
                 const T right = (i0 + EPT < n) ? xrow[off + EPT] : T(0);
                 T xr = T(0);
                 if (EPT < 4) xv[EPT < 4 ? EPT : 3] = right; else xr = right;
-                acc[1] += obj.eval(i0, cnt, xv, xl, xr, gv);
+                if constexpr (DV == 2) acc[1] += obj.staged(base + 2 * (size_t)TE + 2 * PAD, base + 3 * (size_t)TE + 2 * PAD, e0).eval(i0, cnt, xv, xl, xr, gv);
+                else acc[1] += obj.eval(i0, cnt, xv, xl, xr, gv);
                 Unit<T> ug, uo;
 #pragma unroll
                 for (int k = 0; k < EPT; k++)
@@ -1446,7 +1472,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
                         sh.slots[j] = (unsigned char)runs.row_of(g.slots[j]);
                         sh.slotid[j] = g.slots[j];
                     }
-                    if (tid == 0) { sh.vecs[0] = vg; sh.vecs[1] = vx; }
+                    if (tid == 0) { sh.vecs[0] = vg; sh.vecs[1] = vx; sh.vecs[2] = st->data0; sh.vecs[3] = st->data1; }
                 }
                 if (fuse)
                 {

@@ -412,8 +412,8 @@ template <class T> struct GramSolveArgs
     unsigned char slots[kMaxM];
 };
 
-// smem layout (T units): SY[c*c] | YY[c*c] | coef[2c+1] | alpha[c] ; everything indexed by AGE (0 = newest).
-inline size_t gram_solve_smem_elems(int c) { return (size_t)2 * c * c + 3 * c + 1; }
+// smem layout (T units): SY[c*c] | YY[c*c] | coef[2c+1] | alpha[c] | a*S'v[c] | a*Y'v[c] | ys[c] ; everything indexed by AGE (0 = newest).
+inline size_t gram_solve_smem_elems(int c) { return (size_t)2 * c * c + 6 * c + 1; }
 
 // All global reads go through L2 (__ldcg): inside the persistent solve these scalars are rewritten by another CTA between rounds.
 template <class T>
@@ -447,33 +447,60 @@ __device__ void gram_solve_in_smem(const GramSolveArgs<T>& g, T* sm, bool writer
             g.SS_out[pi * M + pj] = ss;
         }
     }
+    // right-hand sides and ys by age next to the matrices (one global read each instead of one per use)
+    T* b0 = al + c;        // a * s_i'v
+    T* b1 = b0 + c;        // a * y_i'v
+    T* ysv = b1 + c;
+    if (g.with_v)
+        for (int i = tid; i < c; i += nt)
+        {
+            b0[i] = g.a * (T)__ldcg(g.raw + i * kGramVals + 0);
+            b1[i] = g.a * (T)__ldcg(g.raw + i * kGramVals + 1);
+            ysv[i] = (g.slots[i] == g.ov_slot) ? g.ov_ys : __ldcg(g.ys + g.slots[i]);
+        }
     __syncthreads();
-    if (tid == 0 && g.with_v)
+    if (tid < 32 && g.with_v)
     {
+        // One warp runs the recursion: the sweeps are sequential in i, the inner products over t are spread over the lanes and
+        // summed by a fixed shuffle tree (deterministic; ~10x shorter critical path than one thread at c = 20).
+        const int lane = tid;
         const T theta = g.ov_theta_on ? g.ov_theta : __ldcg(g.theta);
-        auto ys_of = [&](int i) { return (g.slots[i] == g.ov_slot) ? g.ov_ys : __ldcg(g.ys + g.slots[i]); };
+        auto lanes_sum = [](T v) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            return v;
+        };
         // backward sweep (BFGSMat.h:285-290): alpha_i = s_i'q / ys_i with q = a*v - sum_{newer t} alpha_t y_t
         for (int i = 0; i < c; i++)
         {
-            T sq = g.a * (T)__ldcg(g.raw + i * kGramVals + 0);
-            for (int t = 0; t < i; t++) sq -= al[t] * sSY[i * c + t];
-            al[i] = sq / ys_of(i);
+            T part = T(0);
+            for (int t = lane; t < i; t += 32) part += al[t] * sSY[i * c + t];
+            const T sum = lanes_sum(part);
+            if (lane == 0) al[i] = (b0[i] - sum) / ysv[i];
+            __syncwarp();
         }
         // forward sweep (BFGSMat.h:293-301): r = q/theta + sum_{older t} (alpha_t - beta_t) s_t ; beta_i = y_i'r / ys_i
         T* cs = coef + 1 + c;
         for (int i = c - 1; i >= 0; i--)
         {
-            T yq = g.a * (T)__ldcg(g.raw + i * kGramVals + 1);
-            for (int t = 0; t < c; t++) yq -= al[t] * sYY[i * c + t];
-            T yr = yq / theta;
-            for (int t = c - 1; t > i; t--) yr += cs[t] * sSY[t * c + i];
-            const T beta = yr / ys_of(i);
-            cs[i] = al[i] - beta;
+            T p1 = T(0), p2 = T(0);
+            for (int t = lane; t < c; t += 32) p1 += al[t] * sYY[i * c + t];
+            for (int t = i + 1 + lane; t < c; t += 32) p2 += cs[t] * sSY[t * c + i];
+            const T s1 = lanes_sum(p1), s2 = lanes_sum(p2);
+            if (lane == 0)
+            {
+                const T yr = (b1[i] - s1) / theta + s2;
+                const T beta = yr / ysv[i];
+                cs[i] = al[i] - beta;
+            }
+            __syncwarp();
         }
-        coef[0] = g.a / theta;
-        for (int i = 0; i < c; i++) coef[1 + i] = -(al[i] / theta);
-        if (writer)
-            for (int i = 0; i < c; i++) g.alpha[g.slots[i]] = al[i];
+        if (lane == 0) coef[0] = g.a / theta;
+        for (int i = lane; i < c; i += 32)
+        {
+            coef[1 + i] = -(al[i] / theta);
+            if (writer) g.alpha[g.slots[i]] = al[i];
+        }
     }
     __syncthreads();
 }

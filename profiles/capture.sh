@@ -2,24 +2,22 @@
 # profiles/capture.sh -- regenerate the ncu evidence of profiles/ on a GPU box (one GPU; ncu replays every kernel ~40 times):
 #     gpurun --timeout 1500 -- 'bash profiles/capture.sh r02'
 # writes gpurun_out/<round>_*.ncu-rep and the launch list; afterwards, in the build container:
-#     bash profiles/capture.sh r02 export        # .ncu-rep -> profiles/<round>_*.{raw,details}.csv
-# The command profiled is always `python bench.py --steps 1 --warmup 3 --profile-mode` (config C2: 22 iterations per solve, the
-# history is full (c = 10) from the 11th iteration on).  Numbers printed by runs under ncu are never bench values.
+#     bash profiles/capture.sh r02 export        # .ncu-rep -> profiles/<round>_*.{raw,details}.csv + <round>_*_hotspots.txt
+# The command profiled is `python bench.py --config cN --steps 1 --warmup 3 --profile-mode` (the 4th launch of k_persist = one
+# whole minimize(): C2 22 iterations / 71 rounds).  Numbers printed by runs under ncu are never bench values.
 set -u
 ROUND=${1:-rXX}
 MODE=${2:-capture}
 cd "$(dirname "$0")/.."
 OUT=gpurun_out
-CMD="python bench.py --steps 1 --warmup 3 --profile-mode"
-# kernel regex : launches to skip so that the captured one runs with a full history in the 4th solve
-#   fused calls per solve: 21 (k_pair_dots, k_gram_combine); trials per solve: 50; 3 warm-up solves come first
-declare -A SKIP=( [k_pair_dots]=75 [k_gram_combine]=75 [k_trial]=165 [k_gram_dots]=0 [k_update]=0 )
 if [ "$MODE" = "capture" ]; then
     mkdir -p $OUT
-    ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 80 --csv --log-file $OUT/${ROUND}_launches_bench_c2.csv $CMD > $OUT/${ROUND}_launches.log 2>&1
-    for k in k_pair_dots k_gram_combine k_trial; do
-        ncu --set full --clock-control none --import-source on -k regex:$k -s ${SKIP[$k]} -c 1 -o $OUT/${ROUND}_${k}_c10_full $CMD > $OUT/${ROUND}_${k}.log 2>&1
-        tail -2 $OUT/${ROUND}_${k}.log | cut -c1-200
+    CMD="python bench.py --config c2 --steps 1 --warmup 3 --profile-mode --no-cpu-baseline"
+    ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/${ROUND}_launches_bench_c2.csv $CMD > $OUT/${ROUND}_launches.log 2>&1
+    for c in c2 c3; do
+        ncu --set full --clock-control none --import-source on -k regex:k_persist -s 3 -c 1 -o $OUT/${ROUND}_k_persist_${c}_full \
+            python bench.py --config $c --steps 1 --warmup 3 --profile-mode --no-cpu-baseline > $OUT/${ROUND}_k_persist_${c}.log 2>&1
+        tail -2 $OUT/${ROUND}_k_persist_${c}.log | cut -c1-200
     done
     ls -la $OUT/${ROUND}_*
 else
@@ -27,8 +25,10 @@ else
         base=profiles/$(basename "${rep%.ncu-rep}")
         ncu -i "$rep" --page raw --csv > "$base.raw.csv" 2>/dev/null
         ncu -i "$rep" --page details --csv > "$base.details.csv" 2>/dev/null
-        echo "exported $base.{raw,details}.csv"
+        ncu -i "$rep" --page source --csv --print-source cuda,sass > /tmp/_src.csv 2>/dev/null
+        python profiles/hotspots.py /tmp/_src.csv "$base.raw.csv" > "${base}_hotspots.txt"
+        echo "exported $base.{raw,details}.csv ${base}_hotspots.txt"
     done
     [ -f $OUT/${ROUND}_launches_bench_c2.csv ] && cp $OUT/${ROUND}_launches_bench_c2.csv profiles/
-    echo "now update profiles/README.md and profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of k_pair_dots + k_gram_combine)"
+    echo "now update profiles/README.md and profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of the k_persist launch)"
 fi
