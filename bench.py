@@ -315,7 +315,9 @@ def main():
                 "launches_timed": len(profs), "ms_per_launch": ms / max(1, len(profs)),
                 "passes": {k: {"ms_per_solve": v["ms"] / len(profs), "rounds_per_solve": v["rounds"] / len(profs),
                                "gb_per_s": v["alg_bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None} for k, v in ops.items()},
-                "sync_ms_per_solve": sum(p["sync_ms"] for p in profs) / len(profs)}
+                "sync_ms_per_solve": sum(p["sync_ms"] for p in profs) / len(profs),
+                "sync_wait_last_cta_ms_per_solve": sum(p["wait_last_cta_ms"] for p in profs) / len(profs),
+                "sync_cross_rank_exchange_ms_per_solve": sum(p["exchange_ms"] for p in profs) / len(profs)}
 
     # ================================================================================================================ c2 / c3
     if name in ("c2", "c3"):

@@ -112,7 +112,33 @@ struct XInbox
 {
     double vals[kXRing][kXMaxRanks][kXMaxVals];
     unsigned long long flag[kXRing][kXMaxRanks];
+    // the persistent solve's exchange: every double travels as two self-validating 8-byte words {32 data bits, 32-bit epoch tag}
+    // (single-copy atomic stores): no fence, no flag, one NVLink crossing (see ll_push / ll_pull)
+    unsigned long long ll[kXRing][kXMaxRanks][kXMaxVals][2];
 };
+
+__device__ __forceinline__ void ll_push(unsigned long long* dst2, double v, unsigned tag)
+{
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long w0 = (bits & 0xffffffffull) | ((unsigned long long)tag << 32);
+    const unsigned long long w1 = (bits >> 32) | ((unsigned long long)tag << 32);
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" :: "l"(dst2), "l"(w0), "l"(w1) : "memory");
+}
+// spins until both words carry `tag`; false when `give_up` says so (watchdog)
+template <class GiveUp> __device__ __forceinline__ bool ll_pull(const unsigned long long* src2, unsigned tag, double& v, GiveUp give_up)
+{
+    for (;;)
+    {
+        unsigned long long w0, w1;
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src2) : "memory");
+        if ((unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag)
+        {
+            v = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+            return true;
+        }
+        if (give_up()) return false;
+    }
+}
 
 struct XComm
 {

@@ -422,7 +422,7 @@ int lbfgsb200_drv_session_solve(void* handle, int from_host, int to_host, drv_re
 
 const double* lbfgsb200_drv_session_result(void* handle) { return static_cast<Session*>(handle)->pinned_out; }
 
-// accounting of the session's last device-resident solve (lbfgs_b200_solver_profile; sync_ms has 2 slots); returns 1 when the
+// accounting of the session's last device-resident solve (lbfgs_b200_solver_profile; sync_ms has 3 slots); returns 1 when the
 // session runs the host-driven loop
 int lbfgsb200_drv_session_profile(void* handle, double* kernel_ms, double* ms_by_op10, unsigned long long* rounds_by_op10, double* alg_bytes_by_op10,
                                   double* sync_ms)

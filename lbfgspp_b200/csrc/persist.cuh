@@ -132,6 +132,7 @@ struct alignas(128) PCtl
     long long cyc_op[kPOps];
     long long cyc_sync;
     long long cyc_wait_all;     // of cyc_sync: from CTA 0's own arrival until the last CTA has arrived
+    long long cyc_exchange;     // of cyc_sync: the cross-rank exchange (push, wait for every peer's flag, rank-ordered sums)
     unsigned long long n_op[kPOps];
     double words_op[kPOps];
 };
@@ -149,6 +150,7 @@ template <class T> struct PArgs
     int grain;                  // chunk boundaries are multiples of this many elements (= the history's block length)
     const XComm* xc;
     int64_t index_offset, n_global;
+    long long wait_cycles;      // watchdog budget of a grid-barrier wait (clock64 ticks); cross-rank waits get 4x, the release wait 6x
 };
 
 template <class V> __device__ __forceinline__ V ldv(const V* p) { return *reinterpret_cast<const volatile V*>(p); }
@@ -908,7 +910,7 @@ __device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, const 
 }
 
 // ---- waits with a watchdog ----------------------------------------------------------------------------------------------------
-constexpr long long kPWaitCycles = 6000000000ll;   // ~3 s at 2 GHz: far beyond any legitimate wait, short of gpurun's own limits
+constexpr long long kPWaitCycles = 6000000000ll;   // default watchdog budget, ~3 s at 2 GHz: far beyond any legitimate wait (LBFGS_B200_WATCHDOG_SCALE multiplies it, e.g. under compute-sanitizer)
 
 __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p)
 {
@@ -1164,11 +1166,18 @@ __device__ int leader_round(const PArgs<T>& a, int G, PShared& sh, PState<T>* ca
     // 2. n sharded over ranks: ONE exchange for all running problems (sums in rank order: identical bits on every rank)
     if (a.xc != nullptr)
     {
+        const long long t_x0 = clock64();
         const XComm* xc = a.xc;
         const int me = xc->rank, R = xc->nranks;
         const unsigned long long epoch = a.ctl->epoch + 1ull;
         const int slot = (int)(epoch % kXRing);
-        // payload layout: problem after problem, nv sums then (HALO) 4 gathered boundary values
+        const unsigned tag = (unsigned)epoch;
+        auto give_up = [&]() {
+            if (clock64() - t_x0 > 4 * a.wait_cycles || ldv(&a.ctl->abort)) { a.ctl->abort = 1; return true; }
+            return false;
+        };
+        // payload layout: problem after problem, nv sums then (HALO) 4 gathered boundary values.  Every value goes to every rank
+        // (this one included) as two tagged 8-byte words: the receiver needs no flag and the sender no fence.
         int ofs = 0;
         for (int b = 0; b < a.B; b++)
         {
@@ -1177,7 +1186,7 @@ __device__ int leader_round(const PArgs<T>& a, int G, PShared& sh, PState<T>* ca
             if (op == POP_IDLE) continue;
             const int nv = nvals_of(op, st->c_round);
             for (int r = tid; r < R * nv; r += kPThreads)
-                xc->inbox[r / nv]->vals[slot][me][ofs + r % nv] = st->raw[r % nv];
+                ll_push(xc->inbox[r / nv]->ll[slot][me][ofs + r % nv], st->raw[r % nv], tag);
             ofs += nv;
             if (HALO)
             {
@@ -1187,22 +1196,12 @@ __device__ int leader_round(const PArgs<T>& a, int G, PShared& sh, PState<T>* ca
                     const int k = tid & 3;
                     const T* src = (k & 1) ? st->drt : st->x;
                     const double val = (double)__ldcg(src + ((k & 2) ? a.n - 1 : 0));
-                    xc->inbox[tid >> 2]->vals[slot][me][ofs + k] = val;
+                    ll_push(xc->inbox[tid >> 2]->ll[slot][me][ofs + k], val, tag);
                 }
                 ofs += 4;
             }
         }
-        __threadfence_system();
-        __syncthreads();
-        if (tid < R) st_release_sys(&xc->inbox[tid]->flag[slot][me], epoch);
-        if (tid < R)
-        {
-            const unsigned long long* f = &xc->inbox[me]->flag[slot][tid];
-            const long long t_start = clock64();
-            while (ld_acquire_sys(f) != epoch)
-                if (clock64() - t_start > 4 * kPWaitCycles || ldv(&a.ctl->abort)) { a.ctl->abort = 1; break; }
-        }
-        __syncthreads();
+        __syncthreads();   // (raw[] is about to be overwritten with the global sums)
         ofs = 0;
         for (int b = 0; b < a.B; b++)
         {
@@ -1213,7 +1212,12 @@ __device__ int leader_round(const PArgs<T>& a, int G, PShared& sh, PState<T>* ca
             for (int k = tid; k < nv; k += kPThreads)
             {
                 double t = 0.0;
-                for (int r = 0; r < R; r++) t += ld_volatile_f64(&xc->inbox[me]->vals[slot][r][ofs + k]);
+                for (int r = 0; r < R; r++)           // rank order: identical bits on every rank
+                {
+                    double v = 0.0;
+                    ll_pull(xc->inbox[me]->ll[slot][r][ofs + k], tag, v, give_up);
+                    t += v;
+                }
                 st->raw[k] = t;
             }
             ofs += nv;
@@ -1223,13 +1227,15 @@ __device__ int leader_round(const PArgs<T>& a, int G, PShared& sh, PState<T>* ca
                 {
                     const int side = tid >> 2, k = tid & 3;       // side 0: left neighbour, 1: right neighbour
                     const int nb = side == 0 ? me - 1 : me + 1;
-                    st->halo[4 + 4 * side + k] = (nb >= 0 && nb < R) ? ld_volatile_f64(&xc->inbox[me]->vals[slot][nb][ofs + k]) : 0.0;
+                    double v = 0.0;
+                    if (nb >= 0 && nb < R) ll_pull(xc->inbox[me]->ll[slot][nb][ofs + k], tag, v, give_up);
+                    st->halo[4 + 4 * side + k] = v;
                 }
                 ofs += 4;
             }
         }
         __syncthreads();
-        if (tid == 0) a.ctl->epoch = epoch;
+        if (tid == 0) { a.ctl->epoch = epoch; a.ctl->cyc_exchange += clock64() - t_x0; }
     }
     // 3. scalar logic, one thread per problem; the outcome goes into the problem's round descriptor
     int still = 0;
@@ -1264,6 +1270,12 @@ template <class T> __device__ void leader_halo_prelude(const PArgs<T>& a)
     const int me = xc->rank, R = xc->nranks;
     const unsigned long long epoch = a.ctl->epoch + 1ull;
     const int slot = (int)(epoch % kXRing);
+    const unsigned tag = (unsigned)epoch;
+    const long long t_x0 = clock64();
+    auto give_up = [&]() {
+        if (clock64() - t_x0 > 4 * a.wait_cycles || ldv(&a.ctl->abort)) { a.ctl->abort = 1; return true; }
+        return false;
+    };
     for (int b = 0; b < a.B; b++)
     {
         PState<T>* st = a.probs + b;
@@ -1271,20 +1283,9 @@ template <class T> __device__ void leader_halo_prelude(const PArgs<T>& a)
         {
             const int k = tid & 3;
             const double val = (k & 1) ? 0.0 : (double)__ldcg(st->x + ((k & 2) ? a.n - 1 : 0));
-            xc->inbox[tid >> 2]->vals[slot][me][4 * b + k] = val;
+            ll_push(xc->inbox[tid >> 2]->ll[slot][me][4 * b + k], val, tag);
         }
     }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < R) st_release_sys(&xc->inbox[tid]->flag[slot][me], epoch);
-    if (tid < R)
-    {
-        const unsigned long long* f = &xc->inbox[me]->flag[slot][tid];
-        const long long t_start = clock64();
-        while (ld_acquire_sys(f) != epoch)
-            if (clock64() - t_start > 4 * kPWaitCycles || ldv(&a.ctl->abort)) { a.ctl->abort = 1; break; }
-    }
-    __syncthreads();
     for (int b = 0; b < a.B; b++)
     {
         PState<T>* st = a.probs + b;
@@ -1292,10 +1293,11 @@ template <class T> __device__ void leader_halo_prelude(const PArgs<T>& a)
         {
             const int side = tid >> 2, k = tid & 3;
             const int nb = side == 0 ? me - 1 : me + 1;
-            st->halo[4 + 4 * side + k] = (nb >= 0 && nb < R) ? ld_volatile_f64(&xc->inbox[me]->vals[slot][nb][4 * b + k]) : 0.0;
+            double v = 0.0;
+            if (nb >= 0 && nb < R) ll_pull(xc->inbox[me]->ll[slot][nb][4 * b + k], tag, v, give_up);
+            st->halo[4 + 4 * side + k] = v;
         }
     }
-    __threadfence();
     __syncthreads();
     if (tid == 0) a.ctl->epoch = epoch;
 }
@@ -1349,7 +1351,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
                 const long long t_start = clock64();
                 t_arrive = t_start;
                 while (ld_acquire_gpu_u32(&a.ctl->arrive) != episode * (unsigned)G)
-                    if (clock64() - t_start > kPWaitCycles || ldv(&a.ctl->abort)) { a.ctl->abort = 1; break; }
+                    if (clock64() - t_start > a.wait_cycles || ldv(&a.ctl->abort)) { a.ctl->abort = 1; break; }
                 a.ctl->cyc_wait_all += clock64() - t_start;
             }
             __syncthreads();
@@ -1371,7 +1373,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
             const long long t_start = clock64();
             unsigned v;
             while (((v = ld_acquire_gpu_u32(&a.ctl->release)) & ~kPStopBit) < episode)
-                if (clock64() - t_start > 6 * kPWaitCycles || ldv(&a.ctl->abort)) { a.ctl->abort = 1; v = kPStopBit; break; }
+                if (clock64() - t_start > 6 * a.wait_cycles || ldv(&a.ctl->abort)) { a.ctl->abort = 1; v = kPStopBit; break; }
             s_release = v;
         }
         __syncthreads();

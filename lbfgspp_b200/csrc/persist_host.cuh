@@ -163,6 +163,8 @@ static lbfgs_b200_status solver_minimize(lbfgs_b200_solver* s, int objective, co
     a.probs = static_cast<PState<T>*>(s->d_state); a.rounds = static_cast<PRound<T>*>(s->d_rounds); a.B = B; a.ctl = s->d_ctl; a.partials = s->d_partials; a.pstride = s->pstride;
     a.n = s->n; a.grain = 1 << s->bt_log; a.xc = ctx->x_active ? ctx->x_comm : nullptr;
     a.index_offset = index_offset; a.n_global = n_global;
+    a.wait_cycles = kPWaitCycles;
+    if (const char* e = getenv("LBFGS_B200_WATCHDOG_SCALE")) { const long long k = atoll(e); if (k >= 1 && k <= 100000) a.wait_cycles *= k; }
     void* kargs[] = {&a};
     CU(ctx, cudaEventRecord(s->ev0, ctx->stream));
     CU(ctx, cudaLaunchCooperativeKernel(kernel, dim3((unsigned)grid), dim3(kPThreads), kargs, smem, ctx->stream));
@@ -335,7 +337,7 @@ lbfgs_b200_status lbfgs_b200_solver_profile(const lbfgs_b200_solver* s, double* 
         if (rounds_by_op10) rounds_by_op10[k] = c.n_op[k];
         if (alg_bytes_by_op10) alg_bytes_by_op10[k] = c.words_op[k] * (double)s->n * (double)s->elem;
     }
-    if (sync_ms) { sync_ms[0] = scale * (double)c.cyc_sync; sync_ms[1] = scale * (double)c.cyc_wait_all; }
+    if (sync_ms) { sync_ms[0] = scale * (double)c.cyc_sync; sync_ms[1] = scale * (double)c.cyc_wait_all; sync_ms[2] = scale * (double)c.cyc_exchange; }
     return LBFGS_B200_OK;
 }
 const void* lbfgs_b200_solver_final_grad(const lbfgs_b200_solver* s) { return s ? s->final_g[0] : nullptr; }

@@ -133,3 +133,21 @@ def test_final_approx_hessian_after_resident_solve():
     # a second solve on the same solver type from another start must refresh the matrices
     it2, _, B2, _ = lb.solve_dense(lb.OBJ_ROSENBROCK_PAIRED, np.full(10, 0.5), lb.LBFGSParam(), "NocedalWright", resident=True)
     assert it2 > 1 and np.max(np.abs(B2 - B_r)) > 0
+
+
+@pytest.mark.parametrize("m,iters", [(30, 45), (64, 80)])
+def test_resident_large_history(orc, m, iters):
+    """History sizes beyond one column pair per warp (m > 24: the dots pass works in rounds; the tiled history uses short blocks):
+    the first `iters` iterations of the tridiagonal quadratic, evaluation by evaluation against the CPU checker."""
+    n = 30000
+    d, b, _ = po.quad_tridiag_data(n, kappa=1e3, seed=3)
+    prm = lb.LBFGSParam(m=m, max_iterations=iters)
+    g = resident(prm, "Bracketing").minimize(lb.OBJ_QUAD_TRIDIAG, np.zeros(n), data0=d, data1=b)
+    c = orc.lbfgs(po.OBJ_QUAD_TRIDIAG, np.zeros(n), LS["Bracketing"], cpu_param(orc, prm), data0=d, data1=b)
+    assert g["status"] == c["status"] == "ok"
+    assert (g["niter"], g["nfev"]) == (c["niter"], c["nfev"]) == (iters, c["nfev"])
+    k = min(len(g["trace"]), len(c["trace"]))
+    rel = np.abs(g["trace"][1:k] - c["trace"][1:k]) / np.abs(c["trace"][1:k])
+    assert np.max(rel) <= 1e-9, np.max(rel)
+    h = lb.LBFGSSolver(prm, "Bracketing", resident=False).minimize(lb.OBJ_QUAD_TRIDIAG, np.zeros(n), data0=d, data1=b)
+    assert (h["niter"], h["nfev"]) == (g["niter"], g["nfev"]) and abs(h["fx"] - g["fx"]) <= 1e-9 * abs(g["fx"])
