@@ -309,9 +309,11 @@ def main():
         return {"kernel": kernel_name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": load_traffic(traffic_key), "peak_source": peak_src,
                 "algorithmic_bytes": "per launch (= one minimize): sum over the kernel's passes of whole vectors read + written, 8 n x "
-                                     "{first 3, trial 4, pair-forming dots 2c+4, combination + first trial 2c+3 (+2 when its x, g are stored), plain dots 2c+1, materialise 4}, "
-                                     "c = pairs taking part in that pass; one iteration with T trials moves (4c+7) + 4(T-1) words per coordinate "
-                                     "where SURVEY.md 8d counts (4c+2) + 6 + 8T for the unfused sequence",
+                                     "{first 3, trial 4, pair-forming dots 2c+4, combination + first trial 2c+3 (+2 when its x, g are stored, +2 when it also "
+                                     "forms the pair of an accepted first trial and takes its dots from the staged columns), plain dots 2c+1, materialise 4}, "
+                                     "c = pairs taking part in that pass; one iteration with T trials moves (4c+9) + 4(T-1) words per coordinate, or 2c+7 "
+                                     "when the first trial is accepted and its pair dots were taken speculatively, where SURVEY.md 8d counts "
+                                     "(4c+2) + 6 + 8T for the unfused sequence",
                 "launches_timed": len(profs), "ms_per_launch": ms / max(1, len(profs)),
                 "passes": {k: {"ms_per_solve": v["ms"] / len(profs), "rounds_per_solve": v["rounds"] / len(profs),
                                "gb_per_s": v["alg_bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None} for k, v in ops.items()},
@@ -461,7 +463,15 @@ def main():
         for _ in range(max(1, min(args.warmup, 2))):
             res, _, _ = bs.solve(return_x=False)
         sampler.start()
-        outs, dev_seconds = device_timed(lambda: bs.solve(return_x=False)[0], steps)
+        profs = []
+
+        def one_batch():
+            rr = bs.solve(return_x=False)[0]
+            pr = bs.profile()
+            if pr:
+                profs.append(pr)
+            return rr
+        outs, dev_seconds = device_timed(one_batch, steps)
         iters_rank = sum(sum(p["niter"] for p in o) for o in outs)
         iters = iters_rank if shard_n else sum_over_ranks(iters_rank)
         barrier()
@@ -485,6 +495,8 @@ def main():
                                "step": "one batched minimize(): %d problems, iterations min/mean/max = %d/%.0f/%d, rounds (streaming passes) of the longest = %d"
                                        % (len(its), min(its), float(np.mean(its)), max(its), max(rounds)),
                                "converged": int(sum(p["status"] == "ok" for p in outs[-1]))}})
+        if profs:
+            line["roofline"] = roofline_from_profiles(profs, "k_persist (device-resident solve, %d problems in one launch)" % len(mine), "k_persist_dram_bytes_per_launch_c5")
         if not args.no_cpu_baseline and rank == 0 and world == 1:
             line["cpu_baseline"] = cpu_baseline_block(name)
         bs.close()

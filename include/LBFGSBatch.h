@@ -101,6 +101,8 @@ public:
     }
     // gradient of problem b at its solution (device pointer into the solver's storage, valid until the next minimize())
     const Scalar* final_grad(int b) const { return static_cast<const Scalar*>(lbfgs_b200_solver_final_grad_of(m_solver, b)); }
+    // the solver object behind the last minimize() (nullptr before the first one): accounting via lbfgs_b200_solver_profile()
+    lbfgs_b200_solver* solver_handle() const { return m_solver; }
 };
 
 }  // namespace LBFGSpp

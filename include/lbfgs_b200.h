@@ -70,6 +70,11 @@ uint64_t lbfgs_b200_launch_count(const lbfgs_b200_ctx* ctx); /* kernels launched
 
 lbfgs_b200_status lbfgs_b200_malloc(lbfgs_b200_ctx* ctx, void** dptr, size_t bytes); /* replaces Eigen resize(): LBFGS.h:40-50 */
 lbfgs_b200_status lbfgs_b200_free(lbfgs_b200_ctx* ctx, void* dptr);
+/* Device blocks released by lbfgs_b200_free / *_destroy stay with the context and are handed out again (exact size match): the
+ * reference reallocates its work vectors and history in every minimize() (LBFGS.h:84-90, BFGSMat.h:61-67), which on the GPU would
+ * cost a cudaMalloc/cudaFree pair and a device-wide synchronisation each.  lbfgs_b200_trim returns the cached blocks to the driver
+ * (lbfgs_b200_ctx_destroy does so as well). */
+lbfgs_b200_status lbfgs_b200_trim(lbfgs_b200_ctx* ctx);
 lbfgs_b200_status lbfgs_b200_malloc_host(lbfgs_b200_ctx* ctx, void** hptr, size_t bytes); /* pinned */
 lbfgs_b200_status lbfgs_b200_free_host(lbfgs_b200_ctx* ctx, void* hptr);
 lbfgs_b200_status lbfgs_b200_memcpy_h2d(lbfgs_b200_ctx* ctx, void* dst, const void* src_host, size_t bytes);

@@ -599,6 +599,16 @@ class BatchSession:
                for it, r in zip(items, rounds)]
         return res, X, secs.value
 
+    def profile(self):
+        """Accounting of the last batched solve (one kernel launch for the whole batch): same dict as Session.profile()."""
+        ms, rounds, nbytes = (C.c_double * 10)(), (C.c_ulonglong * 10)(), (C.c_double * 10)()
+        kms, sync = C.c_double(0), (C.c_double * 3)()
+        self.drv.lbfgsb200_drv_batch_session_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        if self.drv.lbfgsb200_drv_batch_session_profile(self.h, C.byref(kms), ms, rounds, nbytes, sync):
+            return None
+        return dict(kernel_ms=kms.value, sync_ms=sync[0], wait_last_cta_ms=sync[1], exchange_ms=sync[2],
+                    ops={Session.OPS[k]: dict(ms=ms[k], rounds=int(rounds[k]), alg_bytes=nbytes[k]) for k in range(10) if rounds[k]})
+
     def close(self):
         if self.h:
             self.drv.lbfgsb200_drv_batch_session_destroy(self.h)

@@ -779,6 +779,23 @@ extern "C" int lbfgsb200_drv_batch_session_solve(void* handle, drv_batch_item* i
     }
 }
 
+// accounting of the batch session's last solve (the whole batch is one kernel launch: lbfgs_b200_solver_profile)
+extern "C" int lbfgsb200_drv_batch_session_profile(void* handle, double* kernel_ms, double* ms_by_op10, unsigned long long* rounds_by_op10,
+                                                   double* alg_bytes_by_op10, double* sync_ms)
+{
+    BatchSession* s = static_cast<BatchSession*>(handle);
+    lbfgs_b200_solver* r = nullptr;
+    switch (s->ls)
+    {
+    case DRV_LS_BACKTRACKING: r = s->s_bt.solver_handle(); break;
+    case DRV_LS_BRACKETING: r = s->s_br.solver_handle(); break;
+    case DRV_LS_NOCEDAL_WRIGHT: r = s->s_nw.solver_handle(); break;
+    default: r = s->s_mt.solver_handle(); break;
+    }
+    if (!r) return 1;
+    return lbfgs_b200_solver_profile(r, kernel_ms, ms_by_op10, rounds_by_op10, alg_bytes_by_op10, sync_ms) == LBFGS_B200_OK ? 0 : 2;
+}
+
 // minimize() followed by final_approx_hessian() / final_approx_inverse_hessian() (reference LBFGS.h:192-197) on a built-in objective;
 // resident = 1: the device-resident solve (the matrices then come from the solver's own ring), 0: the host-driven loop.
 extern "C" int lbfgsb200_drv_solve_dense_f64(int device_ordinal, int objective, long n, int ls, const drv_param* q, int resident, double* x_host,

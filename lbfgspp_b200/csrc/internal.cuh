@@ -12,7 +12,10 @@
 #include <new>
 #include <algorithm>
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/lbfgs_b200.h"
@@ -63,8 +66,74 @@ struct lbfgs_b200_ctx
     double prof_ms[3] = {0, 0, 0};
     uint64_t prof_calls[3] = {0, 0, 0};
     double prof_bytes[3] = {0, 0, 0};   // algorithmic bytes of the calls made while profiling
+    // device-memory pool (pool_alloc / pool_free below): the reference reallocates its work vectors and the history in every
+    // minimize() (reference LBFGS.h:84-90, BFGSMat.h:61-67); on the GPU a cudaMalloc/cudaFree pair costs 0.1-1 ms and a device-wide
+    // synchronisation, so blocks released by DeviceVector / hist / box objects are kept and handed out again (exact size match).
+    // Everything the library does is ordered on ctx->stream, so a recycled block needs no synchronisation.
+    struct Pool
+    {
+        std::mutex mu;
+        std::multimap<size_t, void*> free_blocks;
+        std::unordered_map<void*, size_t> sizes;    // every block the pool handed out (live or cached)
+        size_t cached = 0, limit = size_t(64) << 30;
+        uint64_t hits = 0, misses = 0;
+    } pool;
     std::string err;
 };
+
+// pool_alloc: `bytes` rounded up to whole 256-byte lines (callers read ragged tails as full packs / bulk copies; the last line
+// of a recycled block is cleared like the one of a fresh block usually is).  Returns cudaErrorMemoryAllocation only after the
+// cached blocks have been given back to the driver and the allocation failed again.
+inline cudaError_t pool_alloc(lbfgs_b200_ctx* ctx, void** out, size_t bytes)
+{
+    const size_t size = ((bytes ? bytes : 1) + 255) & ~size_t(255);
+    std::lock_guard<std::mutex> lock(ctx->pool.mu);
+    auto it = ctx->pool.free_blocks.find(size);
+    if (it != ctx->pool.free_blocks.end())
+    {
+        *out = it->second;
+        ctx->pool.free_blocks.erase(it);
+        ctx->pool.cached -= size;
+        ctx->pool.hits++;
+        const size_t keep = bytes & ~size_t(255);
+        return cudaMemsetAsync(static_cast<char*>(*out) + keep, 0, size - keep, ctx->stream);
+    }
+    ctx->pool.misses++;
+    cudaError_t e = cudaMalloc(out, size);
+    if (e == cudaErrorMemoryAllocation && !ctx->pool.free_blocks.empty())
+    {
+        cudaGetLastError();
+        cudaStreamSynchronize(ctx->stream);
+        for (auto& kv : ctx->pool.free_blocks) { cudaFree(kv.second); ctx->pool.sizes.erase(kv.second); }
+        ctx->pool.free_blocks.clear();
+        ctx->pool.cached = 0;
+        e = cudaMalloc(out, size);
+    }
+    if (e == cudaSuccess) ctx->pool.sizes[*out] = size;
+    else *out = nullptr;
+    return e;
+}
+inline void pool_free(lbfgs_b200_ctx* ctx, void* p)
+{
+    if (!p) return;
+    if (!ctx) { cudaFree(p); return; }
+    std::lock_guard<std::mutex> lock(ctx->pool.mu);
+    auto it = ctx->pool.sizes.find(p);
+    if (it == ctx->pool.sizes.end()) { cudaFree(p); return; }      // not one of ours
+    const size_t size = it->second;
+    if (ctx->pool.cached + size > ctx->pool.limit) { ctx->pool.sizes.erase(it); cudaFree(p); return; }
+    ctx->pool.free_blocks.emplace(size, p);
+    ctx->pool.cached += size;
+}
+// give every cached block back to the driver (lbfgs_b200_trim, context destruction)
+inline void pool_trim(lbfgs_b200_ctx* ctx)
+{
+    std::lock_guard<std::mutex> lock(ctx->pool.mu);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->pool.free_blocks) { cudaFree(kv.second); ctx->pool.sizes.erase(kv.second); }
+    ctx->pool.free_blocks.clear();
+    ctx->pool.cached = 0;
+}
 
 enum { PH_APPLY_HV = 0, PH_TRIAL = 1, PH_UPDATE = 2 };
 

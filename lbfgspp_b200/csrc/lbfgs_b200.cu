@@ -537,6 +537,7 @@ void lbfgs_b200_ctx_destroy(lbfgs_b200_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    pool_trim(ctx);
     if (ctx->comm) ncclCommDestroy(ctx->comm);
     for (int r = 0; r < kXMaxRanks; r++) if (ctx->x_peer[r]) cudaIpcCloseMemHandle(ctx->x_peer[r]);
     cudaFree(ctx->x_comm);
@@ -569,14 +570,22 @@ lbfgs_b200_status lbfgs_b200_malloc(lbfgs_b200_ctx* ctx, void** dptr, size_t byt
     REQUIRE(ctx, ctx && dptr, "malloc: NULL argument");
     CU(ctx, cudaSetDevice(ctx->device));
     // round up to a whole number of 256-byte lines so that ragged tails can be read as full packs by callers
-    const size_t padded = (bytes + 255) & ~size_t(255);
-    CU(ctx, cudaMalloc(dptr, padded ? padded : 256));
+    // (pool_alloc does the rounding); blocks come from / go back to the context's pool, see internal.cuh
+    CU(ctx, pool_alloc(ctx, dptr, bytes));
     return LBFGS_B200_OK;
 }
 lbfgs_b200_status lbfgs_b200_free(lbfgs_b200_ctx* ctx, void* dptr)
 {
     if (!dptr) return LBFGS_B200_OK;
-    CU(ctx, cudaFree(dptr));
+    if (ctx) pool_free(ctx, dptr);
+    else CU(ctx, cudaFree(dptr));
+    return LBFGS_B200_OK;
+}
+lbfgs_b200_status lbfgs_b200_trim(lbfgs_b200_ctx* ctx)
+{
+    REQUIRE(ctx, ctx, "trim: NULL context");
+    CU(ctx, cudaSetDevice(ctx->device));
+    pool_trim(ctx);
     return LBFGS_B200_OK;
 }
 lbfgs_b200_status lbfgs_b200_malloc_host(lbfgs_b200_ctx* ctx, void** hptr, size_t bytes)
@@ -1334,16 +1343,16 @@ lbfgs_b200_status lbfgs_b200_hist_create(lbfgs_b200_ctx* ctx, lbfgs_b200_hist** 
     h->ld = (n + 31) & ~int64_t(31);  // columns start on 256-byte (fp64) / 128-byte (fp32) boundaries
     const size_t colbytes = (size_t)h->ld * elem_bytes * h->M;
     cudaError_t e = cudaSetDevice(ctx->device);
-    if (e == cudaSuccess) e = cudaMalloc(&h->S, colbytes);
-    if (e == cudaSuccess) e = cudaMalloc(&h->Y, colbytes);
-    if (e == cudaSuccess) e = cudaMalloc(&h->ys, (size_t)elem_bytes * h->M);
-    if (e == cudaSuccess) e = cudaMalloc(&h->alpha, (size_t)elem_bytes * h->M);
-    if (e == cudaSuccess) e = cudaMalloc(&h->theta, 8);
+    if (e == cudaSuccess) e = pool_alloc(ctx, &h->S, colbytes);
+    if (e == cudaSuccess) e = pool_alloc(ctx, &h->Y, colbytes);
+    if (e == cudaSuccess) e = pool_alloc(ctx, &h->ys, (size_t)elem_bytes * h->M);
+    if (e == cudaSuccess) e = pool_alloc(ctx, &h->alpha, (size_t)elem_bytes * h->M);
+    if (e == cudaSuccess) e = pool_alloc(ctx, &h->theta, 8);
     for (int b = 0; b < 2; b++)
     {
-        if (e == cudaSuccess) e = cudaMalloc(&h->SY[b], (size_t)elem_bytes * h->M * h->M);
-        if (e == cudaSuccess) e = cudaMalloc(&h->YY[b], (size_t)elem_bytes * h->M * h->M);
-        if (e == cudaSuccess) e = cudaMalloc(&h->SS[b], (size_t)elem_bytes * h->M * h->M);
+        if (e == cudaSuccess) e = pool_alloc(ctx, &h->SY[b], (size_t)elem_bytes * h->M * h->M);
+        if (e == cudaSuccess) e = pool_alloc(ctx, &h->YY[b], (size_t)elem_bytes * h->M * h->M);
+        if (e == cudaSuccess) e = pool_alloc(ctx, &h->SS[b], (size_t)elem_bytes * h->M * h->M);
     }
     if (e != cudaSuccess)
     {
@@ -1358,9 +1367,8 @@ lbfgs_b200_status lbfgs_b200_hist_create(lbfgs_b200_ctx* ctx, lbfgs_b200_hist** 
 void lbfgs_b200_hist_destroy(lbfgs_b200_hist* h)
 {
     if (!h) return;
-    if (h->ctx && h->ctx->stream) cudaStreamSynchronize(h->ctx->stream);
-    cudaFree(h->S); cudaFree(h->Y); cudaFree(h->ys); cudaFree(h->alpha); cudaFree(h->theta);
-    for (int b = 0; b < 2; b++) { cudaFree(h->SY[b]); cudaFree(h->YY[b]); cudaFree(h->SS[b]); }
+    // (no synchronisation: the blocks go back to the context's pool and everything that used them is ordered on its stream)
+    for (void* p : {h->S, h->Y, h->ys, h->alpha, h->theta, h->SY[0], h->YY[0], h->SS[0], h->SY[1], h->YY[1], h->SS[1]}) pool_free(h->ctx, p);
     delete h;
 }
 

@@ -142,7 +142,7 @@ static void box_free(lbfgs_b200_box* b)
     if (!b) return;
     for (void* p : {b->brk, b->dvec, b->xcp, b->vecc, b->vecy, b->lambda, b->mu, b->tmp, b->tmp2, b->yfb, (void*)b->cls,
                     (void*)b->keys, (void*)b->ord, (void*)b->keys2, (void*)b->ord2, (void*)b->radix_hist, b->block_sums, (void*)b->best, b->small, (void*)b->mg_partials, (void*)b->mg_result})
-        cudaFree(p);
+        pool_free(b->h ? b->h->ctx : nullptr, p);
     delete b;
 }
 
@@ -327,18 +327,18 @@ lbfgs_b200_status lbfgs_b200_box_create(lbfgs_b200_hist* h, lbfgs_b200_box** out
     const int m = h->m, w = 2 * m;
     cudaError_t e = cudaSetDevice(ctx->device);
     for (void** p : {&b->brk, &b->dvec, &b->xcp, &b->vecc, &b->vecy, &b->lambda, &b->mu, &b->tmp, &b->tmp2, &b->yfb})
-        if (e == cudaSuccess) e = cudaMalloc(p, vb);
-    if (e == cudaSuccess) e = cudaMalloc(&b->cls, (size_t)h->ld);
-    if (e == cudaSuccess) e = cudaMalloc(&b->keys, sizeof(unsigned long long) * npad);
-    if (e == cudaSuccess) e = cudaMalloc(&b->ord, sizeof(unsigned) * npad);
-    if (e == cudaSuccess) e = cudaMalloc(&b->keys2, sizeof(unsigned long long) * npad);
-    if (e == cudaSuccess) e = cudaMalloc(&b->ord2, sizeof(unsigned) * npad);
-    if (e == cudaSuccess) e = cudaMalloc(&b->radix_hist, sizeof(unsigned) * (size_t)kRadix * (npad / kSortTile));
-    if (e == cudaSuccess) e = cudaMalloc(&b->block_sums, (size_t)h->elem * (npad / kScanBlock + 1) * (4 * m + 1));
-    if (e == cudaSuccess) e = cudaMalloc(&b->best, sizeof(long long));
-    if (e == cudaSuccess) e = cudaMalloc(&b->small, (size_t)h->elem * (4 * m * m + 4 * m + 5 + w + 16));
-    if (e == cudaSuccess) e = cudaMalloc(&b->mg_partials, sizeof(double) * 2 * ctx->sm_count * w * w);
-    if (e == cudaSuccess) e = cudaMalloc(&b->mg_result, sizeof(double) * w * w);
+        if (e == cudaSuccess) e = pool_alloc(ctx, p, vb);
+    if (e == cudaSuccess) e = pool_alloc(ctx, (void**)&b->cls, (size_t)h->ld);
+    if (e == cudaSuccess) e = pool_alloc(ctx, (void**)&b->keys, sizeof(unsigned long long) * npad);
+    if (e == cudaSuccess) e = pool_alloc(ctx, (void**)&b->ord, sizeof(unsigned) * npad);
+    if (e == cudaSuccess) e = pool_alloc(ctx, (void**)&b->keys2, sizeof(unsigned long long) * npad);
+    if (e == cudaSuccess) e = pool_alloc(ctx, (void**)&b->ord2, sizeof(unsigned) * npad);
+    if (e == cudaSuccess) e = pool_alloc(ctx, (void**)&b->radix_hist, sizeof(unsigned) * (size_t)kRadix * (npad / kSortTile));
+    if (e == cudaSuccess) e = pool_alloc(ctx, (void**)&b->block_sums, (size_t)h->elem * (npad / kScanBlock + 1) * (4 * m + 1));
+    if (e == cudaSuccess) e = pool_alloc(ctx, (void**)&b->best, sizeof(long long));
+    if (e == cudaSuccess) e = pool_alloc(ctx, (void**)&b->small, (size_t)h->elem * (4 * m * m + 4 * m + 5 + w + 16));
+    if (e == cudaSuccess) e = pool_alloc(ctx, (void**)&b->mg_partials, sizeof(double) * 2 * ctx->sm_count * w * w);
+    if (e == cudaSuccess) e = pool_alloc(ctx, (void**)&b->mg_result, sizeof(double) * w * w);
     if (e != cudaSuccess)
     {
         box_free(b);
@@ -350,7 +350,6 @@ lbfgs_b200_status lbfgs_b200_box_create(lbfgs_b200_hist* h, lbfgs_b200_box** out
 
 void lbfgs_b200_box_destroy(lbfgs_b200_box* b)
 {
-    if (b && b->h && b->h->ctx && b->h->ctx->stream) cudaStreamSynchronize(b->h->ctx->stream);
     box_free(b);
 }
 

@@ -95,6 +95,12 @@ template <class T> struct PState
     int lo_virtual;             // the best-so-far point (x_lo, g_lo) is the virtual first trial: materialise it at lo_step if needed
     T lo_step;
     int after_materialize;      // what MATERIALIZE was for: 1 = the accepted trial, 2 = the best-so-far point
+    // speculative pair dots: a COMBINE_TRIAL pass that stores its first trial can also form the pair (s, y) = (x1 - x, g1 - g) that
+    // an ACCEPTED first trial leads to, write it to the free ring slot and take its dots against the history columns it has staged
+    // anyway -- the DOTS_FORM round (2c+4 words, one grid synchronisation) then disappears from that iteration (see p_combine)
+    int spec_policy;            // 0 never, 1 always, 2 iff the previous search accepted its first trial (default)
+    int spec_now;               // the COMBINE_TRIAL round about to run / just run speculates
+    int last_first_accepted;
     // iteration scalars
     T fx, dg, gg, xx, gnorm, step;
     int k;
@@ -113,7 +119,7 @@ template <class T> struct alignas(128) PRound
 {
     T *x, *xp, *g, *gp, *drt;
     T step;
-    int op, c_round, head, pending, gram_cur, store_first;
+    int op, c_round, head, pending, gram_cur, store_first, spec;
 };
 
 struct alignas(128) PCtl
@@ -151,6 +157,8 @@ template <class T> struct PArgs
     const XComm* xc;
     int64_t index_offset, n_global;
     long long wait_cycles;      // watchdog budget of a grid-barrier wait (clock64 ticks); cross-rank waits get 4x, the release wait 6x
+    int tune;                   // experiment switches (LBFGS_B200_TUNE, default 0): 4 = the trial pass stores x, g with L2 evict-first (measured on config 2:
+                                // +3 % on that pass; unrolling it 4x or prefetching its inputs into L2 changed nothing / lost 5 %)
 };
 
 template <class V> __device__ __forceinline__ V ldv(const V* p) { return *reinterpret_cast<const volatile V*>(p); }
@@ -278,14 +286,13 @@ template <int NV> __device__ __forceinline__ void block_sums(const double (&acc)
 // registers with 256-bit loads/stores (a shared-memory staged variant measured slower for this 1:1 read/write pass).
 template <class T, class OBJ, int MODE>
 __device__ __forceinline__ void p_trial(const OBJ& obj, const Own& own, const T* __restrict__ xp, const T* __restrict__ d, T step,
-                                        T* __restrict__ x, T* __restrict__ g, T* __restrict__ dout, PShared& sh, double* dst, int G)
+                                        T* __restrict__ x, T* __restrict__ g, T* __restrict__ dout, PShared& sh, double* dst, int G, int tune)
 {
     T acc[4] = {T(0), T(0), T(0), T(0)};
     const int64_t n = own.n;
     const int64_t p1 = (own.c1 + 3) >> 2;
-#pragma unroll 2
-    for (int64_t q = (own.c0 >> 2) + threadIdx.x; q < p1; q += kPThreads)
-    {
+    const bool evict_first = (tune & 4) != 0;
+    auto body = [&](int64_t q) {
         const int64_t i0 = q << 2;
         const int cnt = (n - i0 >= 4) ? 4 : int(n - i0);
         T xv[4], dv[4] = {T(0), T(0), T(0), T(0)}, gv[4];
@@ -327,10 +334,12 @@ __device__ __forceinline__ void p_trial(const OBJ& obj, const Own& own, const T*
             pg.v[k] = gv[k];
             po.v[k] = (MODE == 1) ? xv[k] : T(-1) * gv[k];
         }
-        if (MODE == 1) store4<T, Hint::Plain, true>(x, i0, cnt, po);
-        else store4<T, Hint::Plain, true>(dout, i0, cnt, po);
-        store4<T, Hint::Plain, true>(g, i0, cnt, pg);
-    }
+        T* const out0 = (MODE == 1) ? x : dout;
+        if (evict_first) { store4<T, Hint::Stream, true>(out0, i0, cnt, po); store4<T, Hint::Stream, true>(g, i0, cnt, pg); }
+        else { store4<T, Hint::Plain, true>(out0, i0, cnt, po); store4<T, Hint::Plain, true>(g, i0, cnt, pg); }
+    };
+#pragma unroll 2
+    for (int64_t q = (own.c0 >> 2) + threadIdx.x; q < p1; q += kPThreads) body(q);
     const double dacc[4] = {(double)acc[0], (double)acc[1], (double)acc[2], (double)acc[3]};
     block_sums<4>(dacc, sh, dst, G);
 }
@@ -651,6 +660,19 @@ __device__ __forceinline__ void p_dots(const PDots<T>& a, const Own& own, T* til
     }
 }
 
+// how the warps of the dots pass share the columns: `split` warps per column pair, cols_per_round column pairs at a time
+__device__ __forceinline__ void dots_geometry(int c, int units, int& split, int& cols_per_round)
+{
+    split = 8;
+    while (split > 1 && (c * split > kGramMaxWarps || units / split < 32)) split >>= 1;
+    cols_per_round = c < kGramMaxWarps / split ? c : kGramMaxWarps / split;
+}
+
+// speculative pair dots of a COMBINE_TRIAL pass (see PState::spec_policy): the pair an accepted first trial would produce takes part
+// as column 0 of a DOTS_FORM pass over c columns, with exactly that pass's thread mapping and summation order (the per-CTA partial
+// sums are bit-identical to the ones a separate DOTS_FORM round would deposit)
+struct PSpec { int on, c, split, cols_per_round, new_slot; };
+
 // ---- COMBINE (+ first trial) ---------------------------------------------------------------------------------------------------
 // d = cv*v + sum_j cy_j*y_j + cs_j*s_j ; FUSE: x1 = xc + d, g1 = grad f(x1) written to (x1_out, g1_out) and the four trial sums.
 // Staged rows of a tile: v, (xc,) then the history block's live slots; sh.slots[j] = packed row of the pair of age j.  A thread owns
@@ -659,19 +681,26 @@ __device__ __forceinline__ void p_dots(const PDots<T>& a, const Own& own, T* til
 // HALO (neighbour-coupled objectives, one GPU): x1 goes back into the staged x row, two spare warps form d and x1 of the element on
 // either side of the tile from global memory with the very arithmetic of the tile that owns it, and after a barrier the objective
 // takes x1_{i-1}, x1_{i+1} from shared memory.
-template <class T, class OBJ, bool FUSE, bool HALO>
+// SPEC (sp.on; FUSE with ROUNDS == 1 only): every stage has one (HALO: two) spare rows after the history block.  After the units of a
+// tile have their x1 and g1, the rows that are no longer needed take s' = x1 - xc (the xc row; HALO: the second spare row), y' = g1 - v
+// (the v row) and g1 (the first spare row), s' and y' also go to ring slot sp.new_slot, and after a barrier the warps take the
+// DOTS_FORM sums [S Y s' y']'[g1 s' y'] from shared memory in the mapping of p_dots.
+template <class T, class OBJ, bool FUSE, bool HALO, bool SPEC>
 __device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, const PHist<T>& h, int c, int end, T* tiles, T* __restrict__ res,
-                                          T* __restrict__ x1_out, T* __restrict__ g1_out, PShared& sh, unsigned& phase_bits, double* dst, int G)
+                                          T* __restrict__ x1_out, T* __restrict__ g1_out, PShared& sh, unsigned& phase_bits, double* dst, int G,
+                                          const PSpec& sp)
 {
     constexpr int EPT = 16 / (int)sizeof(T);
     constexpr int DV = HALO ? OBJ::kDataVectors : 0;              // HALO: the objective's data vectors ride in the stage as well
     constexpr int NRHS = (FUSE ? 2 : 1) + DV;                     // v (, xc) (, data0, data1)
     constexpr int PAD = EPT;                                      // HALO: room for x1 of the neighbouring element on either side of the x row
+    static_assert(!SPEC || FUSE, "speculative pair dots ride on the fused first trial");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int TE = h.BT();
     const SlotRuns runs(end, c, h.M);
     const int nrows = NRHS + 2 * c;
-    const size_t stage_elems = (size_t)nrows * TE + (HALO ? 2 * PAD : 0);
+    constexpr bool spec = SPEC;      // (a separate instantiation: the plain pass keeps its registers)
+    const size_t stage_elems = (size_t)(nrows + (spec ? (HALO ? 2 : 1) : 0)) * TE + (HALO ? 2 * PAD : 0);
     int stages = (int)((size_t)kPStageBytes / (stage_elems * sizeof(T)));
     stages = stages > kPMaxStages ? kPMaxStages : stages;
     const int64_t n = own.n;
@@ -705,6 +734,39 @@ __device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, const 
 
     T acc[5] = {T(0), T(0), T(0), T(0), T(0)};
     T pre[5] = {T(0), T(0), T(0), T(0), T(0)};   // HALO, right-margin warp: operands of the element after the current tile
+    T accd[kGramVals] = {T(0), T(0), T(0), T(0), T(0), T(0)};   // SPEC: this thread's share of column my_col's six sums
+    const int my_col = spec ? warp / sp.split : 0, my_part = spec ? warp % sp.split : 0;
+    const int upp = spec ? (TE / EPT) / sp.split : 0;
+    // the DOTS_FORM sums of one tile from shared-memory rows (p_dots' inner loop, operands already formed)
+    auto spec_dots = [&](const T* g1row, const T* snrow, const T* ynrow, const T* hist, int len) {
+        if (!(my_col < sp.cols_per_round && my_col < sp.c)) return;
+        const bool is_new = my_col == 0;
+        const T* srow = is_new ? snrow : hist + (size_t)2 * sh.slots[my_col - 1] * TE;      // column j >= 1 is the pair of age j - 1 of this pass
+        const T* yrow = is_new ? ynrow : srow + TE;
+        for (int u = my_part * upp + lane; u < (my_part + 1) * upp; u += 32)
+        {
+            const int off = u * EPT;
+            const int cnt = len - off;
+            if (cnt <= 0) break;
+            Unit<T> ug = lds_unit<T>(g1row + off), usn = lds_unit<T>(snrow + off), uyn = lds_unit<T>(ynrow + off);
+            Unit<T> us = lds_unit<T>(srow + off), uy = lds_unit<T>(yrow + off);
+            if (cnt < EPT) { mask_unit(ug, cnt); mask_unit(usn, cnt); mask_unit(uyn, cnt); mask_unit(us, cnt); mask_unit(uy, cnt); }
+#pragma unroll
+            for (int k = 0; k < EPT; k++)
+            {
+                accd[0] += us.v[k] * ug.v[k];
+                accd[1] += uy.v[k] * ug.v[k];
+            }
+#pragma unroll
+            for (int k = 0; k < EPT; k++)
+            {
+                accd[2] += us.v[k] * uyn.v[k];
+                accd[3] += uy.v[k] * uyn.v[k];
+                accd[4] += uy.v[k] * usn.v[k];
+                accd[5] += us.v[k] * usn.v[k];
+            }
+        }
+    };
     __syncthreads();   // sh.vecs / sh.coef / sh.slots are in place and the staging ring is free
     int64_t next_tile = 0;
     for (int s = 0; s < stages; s++, next_tile++)
@@ -781,8 +843,28 @@ __device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, const 
                         st_unit<T>(x1_out, i0, cnt, uo);
                         st_unit<T>(g1_out, i0, cnt, ug);
                     }
+                    if constexpr (SPEC)
+                        if (spec)
+                        {
+                            Unit<T> usn, uyn;
+#pragma unroll
+                            for (int k = 0; k < EPT; k++) { usn.v[k] = xv[k] - ux.v[k]; uyn.v[k] = gv[k] - uv.v[k]; }
+                            if (cnt < EPT) { mask_unit(usn, cnt); mask_unit(uyn, cnt); }
+                            *reinterpret_cast<float4*>(xrow + off) = *reinterpret_cast<const float4*>(usn.v);                 // s' over xc
+                            *reinterpret_cast<float4*>(base + off) = *reinterpret_cast<const float4*>(uyn.v);                 // y' over v
+                            *reinterpret_cast<float4*>(base + (size_t)nrows * TE + off) = *reinterpret_cast<const float4*>(ug.v);   // g1: spare row
+                            T* s_new = h.s_at(sp.new_slot, e0);
+                            st_unit<T>(s_new, off, cnt, usn);
+                            st_unit<T>(s_new + TE, off, cnt, uyn);
+                        }
                 }
             }
+            if constexpr (SPEC)
+                if (spec)
+                {
+                    __syncthreads();
+                    spec_dots(base + (size_t)nrows * TE, xrow, base, hist, len);
+                }
         }
         else
         {
@@ -792,8 +874,9 @@ __device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, const 
             const int64_t i0 = e0 + off;
             const int cnt = mine ? ((len - off >= EPT) ? EPT : (len - off)) : 0;
             T r[EPT];
+            Unit<T> usn_keep;                                      // SPEC: s' = x1 - xc of this thread's unit, formed before x1 replaces xc
 #pragma unroll
-            for (int k = 0; k < EPT; k++) r[k] = T(0);
+            for (int k = 0; k < EPT; k++) { r[k] = T(0); usn_keep.v[k] = T(0); }
             if (mine)
             {
                 Unit<T> uv;
@@ -811,6 +894,12 @@ __device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, const 
 #pragma unroll
                 for (int k = 0; k < EPT; k++) u1.v[k] = (k < cnt) ? ux.v[k] + T(1) * r[k] : T(0);
                 *reinterpret_cast<float4*>(xrow + off) = *reinterpret_cast<const float4*>(u1.v);
+                if constexpr (SPEC)
+                    if (spec)
+                    {
+#pragma unroll
+                        for (int k = 0; k < EPT; k++) usn_keep.v[k] = (k < cnt) ? u1.v[k] - ux.v[k] : T(0);
+                    }
             }
             // the element on either side of the tile.  Left: the previous tile of this chunk left its last x1 in sh.carry (only a chunk's
             // first tile asks global memory).  Right: warp kPWarps-1 holds the operands of the element after the tile (fetched through
@@ -889,7 +978,29 @@ __device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, const 
                     st_unit<T>(x1_out, i0, cnt, uo);
                     st_unit<T>(g1_out, i0, cnt, ug);
                 }
+                if constexpr (SPEC)
+                    if (spec)
+                    {
+                        const Unit<T> uv2 = lds_unit<T>(base + off);
+                        Unit<T> uyn;
+#pragma unroll
+                        for (int k = 0; k < EPT; k++) uyn.v[k] = (k < cnt) ? gv[k] - uv2.v[k] : T(0);
+                        T* g1row = const_cast<T*>(hist) + (size_t)2 * c * TE;
+                        *reinterpret_cast<float4*>(base + off) = *reinterpret_cast<const float4*>(uyn.v);            // y' over v
+                        *reinterpret_cast<float4*>(g1row + off) = *reinterpret_cast<const float4*>(ug.v);            // g1: first spare row
+                        *reinterpret_cast<float4*>(g1row + TE + off) = *reinterpret_cast<const float4*>(usn_keep.v); // s': second spare row
+                        T* s_new = h.s_at(sp.new_slot, e0);
+                        st_unit<T>(s_new, off, cnt, usn_keep);
+                        st_unit<T>(s_new + TE, off, cnt, uyn);
+                    }
             }
+            if constexpr (SPEC)
+                if (spec)
+                {
+                    __syncthreads();
+                    const T* g1row = hist + (size_t)2 * c * TE;
+                    spec_dots(g1row, g1row + TE, base, hist, len);
+                }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
@@ -899,8 +1010,32 @@ __device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, const 
     }
     if (FUSE)
     {
+        double* dst_trial = dst;
+        if constexpr (SPEC)
+            if (spec)
+            {
+                // the dots first (the Gram recursion of the next pass finds them where a DOTS_FORM round leaves them), the five sums of
+                // the trial after them; reduction exactly as at the end of p_dots
+                __syncthreads();   // sh.red may still be read from the previous use
+#pragma unroll
+                for (int k = 0; k < kGramVals; k++)
+                {
+                    const double w = warp_sum((double)accd[k]);
+                    if (lane == 0) sh.red[warp][k] = w;
+                }
+                __syncthreads();
+                const int nvals = sp.c * kGramVals;
+                for (int idx = tid; idx < nvals; idx += kPThreads)
+                {
+                    const int j = idx / kGramVals, k = idx % kGramVals;
+                    double t = 0.0;
+                    for (int p = 0; p < sp.split; p++) t += sh.red[j * sp.split + p][k];
+                    dst[(size_t)idx * G] = t;
+                }
+                dst_trial = dst + (size_t)nvals * G;
+            }
         const double dacc[5] = {(double)acc[0], (double)acc[1], (double)acc[2], (double)acc[3], (double)acc[4]};
-        block_sums<5>(dacc, sh, dst, G);
+        block_sums<5>(dacc, sh, dst_trial, G);
     }
     else
     {
@@ -978,6 +1113,7 @@ template <class T> __device__ __forceinline__ void digest_trial(PState<T>* st, T
     const T step_tried = ls_step_ref(st);
     const int rc = ls_advance(st, fx, dg, keep);
     if (is_first && st->adaptive_first_store) st->first_store = (rc == LBFGSpp::LSC_ACCEPT) ? 1 : 0;
+    if (is_first) st->last_first_accepted = (rc == LBFGSpp::LSC_ACCEPT) ? 1 : 0;
     if (keep)
     {
         if (is_virtual) { st->lo_virtual = 1; st->lo_step = step_tried; }
@@ -1041,7 +1177,36 @@ template <class T> __device__ __forceinline__ bool begin_search(PState<T>* st, T
     return true;
 }
 
-template <class T> __device__ void advance_problem(PState<T>* st, const double* vals)
+// number of columns of the DOTS_FORM pass that follows a search at the current ring state
+template <class T> __device__ __forceinline__ int dots_form_columns(const PState<T>* st) { return st->ncorr < st->m ? st->ncorr + 1 : st->m; }
+
+// the COMBINE(_TRIAL) round about to be scheduled: does it take the speculative pair dots along?  spec_cmax: the largest number of
+// combined columns for which two stages with the spare rows still fit the staging ring (-1: this instantiation cannot speculate)
+template <class T> __device__ __forceinline__ void schedule_combine(PState<T>* st, int spec_cmax)
+{
+    st->op = st->fuse_first_trial ? POP_COMBINE_TRIAL : POP_COMBINE;
+    const bool want = st->spec_policy == 1 || (st->spec_policy == 2 && st->last_first_accepted);
+    st->spec_now = (want && st->fuse_first_trial && st->first_store && st->c_round <= spec_cmax) ? 1 : 0;
+}
+
+// curvature gate on the pair's own dots (age-0 column: [2] = s'y, [3] = y'y), LBFGS.h:161; commit = BFGSMat.h:89-97
+template <class T> __device__ __forceinline__ void after_pair_dots(PState<T>* st, const double* vals, int spec_cmax)
+{
+    const T sy = (T)vals[2], yy = (T)vals[3];
+    if (sy > st->eps_gate * yy)
+    {
+        st->ys[st->head] = sy;
+        *st->theta = yy / sy;
+        st->pending = st->head;
+        st->head = (st->head + 1) % st->M;
+        st->ncorr = st->c_round;
+        schedule_combine(st, spec_cmax);
+    }
+    else if (st->ncorr > 0) { st->op = POP_DOTS_PLAIN; st->c_round = st->ncorr; }
+    else { st->c_round = 0; schedule_combine(st, spec_cmax); }
+}
+
+template <class T> __device__ void advance_problem(PState<T>* st, const double* vals, int spec_cmax)
 {
     st->rounds++;
     switch (st->op)
@@ -1068,36 +1233,31 @@ template <class T> __device__ void advance_problem(PState<T>* st, const double* 
         after_search(st);
         return;
     case POP_DOTS_FORM:
-    {
-        // curvature gate on the pair's own dots (age-0 column: [2] = s'y, [3] = y'y), LBFGS.h:161; commit = BFGSMat.h:89-97
-        const T sy = (T)vals[2], yy = (T)vals[3];
-        if (sy > st->eps_gate * yy)
-        {
-            st->ys[st->head] = sy;
-            *st->theta = yy / sy;
-            st->pending = st->head;
-            st->head = (st->head + 1) % st->M;
-            st->ncorr = st->c_round;
-            st->op = st->fuse_first_trial ? POP_COMBINE_TRIAL : POP_COMBINE;
-        }
-        else if (st->ncorr > 0) { st->op = POP_DOTS_PLAIN; st->c_round = st->ncorr; }
-        else { st->op = st->fuse_first_trial ? POP_COMBINE_TRIAL : POP_COMBINE; st->c_round = 0; }
+        after_pair_dots(st, vals, spec_cmax);
         return;
-    }
     case POP_DOTS_PLAIN:
-        st->op = st->fuse_first_trial ? POP_COMBINE_TRIAL : POP_COMBINE;
+        schedule_combine(st, spec_cmax);
         return;
     case POP_COMBINE:
     case POP_COMBINE_TRIAL:
     {
         const bool fused = st->op == POP_COMBINE_TRIAL;
         const bool stored = st->first_store != 0;      // what this pass was told (the policy flag changes in digest_trial)
+        const bool spec = fused && st->spec_now != 0;  // the pass also left the DOTS_FORM sums of the pair (x1 - x, g1 - g) in vals[0 ..)
+        const double* tv = vals + (spec ? dots_form_columns(st) * kGramVals : 0);   // {g.d, f1, g1.d, g1.g1, x1.x1}
+        st->spec_now = 0;
         if (st->pending >= 0) { st->gram_cur = 1 - st->gram_cur; st->pending = -1; }
-        st->dg = (T)vals[0];                // LBFGS.h:123 for the next pass
+        st->dg = (T)tv[0];                  // LBFGS.h:123 for the next pass
         st->k += 1;
         if (!begin_search(st, T(1))) return;   // LBFGS.h:168
         // the pass already evaluated x + 1*d into the buffers that the rotation just made (x, g)
-        if (fused && ls_step_ref(st) == T(1)) digest_trial(st, (T)vals[1], (T)vals[2], (T)vals[3], (T)vals[4], true, !stored);
+        if (fused && ls_step_ref(st) == T(1))
+        {
+            digest_trial(st, (T)tv[1], (T)tv[2], (T)tv[3], (T)tv[4], true, !stored);
+            // accepted and not converged: the search is over, the pair it leads to is the one the pass formed -- its DOTS_FORM round
+            // has already happened
+            if (spec && st->op == POP_DOTS_FORM) after_pair_dots(st, vals, spec_cmax);
+        }
         return;
     }
     default: return;
@@ -1105,7 +1265,7 @@ template <class T> __device__ void advance_problem(PState<T>* st, const double* 
 }
 
 // n-words a pass has to move (reads + writes of whole vectors): the roofline numerator of the persistent kernel
-__device__ __forceinline__ double words_of(int op, int c, int data_vectors, int store_first)
+__device__ __forceinline__ double words_of(int op, int c, int data_vectors, int store_first, int spec = 0)
 {
     switch (op)
     {
@@ -1115,19 +1275,19 @@ __device__ __forceinline__ double words_of(int op, int c, int data_vectors, int 
     case POP_DOTS_FORM: return 2.0 * c + 4.0;               // R x, xp, g, gp, 2(c-1) columns ; W s, y
     case POP_DOTS_PLAIN: return 2.0 * c + 1.0;              // R g, 2c columns
     case POP_COMBINE: return 2.0 * c + 2.0;                 // R g, 2c columns ; W d
-    case POP_COMBINE_TRIAL: return 2.0 * c + 3.0 + (store_first ? 2.0 : 0.0) + data_vectors;   // R g, x, 2c columns ; W d (, x1, g1)
+    case POP_COMBINE_TRIAL: return 2.0 * c + 3.0 + (store_first ? 2.0 : 0.0) + (spec ? 2.0 : 0.0) + data_vectors;   // R g, x, 2c columns ; W d (, x1, g1) (, s', y')
     default: return 0.0;
     }
 }
 
-__device__ __forceinline__ int nvals_of(int op, int c_round)
+template <class T> __device__ __forceinline__ int nvals_of(const PState<T>* st)
 {
-    switch (op)
+    switch (st->op)
     {
     case POP_FIRST: case POP_TRIAL: case POP_MATERIALIZE: return 4;
-    case POP_DOTS_FORM: case POP_DOTS_PLAIN: return c_round * kGramVals;
+    case POP_DOTS_FORM: case POP_DOTS_PLAIN: return st->c_round * kGramVals;
     case POP_COMBINE: return 1;
-    case POP_COMBINE_TRIAL: return 5;
+    case POP_COMBINE_TRIAL: return 5 + (st->spec_now ? dots_form_columns(st) * kGramVals : 0);
     default: return 0;
     }
 }
@@ -1136,7 +1296,7 @@ __device__ __forceinline__ int nvals_of(int op, int c_round)
 // publication of the next round's descriptors.  Called by all threads of CTA 0 once every CTA has arrived.  Returns (in every
 // thread) the number of problems still running.
 template <class T, bool HALO>
-__device__ int leader_round(const PArgs<T>& a, int G, PShared& sh, PState<T>* cache)
+__device__ int leader_round(const PArgs<T>& a, int G, PShared& sh, PState<T>* cache, int spec_cmax)
 {
     const int tid = threadIdx.x;
     // the leader's working copies: the first kPCache problems live in shared memory for the duration of the kernel
@@ -1147,7 +1307,7 @@ __device__ int leader_round(const PArgs<T>& a, int G, PShared& sh, PState<T>* ca
         PState<T>* st = state_of(b);
         const int op = st->op;           // the pass this problem just ran (advance_problem below moves it on)
         if (op == POP_IDLE) continue;
-        const int nv = nvals_of(op, st->c_round);
+        const int nv = nvals_of(st);
         const double* part = a.partials + (size_t)b * a.pstride * G;
         for (int v0 = 0; v0 < nv; v0 += kPThreads / 16)
         {
@@ -1184,7 +1344,7 @@ __device__ int leader_round(const PArgs<T>& a, int G, PShared& sh, PState<T>* ca
             PState<T>* st = state_of(b);
             const int op = st->op;
             if (op == POP_IDLE) continue;
-            const int nv = nvals_of(op, st->c_round);
+            const int nv = nvals_of(st);
             for (int r = tid; r < R * nv; r += kPThreads)
                 ll_push(xc->inbox[r / nv]->ll[slot][me][ofs + r % nv], st->raw[r % nv], tag);
             ofs += nv;
@@ -1208,7 +1368,7 @@ __device__ int leader_round(const PArgs<T>& a, int G, PShared& sh, PState<T>* ca
             PState<T>* st = state_of(b);
             const int op = st->op;
             if (op == POP_IDLE) continue;
-            const int nv = nvals_of(op, st->c_round);
+            const int nv = nvals_of(st);
             for (int k = tid; k < nv; k += kPThreads)
             {
                 double t = 0.0;
@@ -1246,12 +1406,13 @@ __device__ int leader_round(const PArgs<T>& a, int G, PShared& sh, PState<T>* ca
         if (b < a.B && state_of(b)->op != POP_IDLE)
         {
             PState<T>* st = state_of(b);
-            advance_problem(st, st->raw);
+            advance_problem(st, st->raw, spec_cmax);
             PRound<T>* rd = a.rounds + b;
             rd->x = st->x; rd->xp = st->xp; rd->g = st->g; rd->gp = st->gp; rd->drt = st->drt;
             rd->step = st->step;
             rd->c_round = st->c_round; rd->head = st->head; rd->pending = st->pending; rd->gram_cur = st->gram_cur;
             rd->store_first = st->first_store;
+            rd->spec = st->spec_now;
             rd->op = st->op;
             running = st->op != POP_IDLE;
         }
@@ -1327,6 +1488,15 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
     __shared__ unsigned s_release;
     __shared__ PState<T> s_state[kPCache];     // CTA 0: working copies of the first problems' states (scalar logic at shared-memory latency)
     const int ncache = a.B < kPCache ? a.B : kPCache;
+    // speculative pair dots (PSpec): the largest number of combined columns for which two stages with the spare rows fit the ring
+    int spec_cmax = -1;
+    if (ROUNDS == 1)
+    {
+        constexpr int EPT = 16 / (int)sizeof(T);
+        constexpr int NRHS_CT = 2 + (HALO ? kDataVectors : 0);
+        for (int c = 0; c <= kMaxM; c++)
+            if (2 * (((size_t)(NRHS_CT + 2 * c + (HALO ? 2 : 1)) << a.probs[0].hist.bt_log) + (HALO ? 2 * EPT : 0)) * sizeof(T) <= (size_t)kPStageBytes) spec_cmax = c;
+    }
     if (cta == 0)
     {
         const unsigned* src = reinterpret_cast<const unsigned*>(a.probs);
@@ -1403,20 +1573,21 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
             const T step = ldv(&rd->step);
             const int c_round = ldv(&rd->c_round), head = ldv(&rd->head), pending = ldv(&rd->pending), gram_cur = ldv(&rd->gram_cur);
             const int store_first = ldv(&rd->store_first);
+            const int spec_round = ldv(&rd->spec);
             acct_bucket = (acct_bucket == -1 || acct_bucket == op) ? op : 0;
-            acct_words += words_of(op, c_round, kDataVectors, store_first);
+            acct_words += words_of(op, c_round, kDataVectors, store_first, spec_round);
             double* dst = a.partials + (size_t)b * a.pstride * G + cta;
             const OBJ obj = PObjMaker<T, OBJ>::make(a, st->data0, st->data1, (HALO && a.xc != nullptr) ? st->halo : nullptr);
             switch (op)
             {
             case POP_FIRST:
                 if constexpr (HALO) p_trial_halo<T, OBJ, 0>(obj, own, nullptr, nullptr, T(0), vx, vg, vd, tiles, sh, phase_bits, dst, G);
-                else p_trial<T, OBJ, 0>(obj, own, nullptr, nullptr, T(0), vx, vg, vd, sh, dst, G);
+                else p_trial<T, OBJ, 0>(obj, own, nullptr, nullptr, T(0), vx, vg, vd, sh, dst, G, a.tune);
                 break;
             case POP_TRIAL:
             case POP_MATERIALIZE:
                 if constexpr (HALO) p_trial_halo<T, OBJ, 1>(obj, own, vxp, vd, step, vx, vg, nullptr, tiles, sh, phase_bits, dst, G);
-                else p_trial<T, OBJ, 1>(obj, own, vxp, vd, step, vx, vg, nullptr, sh, dst, G);
+                else p_trial<T, OBJ, 1>(obj, own, vxp, vd, step, vx, vg, nullptr, sh, dst, G, a.tune);
                 break;
             case POP_RESTORE:
                 p_restore<T>(own, vxp, vgp, vx, vg);
@@ -1430,11 +1601,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
                 d.end = head;                                   // the old columns: the slots below the free slot `head`
                 d.cnt_old = form ? c_round - 1 : c_round;
                 d.new_slot = form ? head : -1;
-                const int units = d.h.BT() / (16 / (int)sizeof(T));
-                int split = 8;
-                while (split > 1 && (d.c * split > kGramMaxWarps || units / split < 32)) split >>= 1;
-                d.split = split;
-                d.cols_per_round = d.c < kGramMaxWarps / split ? d.c : kGramMaxWarps / split;
+                dots_geometry(d.c, d.h.BT() / (16 / (int)sizeof(T)), d.split, d.cols_per_round);
                 __syncthreads();   // sh.slots / sh.vecs may still be read by the previous problem's pass
                 {
                     const SlotRuns runs(d.end, d.cnt_old, d.h.M);
@@ -1476,19 +1643,26 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
                     }
                     if (tid == 0) { sh.vecs[0] = vg; sh.vecs[1] = vx; sh.vecs[2] = st->data0; sh.vecs[3] = st->data1; }
                 }
-                if (fuse)
+                PSpec sp{0, 0, 1, 1, head};
+                if (fuse && spec_round && store_first)
                 {
-                    if constexpr (OBJ::kHalo) p_combine<T, OBJ, true, true>(obj, own, st->hist, g.c, head, tiles, vd, store_first ? vxp : nullptr, store_first ? vgp : nullptr, sh, phase_bits, dst, G);
-                    else p_combine<T, OBJ, true, false>(obj, own, st->hist, g.c, head, tiles, vd, store_first ? vxp : nullptr, store_first ? vgp : nullptr, sh, phase_bits, dst, G);
+                    sp.on = 1;
+                    sp.c = g.c + 1 < g.M - 1 ? g.c + 1 : g.M - 1;      // = dots_form_columns: the new pair + the newest old ones (M = m + 1)
+                    dots_geometry(sp.c, st->hist.BT() / (16 / (int)sizeof(T)), sp.split, sp.cols_per_round);
                 }
-                else p_combine<T, OBJ, false, false>(obj, own, st->hist, g.c, head, tiles, vd, nullptr, nullptr, sh, phase_bits, dst, G);
+                if (fuse && sp.on)
+                {
+                    if constexpr (ROUNDS == 1) p_combine<T, OBJ, true, OBJ::kHalo, true>(obj, own, st->hist, g.c, head, tiles, vd, vxp, vgp, sh, phase_bits, dst, G, sp);
+                }
+                else if (fuse) p_combine<T, OBJ, true, OBJ::kHalo, false>(obj, own, st->hist, g.c, head, tiles, vd, store_first ? vxp : nullptr, store_first ? vgp : nullptr, sh, phase_bits, dst, G, sp);
+                else p_combine<T, OBJ, false, false, false>(obj, own, st->hist, g.c, head, tiles, vd, nullptr, nullptr, sh, phase_bits, dst, G, sp);
                 break;
             }
             default: break;
             }
         }
         if (acct_bucket < 0) acct_bucket = 0;
-        if (grid_barrier([&]() { return leader_round<T, HALO>(a, G, sh, s_state) == 0 || ldv(&a.ctl->abort) != 0; })) break;
+        if (grid_barrier([&]() { return leader_round<T, HALO>(a, G, sh, s_state, spec_cmax) == 0 || ldv(&a.ctl->abort) != 0; })) break;
     }
     if (cta == 0)
     {

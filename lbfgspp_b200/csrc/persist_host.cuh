@@ -86,9 +86,9 @@ static lbfgs_b200_status solver_minimize(lbfgs_b200_solver* s, int objective, co
 
     if (trace_host && trace_cap > s->trace_cap)
     {
-        cudaFree(s->d_trace);
+        pool_free(ctx, s->d_trace);
         s->d_trace = nullptr;
-        CU(ctx, cudaMalloc(&s->d_trace, sizeof(double) * (size_t)trace_cap));
+        CU(ctx, pool_alloc(ctx, (void**)&s->d_trace, sizeof(double) * (size_t)trace_cap));
         s->trace_cap = trace_cap;
     }
 
@@ -122,6 +122,9 @@ static lbfgs_b200_status solver_minimize(lbfgs_b200_solver* s, int objective, co
         p.fuse_first_trial = (coupled && ctx->nranks > 1) ? 0 : 1;
         p.adaptive_first_store = (getenv("LBFGS_B200_VIRTUAL_FIRST_TRIAL") && atoi(getenv("LBFGS_B200_VIRTUAL_FIRST_TRIAL")) != 0) ? 1 : 0;
         p.first_store = p.adaptive_first_store ? 0 : 1;
+        p.spec_policy = 0;                       // speculative pair dots: off (LBFGS_B200_SPECULATE = 1 always, 2 iff the previous search accepted its first trial)
+        if (const char* e = getenv("LBFGS_B200_SPECULATE")) { const int v = atoi(e); if (v >= 0 && v <= 2) p.spec_policy = v; }
+        p.spec_now = 0; p.last_first_accepted = 0;
         p.ls_opt.linesearch = (ls_kind == 3) ? 3 : prm->linesearch;
         p.ls_opt.max_linesearch = prm->max_linesearch;
         p.ls_opt.min_step = (T)prm->min_step; p.ls_opt.max_step = (T)prm->max_step; p.ls_opt.ftol = (T)prm->ftol; p.ls_opt.wolfe = (T)prm->wolfe;
@@ -135,7 +138,7 @@ static lbfgs_b200_status solver_minimize(lbfgs_b200_solver* s, int objective, co
     {
         const PState<T>& p = hs[b];
         hr[b].x = p.x; hr[b].xp = p.xp; hr[b].g = p.g; hr[b].gp = p.gp; hr[b].drt = p.drt;
-        hr[b].step = T(0); hr[b].op = p.op; hr[b].c_round = 0; hr[b].head = 0; hr[b].pending = -1; hr[b].gram_cur = p.gram_cur; hr[b].store_first = p.first_store;
+        hr[b].step = T(0); hr[b].op = p.op; hr[b].c_round = 0; hr[b].head = 0; hr[b].pending = -1; hr[b].gram_cur = p.gram_cur; hr[b].store_first = p.first_store; hr[b].spec = 0;
     }
     // BFGSMat::reset (BFGSMat.h:61-78): no pairs, theta = 1, Gram matrices cleared
     CU(ctx, cudaMemsetAsync(s->d_small, 0, sizeof(T) * s->small_elems * (size_t)B, ctx->stream));
@@ -165,6 +168,8 @@ static lbfgs_b200_status solver_minimize(lbfgs_b200_solver* s, int objective, co
     a.index_offset = index_offset; a.n_global = n_global;
     a.wait_cycles = kPWaitCycles;
     if (const char* e = getenv("LBFGS_B200_WATCHDOG_SCALE")) { const long long k = atoll(e); if (k >= 1 && k <= 100000) a.wait_cycles *= k; }
+    a.tune = 0;
+    if (const char* e = getenv("LBFGS_B200_TUNE")) a.tune = atoi(e);
     void* kargs[] = {&a};
     CU(ctx, cudaEventRecord(s->ev0, ctx->stream));
     CU(ctx, cudaLaunchCooperativeKernel(kernel, dim3((unsigned)grid), dim3(kPThreads), kargs, smem, ctx->stream));
@@ -262,8 +267,9 @@ lbfgs_b200_status lbfgs_b200_solver_create_batch(lbfgs_b200_ctx* ctx, int64_t n,
     s->M = m + 1;
     // block length of the tiled history: the largest power of two for which two stages of 2m+4 rows fit the kernel's staging ring
     {
-        int bt = 1024;
-        while (bt > 32 && (size_t)2 * (2 * m + 4) * bt * elem_bytes > (size_t)lb::kPStageBytes) bt >>= 1;
+        int bt = 1024, want_stages = 2;
+        if (const char* e = getenv("LBFGS_B200_STAGES")) { const int v = atoi(e); if (v >= 1 && v <= lb::kPMaxStages) want_stages = v; }
+        while (bt > 32 && (size_t)want_stages * (2 * m + 4) * bt * elem_bytes > (size_t)lb::kPStageBytes) bt >>= 1;
         s->bt_log = 0;
         while ((1 << s->bt_log) < bt) s->bt_log++;
     }
@@ -274,17 +280,17 @@ lbfgs_b200_status lbfgs_b200_solver_create_batch(lbfgs_b200_ctx* ctx, int64_t n,
     s->exported.assign((size_t)batch, nullptr); s->export_fresh.assign((size_t)batch, 0);
     cudaError_t e = cudaSuccess;
     s->vec_elems = (((size_t)n * elem_bytes + 255) & ~size_t(255)) / elem_bytes;
-    s->pstride = ((m * lb::kGramVals > 8 ? m * lb::kGramVals : 8) + 7) & ~7;
+    s->pstride = (m * lb::kGramVals + 5 + 7) & ~7;      // a dots pass leaves 6 sums per column pair, a combination pass with speculative pair dots 5 more
     const size_t state_bytes = (elem_bytes == 8 ? sizeof(lb::PState<double>) : sizeof(lb::PState<float>)) * (size_t)batch;
-    if (e == cudaSuccess) e = cudaMalloc(&s->vec_slab, (size_t)batch * 7 * s->vec_elems * elem_bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_hist, (size_t)batch * s->hist_elems * elem_bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_small, (size_t)batch * s->small_elems * elem_bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_state, state_bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_rounds, (elem_bytes == 8 ? sizeof(lb::PRound<double>) : sizeof(lb::PRound<float>)) * (size_t)batch);
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_ctl, sizeof(lb::PCtl));
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_partials, sizeof(double) * (size_t)batch * s->pstride * ctx->sm_count);
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_raw, sizeof(double) * (size_t)batch * s->pstride);
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_halo, sizeof(double) * (size_t)batch * lb::kHaloDoubles);
+    if (e == cudaSuccess) e = pool_alloc(ctx, (void**)&s->vec_slab, (size_t)batch * 7 * s->vec_elems * elem_bytes);
+    if (e == cudaSuccess) e = pool_alloc(ctx, (void**)&s->d_hist, (size_t)batch * s->hist_elems * elem_bytes);
+    if (e == cudaSuccess) e = pool_alloc(ctx, (void**)&s->d_small, (size_t)batch * s->small_elems * elem_bytes);
+    if (e == cudaSuccess) e = pool_alloc(ctx, (void**)&s->d_state, state_bytes);
+    if (e == cudaSuccess) e = pool_alloc(ctx, (void**)&s->d_rounds, (elem_bytes == 8 ? sizeof(lb::PRound<double>) : sizeof(lb::PRound<float>)) * (size_t)batch);
+    if (e == cudaSuccess) e = pool_alloc(ctx, (void**)&s->d_ctl, sizeof(lb::PCtl));
+    if (e == cudaSuccess) e = pool_alloc(ctx, (void**)&s->d_partials, sizeof(double) * (size_t)batch * s->pstride * ctx->sm_count);
+    if (e == cudaSuccess) e = pool_alloc(ctx, (void**)&s->d_raw, sizeof(double) * (size_t)batch * s->pstride);
+    if (e == cudaSuccess) e = pool_alloc(ctx, (void**)&s->d_halo, sizeof(double) * (size_t)batch * lb::kHaloDoubles);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
     if (e != cudaSuccess)
@@ -304,19 +310,12 @@ lbfgs_b200_status lbfgs_b200_solver_create(lbfgs_b200_ctx* ctx, int64_t n, int m
 void lbfgs_b200_solver_destroy(lbfgs_b200_solver* s)
 {
     if (!s) return;
-    if (s->ctx && s->ctx->stream) cudaStreamSynchronize(s->ctx->stream);
-    cudaFree(s->vec_slab);
-    cudaFree(s->d_state);
-    cudaFree(s->d_rounds);
-    cudaFree(s->d_ctl);
-    cudaFree(s->d_partials);
-    cudaFree(s->d_raw);
-    cudaFree(s->d_halo);
-    cudaFree(s->d_trace);
+    if (s->ctx && s->ctx->stream) cudaStreamSynchronize(s->ctx->stream);   // the events below must not be in use
+    for (void* p : {(void*)s->vec_slab, (void*)s->d_state, (void*)s->d_rounds, (void*)s->d_ctl, (void*)s->d_partials, (void*)s->d_raw, (void*)s->d_halo,
+                    (void*)s->d_trace, (void*)s->d_hist, (void*)s->d_small})
+        pool_free(s->ctx, p);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
-    cudaFree(s->d_hist);
-    cudaFree(s->d_small);
     for (lbfgs_b200_hist* h : s->exported) lbfgs_b200_hist_destroy(h);
     delete s;
 }

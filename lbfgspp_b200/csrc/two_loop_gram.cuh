@@ -412,8 +412,8 @@ template <class T> struct GramSolveArgs
     unsigned char slots[kMaxM];
 };
 
-// smem layout (T units): SY[c*c] | YY[c*c] | coef[2c+1] | alpha[c] | a*S'v[c] | a*Y'v[c] | ys[c] ; everything indexed by AGE (0 = newest).
-inline size_t gram_solve_smem_elems(int c) { return (size_t)2 * c * c + 6 * c + 1; }
+// smem layout (T units): SY[c*c] | YY[c*c] | coef[2c+1] | alpha[c] | a*S'v[c] | a*Y'v[c] | ys[c] | theta ; everything indexed by AGE (0 = newest).
+inline size_t gram_solve_smem_elems(int c) { return (size_t)2 * c * c + 6 * c + 2; }
 
 // All global reads go through L2 (__ldcg): inside the persistent solve these scalars are rewritten by another CTA between rounds.
 template <class T>
@@ -447,60 +447,71 @@ __device__ void gram_solve_in_smem(const GramSolveArgs<T>& g, T* sm, bool writer
             g.SS_out[pi * M + pj] = ss;
         }
     }
-    // right-hand sides and ys by age next to the matrices (one global read each instead of one per use)
+    // right-hand sides, ys and theta by age next to the matrices: fetched by the LAST threads of the block, so that their L2 round trip
+    // overlaps the matrices' (the first threads') instead of following it
     T* b0 = al + c;        // a * s_i'v
     T* b1 = b0 + c;        // a * y_i'v
     T* ysv = b1 + c;
+    T* th = ysv + c;       // theta
     if (g.with_v)
-        for (int i = tid; i < c; i += nt)
+    {
+        for (int i = nt - 1 - tid; i < c; i += nt)
         {
             b0[i] = g.a * (T)__ldcg(g.raw + i * kGramVals + 0);
             b1[i] = g.a * (T)__ldcg(g.raw + i * kGramVals + 1);
             ysv[i] = (g.slots[i] == g.ov_slot) ? g.ov_ys : __ldcg(g.ys + g.slots[i]);
         }
+        if (tid == nt - 1) th[0] = g.ov_theta_on ? g.ov_theta : __ldcg(g.theta);
+    }
     __syncthreads();
     if (tid < 32 && g.with_v)
     {
-        // One warp runs the recursion: the sweeps are sequential in i, the inner products over t are spread over the lanes and
-        // summed by a fixed shuffle tree (deterministic; ~10x shorter critical path than one thread at c = 20).
+        // One warp runs the two triangular sweeps COLUMN by column: lane t owns the entries t and t + 32 of the running right-hand
+        // side; a step is { multiply the pivot entry by 1/ys, broadcast it (one shuffle), one multiply-subtract per lane } -- no
+        // reduction tree, no division and no shared-memory round trip on the critical path (~50 cycles per step instead of ~400
+        // for the row-oriented sweep with a shuffle tree and a division per step; measured 16 us -> ~1 us at c = 20).
         const int lane = tid;
-        const T theta = g.ov_theta_on ? g.ov_theta : __ldcg(g.theta);
-        auto lanes_sum = [](T v) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            return v;
-        };
+        const T theta = th[0];
+        const int tA = lane, tB = lane + 32;
+        const bool hasA = tA < c, hasB = tB < c;
+        const T rA = hasA ? T(1) / ysv[tA] : T(0), rB = hasB ? T(1) / ysv[tB] : T(0);
         // backward sweep (BFGSMat.h:285-290): alpha_i = s_i'q / ys_i with q = a*v - sum_{newer t} alpha_t y_t
+        //   acc_t = a*s_t'v - sum_{i < t} alpha_i s_t'y_i, subtracted in the order i = 0, 1, ... (the order q is built in)
+        T accA = hasA ? b0[tA] : T(0), accB = hasB ? b0[tB] : T(0);
+        T alA = T(0), alB = T(0);
         for (int i = 0; i < c; i++)
         {
-            T part = T(0);
-            for (int t = lane; t < i; t += 32) part += al[t] * sSY[i * c + t];
-            const T sum = lanes_sum(part);
-            if (lane == 0) al[i] = (b0[i] - sum) / ysv[i];
-            __syncwarp();
+            const bool hi = i >= 32;
+            const T mine = hi ? accB * rB : accA * rA;
+            const T ai = __shfl_sync(0xffffffffu, mine, i & 31);
+            if (lane == (i & 31)) { if (hi) alB = ai; else alA = ai; }
+            if (hasA && tA > i) accA -= ai * sSY[tA * c + i];
+            if (hasB && tB > i) accB -= ai * sSY[tB * c + i];
         }
+        if (hasA) al[tA] = alA;
+        if (hasB) al[tB] = alB;
+        __syncwarp();
         // forward sweep (BFGSMat.h:293-301): r = q/theta + sum_{older t} (alpha_t - beta_t) s_t ; beta_i = y_i'r / ys_i
+        //   w_i = (a*y_i'v - sum_t alpha_t y_i'y_t) / theta : independent of the sweep, every lane does its own (Y'Y is symmetric:
+        //   lane i reads column i, consecutive addresses across lanes)
+        T wA = T(0), wB = T(0);
+        if (hasA) { T z = T(0); for (int t = 0; t < c; t++) z += al[t] * sYY[t * c + tA]; wA = (b1[tA] - z) / theta; }
+        if (hasB) { T z = T(0); for (int t = 0; t < c; t++) z += al[t] * sYY[t * c + tB]; wB = (b1[tB] - z) / theta; }
+        //   then w_t += cs_i * s_i'y_t for the older i = c-1 .. t+1, cs_i = alpha_i - w_i / ys_i
         T* cs = coef + 1 + c;
+        T csA = T(0), csB = T(0);
         for (int i = c - 1; i >= 0; i--)
         {
-            T p1 = T(0), p2 = T(0);
-            for (int t = lane; t < c; t += 32) p1 += al[t] * sYY[i * c + t];
-            for (int t = i + 1 + lane; t < c; t += 32) p2 += cs[t] * sSY[t * c + i];
-            const T s1 = lanes_sum(p1), s2 = lanes_sum(p2);
-            if (lane == 0)
-            {
-                const T yr = (b1[i] - s1) / theta + s2;
-                const T beta = yr / ysv[i];
-                cs[i] = al[i] - beta;
-            }
-            __syncwarp();
+            const bool hi = i >= 32;
+            const T mine = hi ? alB - wB * rB : alA - wA * rA;
+            const T ci = __shfl_sync(0xffffffffu, mine, i & 31);
+            if (lane == (i & 31)) { if (hi) csB = ci; else csA = ci; }
+            if (hasA && tA < i) wA += ci * sSY[i * c + tA];
+            if (hasB && tB < i) wB += ci * sSY[i * c + tB];
         }
+        if (hasA) { cs[tA] = csA; coef[1 + tA] = -(alA / theta); if (writer) g.alpha[g.slots[tA]] = alA; }
+        if (hasB) { cs[tB] = csB; coef[1 + tB] = -(alB / theta); if (writer) g.alpha[g.slots[tB]] = alB; }
         if (lane == 0) coef[0] = g.a / theta;
-        for (int i = lane; i < c; i += 32)
-        {
-            coef[1 + i] = -(al[i] / theta);
-            if (writer) g.alpha[g.slots[i]] = al[i];
-        }
     }
     __syncthreads();
 }

@@ -440,6 +440,7 @@ lbfgs_b200_status lbfgs_b200_malloc(lbfgs_b200_ctx* ctx, void** p, size_t bytes)
     return *p ? LBFGS_B200_OK : fail(ctx, LBFGS_B200_ERR_ALLOC, "out of memory");
 }
 lbfgs_b200_status lbfgs_b200_free(lbfgs_b200_ctx*, void* p) { std::free(p); return LBFGS_B200_OK; }
+lbfgs_b200_status lbfgs_b200_trim(lbfgs_b200_ctx*) { return LBFGS_B200_OK; }
 lbfgs_b200_status lbfgs_b200_malloc_host(lbfgs_b200_ctx* ctx, void** p, size_t bytes) { return lbfgs_b200_malloc(ctx, p, bytes); }
 lbfgs_b200_status lbfgs_b200_free_host(lbfgs_b200_ctx*, void* p) { std::free(p); return LBFGS_B200_OK; }
 lbfgs_b200_status lbfgs_b200_memcpy_h2d(lbfgs_b200_ctx*, void* d, const void* s, size_t b) { std::memcpy(d, s, b); return LBFGS_B200_OK; }
