@@ -45,6 +45,7 @@ constexpr int kPCache = 4;                   // problems whose leader-side state
 enum { POP_IDLE = 0, POP_FIRST = 1, POP_TRIAL = 2, POP_DOTS_FORM = 3, POP_DOTS_PLAIN = 4, POP_COMBINE = 5, POP_COMBINE_TRIAL = 6, POP_RESTORE = 7,
        POP_MATERIALIZE = 8 };
 constexpr int kPOps = 10;   // accounting slots (ops + the "mixed" bucket 0)
+constexpr int kPGramScratch = 1024;   // doubles
 
 // ---- the S/Y history of the solve: tiled layout ---------------------------------------------------------------------------------
 // H[block][slot][S|Y][BT]: all ring slots of one block of BT coordinates lie next to each other (BT = the largest power of two for
@@ -157,8 +158,9 @@ template <class T> struct PArgs
     const XComm* xc;
     int64_t index_offset, n_global;
     long long wait_cycles;      // watchdog budget of a grid-barrier wait (clock64 ticks); cross-rank waits get 4x, the release wait 6x
-    int tune;                   // experiment switches (LBFGS_B200_TUNE, default 0): 4 = the trial pass stores x, g with L2 evict-first (measured on config 2:
-                                // +3 % on that pass; unrolling it 4x or prefetching its inputs into L2 changed nothing / lost 5 %)
+    int tune;                   // 4 = the trial pass stores x, g with L2 evict-first: +3 % on that pass at n = 1e7 (set by the host when the vectors cannot stay
+                                // in L2 anyway; LBFGS_B200_TUNE overrides).  Measured and dropped: unrolling the pass 4x (no change), prefetching its inputs
+                                // into L2 (-5 %), a grid-stride instead of a chunked sweep (+1 %)
 };
 
 template <class V> __device__ __forceinline__ V ldv(const V* p) { return *reinterpret_cast<const volatile V*>(p); }
@@ -685,10 +687,12 @@ struct PSpec { int on, c, split, cols_per_round, new_slot; };
 // tile have their x1 and g1, the rows that are no longer needed take s' = x1 - xc (the xc row; HALO: the second spare row), y' = g1 - v
 // (the v row) and g1 (the first spare row), s' and y' also go to ring slot sp.new_slot, and after a barrier the warps take the
 // DOTS_FORM sums [S Y s' y']'[g1 s' y'] from shared memory in the mapping of p_dots.
-template <class T, class OBJ, bool FUSE, bool HALO, bool SPEC>
+// `between` (all threads) runs after the bulk copies of the first tiles have been issued and before anything reads the coefficients:
+// the coefficient recursion overlaps the latency of those copies when it has a scratch area of its own.
+template <class T, class OBJ, bool FUSE, bool HALO, bool SPEC, class Between>
 __device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, const PHist<T>& h, int c, int end, T* tiles, T* __restrict__ res,
                                           T* __restrict__ x1_out, T* __restrict__ g1_out, PShared& sh, unsigned& phase_bits, double* dst, int G,
-                                          const PSpec& sp)
+                                          const PSpec& sp, Between between)
 {
     constexpr int EPT = 16 / (int)sizeof(T);
     constexpr int DV = HALO ? OBJ::kDataVectors : 0;              // HALO: the objective's data vectors ride in the stage as well
@@ -767,10 +771,11 @@ __device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, const 
             }
         }
     };
-    __syncthreads();   // sh.vecs / sh.coef / sh.slots are in place and the staging ring is free
+    __syncthreads();   // sh.vecs / sh.slots are in place and the staging ring is free
     int64_t next_tile = 0;
     for (int s = 0; s < stages; s++, next_tile++)
         if (next_tile < ntl) stage_one(next_tile, s);
+    between();         // (ends with a barrier: sh.coef is in place)
     const T cv = s_coef[0];
     int stage = 0;
     for (int64_t t = 0; t < ntl; t++)
@@ -1486,6 +1491,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
     int acct_bucket = 0;
     double acct_words = 0.0;
     __shared__ unsigned s_release;
+    __shared__ __align__(16) double s_gram[kPGramScratch];   // the coefficient recursion's own scratch (c <= 21: it then runs while the first tiles of the pass are in flight)
     __shared__ PState<T> s_state[kPCache];     // CTA 0: working copies of the first problems' states (scalar logic at shared-memory latency)
     const int ncache = a.B < kPCache ? a.B : kPCache;
     // speculative pair dots (PSpec): the largest number of combined columns for which two stages with the spare rows fit the ring
@@ -1566,14 +1572,17 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
         for (int b = 0; b < a.B; b++)
         {
             const PRound<T>* rd = a.rounds + b;
-            const int op = (a.B > 1) ? (int)sh.ops[b] : ldv(&rd->op);   // a single problem: the op travels with the rest of the descriptor
-            if (op == POP_IDLE) continue;
+            if (a.B > 1 && sh.ops[b] == POP_IDLE) continue;
+            // a single problem: the op travels with the rest of the descriptor, and all its fields are requested before the first one is
+            // looked at (one trip to L2 per round instead of two)
+            const int op = (a.B > 1) ? (int)sh.ops[b] : ldv(&rd->op);
             const PState<T>* st = a.probs + b;     // fields that are fixed for the duration of the kernel only
             T* const vx = ldv(&rd->x); T* const vxp = ldv(&rd->xp); T* const vg = ldv(&rd->g); T* const vgp = ldv(&rd->gp); T* const vd = ldv(&rd->drt);
             const T step = ldv(&rd->step);
             const int c_round = ldv(&rd->c_round), head = ldv(&rd->head), pending = ldv(&rd->pending), gram_cur = ldv(&rd->gram_cur);
             const int store_first = ldv(&rd->store_first);
             const int spec_round = ldv(&rd->spec);
+            if (op == POP_IDLE) continue;
             acct_bucket = (acct_bucket == -1 || acct_bucket == op) ? op : 0;
             acct_words += words_of(op, c_round, kDataVectors, store_first, spec_round);
             double* dst = a.partials + (size_t)b * a.pstride * G + cta;
@@ -1628,13 +1637,9 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
                 g.ov_slot = -1; g.ov_theta_on = 0;
                 for (int age = 0; age < g.c; age++) g.slots[age] = (unsigned char)slot_by_age(head, g.M, age);
                 __syncthreads();   // the tile area / tables may still be in use by the previous problem's pass
-                gram_solve_in_smem<T>(g, tiles, cta == 0);
-                // coefficients out of the tile area (the staging ring is about to overwrite it); per age: packed row and ring slot
+                // per age: packed row of the column in a staged block, and its ring slot
                 const bool fuse = op == POP_COMBINE_TRIAL;
                 {
-                    const T* s_coef = tiles + 2 * g.c * g.c;
-                    T* keep = reinterpret_cast<T*>(sh.coef);
-                    for (int q = tid; q < 2 * g.c + 1; q += kPThreads) keep[q] = s_coef[q];
                     const SlotRuns runs(head, g.c, g.M);
                     for (int j = tid; j < g.c; j += kPThreads)
                     {
@@ -1643,6 +1648,17 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
                     }
                     if (tid == 0) { sh.vecs[0] = vg; sh.vecs[1] = vx; sh.vecs[2] = st->data0; sh.vecs[3] = st->data1; }
                 }
+                // the coefficient recursion (every CTA; CTA 0 also writes the folded Gram matrices back) and its 2c+1 results into sh.coef
+                const bool own_scratch = gram_solve_smem_elems(g.c) * sizeof(T) <= sizeof(s_gram);
+                auto solve_into = [&](T* scratch) {
+                    gram_solve_in_smem<T>(g, scratch, cta == 0);
+                    const T* s_coef = scratch + 2 * g.c * g.c;
+                    T* keep = reinterpret_cast<T*>(sh.coef);
+                    for (int q = tid; q < 2 * g.c + 1; q += kPThreads) keep[q] = s_coef[q];
+                    __syncthreads();
+                };
+                if (!own_scratch) solve_into(tiles);   // a long history: the staging ring is the scratch, the copies start afterwards
+                auto between = [&]() { if (own_scratch) solve_into(reinterpret_cast<T*>(s_gram)); };
                 PSpec sp{0, 0, 1, 1, head};
                 if (fuse && spec_round && store_first)
                 {
@@ -1652,10 +1668,10 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
                 }
                 if (fuse && sp.on)
                 {
-                    if constexpr (ROUNDS == 1) p_combine<T, OBJ, true, OBJ::kHalo, true>(obj, own, st->hist, g.c, head, tiles, vd, vxp, vgp, sh, phase_bits, dst, G, sp);
+                    if constexpr (ROUNDS == 1) p_combine<T, OBJ, true, OBJ::kHalo, true>(obj, own, st->hist, g.c, head, tiles, vd, vxp, vgp, sh, phase_bits, dst, G, sp, between);
                 }
-                else if (fuse) p_combine<T, OBJ, true, OBJ::kHalo, false>(obj, own, st->hist, g.c, head, tiles, vd, store_first ? vxp : nullptr, store_first ? vgp : nullptr, sh, phase_bits, dst, G, sp);
-                else p_combine<T, OBJ, false, false, false>(obj, own, st->hist, g.c, head, tiles, vd, nullptr, nullptr, sh, phase_bits, dst, G, sp);
+                else if (fuse) p_combine<T, OBJ, true, OBJ::kHalo, false>(obj, own, st->hist, g.c, head, tiles, vd, store_first ? vxp : nullptr, store_first ? vgp : nullptr, sh, phase_bits, dst, G, sp, between);
+                else p_combine<T, OBJ, false, false, false>(obj, own, st->hist, g.c, head, tiles, vd, nullptr, nullptr, sh, phase_bits, dst, G, sp, between);
                 break;
             }
             default: break;

@@ -413,7 +413,7 @@ template <class T> struct GramSolveArgs
 };
 
 // smem layout (T units): SY[c*c] | YY[c*c] | coef[2c+1] | alpha[c] | a*S'v[c] | a*Y'v[c] | ys[c] | theta ; everything indexed by AGE (0 = newest).
-inline size_t gram_solve_smem_elems(int c) { return (size_t)2 * c * c + 6 * c + 2; }
+__host__ __device__ inline size_t gram_solve_smem_elems(int c) { return (size_t)2 * c * c + 6 * c + 2; }
 
 // All global reads go through L2 (__ldcg): inside the persistent solve these scalars are rewritten by another CTA between rounds.
 template <class T>
