@@ -309,11 +309,9 @@ def main():
         return {"kernel": kernel_name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": load_traffic(traffic_key), "peak_source": peak_src,
                 "algorithmic_bytes": "per launch (= one minimize): sum over the kernel's passes of whole vectors read + written, 8 n x "
-                                     "{first 3, trial 4, pair-forming dots 2c+4, combination + first trial 2c+3 (+2 when its x, g are stored, +2 when it also "
-                                     "forms the pair of an accepted first trial and takes its dots from the staged columns), plain dots 2c+1, materialise 4}, "
-                                     "c = pairs taking part in that pass; one iteration with T trials moves (4c+9) + 4(T-1) words per coordinate, or 2c+7 "
-                                     "when the first trial is accepted and its pair dots were taken speculatively, where SURVEY.md 8d counts "
-                                     "(4c+2) + 6 + 8T for the unfused sequence",
+                                     "{first 3, trial 4, pair-forming dots 2c+4, combination + first trial 2c+3 (+2 when its x, g are stored), plain dots 2c+1, "
+                                     "materialise 4}, c = pairs taking part in that pass; one iteration with T trials moves (4c+9) + 4(T-1) words per "
+                                     "coordinate where SURVEY.md 8d counts (4c+2) + 6 + 8T for the unfused sequence",
                 "launches_timed": len(profs), "ms_per_launch": ms / max(1, len(profs)),
                 "passes": {k: {"ms_per_solve": v["ms"] / len(profs), "rounds_per_solve": v["rounds"] / len(profs),
                                "gb_per_s": v["alg_bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None} for k, v in ops.items()},

@@ -104,8 +104,8 @@ template <class T, Hint H, bool VEC> __device__ __forceinline__ void store4(T* b
 // that follows can consume result[] without a separate all-reduce launch.  Inboxes form a ring of kXRing epochs.
 constexpr int kXMaxRanks = 8;
 constexpr int kXRing = 4;
-constexpr int kXMaxVals = 5120;  // per exchange: >= kMaxM * (values per column pair of k_gram_dots), and >= B * (6 m + 4) for a batch of B
-                                 // problems whose sums travel in ONE exchange per round (persist.cuh): 64 * (72 + 4) = 4864
+constexpr int kXMaxVals = 4608;  // per exchange: >= kMaxM * (values per column pair of k_gram_dots), and >= B * (6 m + 4) for a batch of B
+                                 // problems whose sums travel in ONE exchange per round (persist.cuh): 64 * (60 + 4) = 4096
 constexpr int kMailVals = 384;   // host mailbox slots
 
 struct XInbox

@@ -96,12 +96,6 @@ template <class T> struct PState
     int lo_virtual;             // the best-so-far point (x_lo, g_lo) is the virtual first trial: materialise it at lo_step if needed
     T lo_step;
     int after_materialize;      // what MATERIALIZE was for: 1 = the accepted trial, 2 = the best-so-far point
-    // speculative pair dots: a COMBINE_TRIAL pass that stores its first trial can also form the pair (s, y) = (x1 - x, g1 - g) that
-    // an ACCEPTED first trial leads to, write it to the free ring slot and take its dots against the history columns it has staged
-    // anyway -- the DOTS_FORM round (2c+4 words, one grid synchronisation) then disappears from that iteration (see p_combine)
-    int spec_policy;            // 0 never, 1 always, 2 iff the previous search accepted its first trial (default)
-    int spec_now;               // the COMBINE_TRIAL round about to run / just run speculates
-    int last_first_accepted;
     // iteration scalars
     T fx, dg, gg, xx, gnorm, step;
     int k;
@@ -120,7 +114,7 @@ template <class T> struct alignas(128) PRound
 {
     T *x, *xp, *g, *gp, *drt;
     T step;
-    int op, c_round, head, pending, gram_cur, store_first, spec;
+    int op, c_round, head, pending, gram_cur, store_first;
 };
 
 struct alignas(128) PCtl
@@ -670,11 +664,6 @@ __device__ __forceinline__ void dots_geometry(int c, int units, int& split, int&
     cols_per_round = c < kGramMaxWarps / split ? c : kGramMaxWarps / split;
 }
 
-// speculative pair dots of a COMBINE_TRIAL pass (see PState::spec_policy): the pair an accepted first trial would produce takes part
-// as column 0 of a DOTS_FORM pass over c columns, with exactly that pass's thread mapping and summation order (the per-CTA partial
-// sums are bit-identical to the ones a separate DOTS_FORM round would deposit)
-struct PSpec { int on, c, split, cols_per_round, new_slot; };
-
 // ---- COMBINE (+ first trial) ---------------------------------------------------------------------------------------------------
 // d = cv*v + sum_j cy_j*y_j + cs_j*s_j ; FUSE: x1 = xc + d, g1 = grad f(x1) written to (x1_out, g1_out) and the four trial sums.
 // Staged rows of a tile: v, (xc,) then the history block's live slots; sh.slots[j] = packed row of the pair of age j.  A thread owns
@@ -683,28 +672,22 @@ struct PSpec { int on, c, split, cols_per_round, new_slot; };
 // HALO (neighbour-coupled objectives, one GPU): x1 goes back into the staged x row, two spare warps form d and x1 of the element on
 // either side of the tile from global memory with the very arithmetic of the tile that owns it, and after a barrier the objective
 // takes x1_{i-1}, x1_{i+1} from shared memory.
-// SPEC (sp.on; FUSE with ROUNDS == 1 only): every stage has one (HALO: two) spare rows after the history block.  After the units of a
-// tile have their x1 and g1, the rows that are no longer needed take s' = x1 - xc (the xc row; HALO: the second spare row), y' = g1 - v
-// (the v row) and g1 (the first spare row), s' and y' also go to ring slot sp.new_slot, and after a barrier the warps take the
-// DOTS_FORM sums [S Y s' y']'[g1 s' y'] from shared memory in the mapping of p_dots.
 // `between` (all threads) runs after the bulk copies of the first tiles have been issued and before anything reads the coefficients:
 // the coefficient recursion overlaps the latency of those copies when it has a scratch area of its own.
-template <class T, class OBJ, bool FUSE, bool HALO, bool SPEC, class Between>
+template <class T, class OBJ, bool FUSE, bool HALO, class Between>
 __device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, const PHist<T>& h, int c, int end, T* tiles, T* __restrict__ res,
                                           T* __restrict__ x1_out, T* __restrict__ g1_out, PShared& sh, unsigned& phase_bits, double* dst, int G,
-                                          const PSpec& sp, Between between)
+                                          Between between)
 {
     constexpr int EPT = 16 / (int)sizeof(T);
     constexpr int DV = HALO ? OBJ::kDataVectors : 0;              // HALO: the objective's data vectors ride in the stage as well
     constexpr int NRHS = (FUSE ? 2 : 1) + DV;                     // v (, xc) (, data0, data1)
     constexpr int PAD = EPT;                                      // HALO: room for x1 of the neighbouring element on either side of the x row
-    static_assert(!SPEC || FUSE, "speculative pair dots ride on the fused first trial");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int TE = h.BT();
     const SlotRuns runs(end, c, h.M);
     const int nrows = NRHS + 2 * c;
-    constexpr bool spec = SPEC;      // (a separate instantiation: the plain pass keeps its registers)
-    const size_t stage_elems = (size_t)(nrows + (spec ? (HALO ? 2 : 1) : 0)) * TE + (HALO ? 2 * PAD : 0);
+    const size_t stage_elems = (size_t)nrows * TE + (HALO ? 2 * PAD : 0);
     int stages = (int)((size_t)kPStageBytes / (stage_elems * sizeof(T)));
     stages = stages > kPMaxStages ? kPMaxStages : stages;
     const int64_t n = own.n;
@@ -738,39 +721,6 @@ __device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, const 
 
     T acc[5] = {T(0), T(0), T(0), T(0), T(0)};
     T pre[5] = {T(0), T(0), T(0), T(0), T(0)};   // HALO, right-margin warp: operands of the element after the current tile
-    T accd[kGramVals] = {T(0), T(0), T(0), T(0), T(0), T(0)};   // SPEC: this thread's share of column my_col's six sums
-    const int my_col = spec ? warp / sp.split : 0, my_part = spec ? warp % sp.split : 0;
-    const int upp = spec ? (TE / EPT) / sp.split : 0;
-    // the DOTS_FORM sums of one tile from shared-memory rows (p_dots' inner loop, operands already formed)
-    auto spec_dots = [&](const T* g1row, const T* snrow, const T* ynrow, const T* hist, int len) {
-        if (!(my_col < sp.cols_per_round && my_col < sp.c)) return;
-        const bool is_new = my_col == 0;
-        const T* srow = is_new ? snrow : hist + (size_t)2 * sh.slots[my_col - 1] * TE;      // column j >= 1 is the pair of age j - 1 of this pass
-        const T* yrow = is_new ? ynrow : srow + TE;
-        for (int u = my_part * upp + lane; u < (my_part + 1) * upp; u += 32)
-        {
-            const int off = u * EPT;
-            const int cnt = len - off;
-            if (cnt <= 0) break;
-            Unit<T> ug = lds_unit<T>(g1row + off), usn = lds_unit<T>(snrow + off), uyn = lds_unit<T>(ynrow + off);
-            Unit<T> us = lds_unit<T>(srow + off), uy = lds_unit<T>(yrow + off);
-            if (cnt < EPT) { mask_unit(ug, cnt); mask_unit(usn, cnt); mask_unit(uyn, cnt); mask_unit(us, cnt); mask_unit(uy, cnt); }
-#pragma unroll
-            for (int k = 0; k < EPT; k++)
-            {
-                accd[0] += us.v[k] * ug.v[k];
-                accd[1] += uy.v[k] * ug.v[k];
-            }
-#pragma unroll
-            for (int k = 0; k < EPT; k++)
-            {
-                accd[2] += us.v[k] * uyn.v[k];
-                accd[3] += uy.v[k] * uyn.v[k];
-                accd[4] += uy.v[k] * usn.v[k];
-                accd[5] += us.v[k] * usn.v[k];
-            }
-        }
-    };
     __syncthreads();   // sh.vecs / sh.slots are in place and the staging ring is free
     int64_t next_tile = 0;
     for (int s = 0; s < stages; s++, next_tile++)
@@ -848,28 +798,8 @@ __device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, const 
                         st_unit<T>(x1_out, i0, cnt, uo);
                         st_unit<T>(g1_out, i0, cnt, ug);
                     }
-                    if constexpr (SPEC)
-                        if (spec)
-                        {
-                            Unit<T> usn, uyn;
-#pragma unroll
-                            for (int k = 0; k < EPT; k++) { usn.v[k] = xv[k] - ux.v[k]; uyn.v[k] = gv[k] - uv.v[k]; }
-                            if (cnt < EPT) { mask_unit(usn, cnt); mask_unit(uyn, cnt); }
-                            *reinterpret_cast<float4*>(xrow + off) = *reinterpret_cast<const float4*>(usn.v);                 // s' over xc
-                            *reinterpret_cast<float4*>(base + off) = *reinterpret_cast<const float4*>(uyn.v);                 // y' over v
-                            *reinterpret_cast<float4*>(base + (size_t)nrows * TE + off) = *reinterpret_cast<const float4*>(ug.v);   // g1: spare row
-                            T* s_new = h.s_at(sp.new_slot, e0);
-                            st_unit<T>(s_new, off, cnt, usn);
-                            st_unit<T>(s_new + TE, off, cnt, uyn);
-                        }
                 }
             }
-            if constexpr (SPEC)
-                if (spec)
-                {
-                    __syncthreads();
-                    spec_dots(base + (size_t)nrows * TE, xrow, base, hist, len);
-                }
         }
         else
         {
@@ -879,9 +809,8 @@ __device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, const 
             const int64_t i0 = e0 + off;
             const int cnt = mine ? ((len - off >= EPT) ? EPT : (len - off)) : 0;
             T r[EPT];
-            Unit<T> usn_keep;                                      // SPEC: s' = x1 - xc of this thread's unit, formed before x1 replaces xc
 #pragma unroll
-            for (int k = 0; k < EPT; k++) { r[k] = T(0); usn_keep.v[k] = T(0); }
+            for (int k = 0; k < EPT; k++) r[k] = T(0);
             if (mine)
             {
                 Unit<T> uv;
@@ -899,12 +828,6 @@ __device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, const 
 #pragma unroll
                 for (int k = 0; k < EPT; k++) u1.v[k] = (k < cnt) ? ux.v[k] + T(1) * r[k] : T(0);
                 *reinterpret_cast<float4*>(xrow + off) = *reinterpret_cast<const float4*>(u1.v);
-                if constexpr (SPEC)
-                    if (spec)
-                    {
-#pragma unroll
-                        for (int k = 0; k < EPT; k++) usn_keep.v[k] = (k < cnt) ? u1.v[k] - ux.v[k] : T(0);
-                    }
             }
             // the element on either side of the tile.  Left: the previous tile of this chunk left its last x1 in sh.carry (only a chunk's
             // first tile asks global memory).  Right: warp kPWarps-1 holds the operands of the element after the tile (fetched through
@@ -983,29 +906,7 @@ __device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, const 
                     st_unit<T>(x1_out, i0, cnt, uo);
                     st_unit<T>(g1_out, i0, cnt, ug);
                 }
-                if constexpr (SPEC)
-                    if (spec)
-                    {
-                        const Unit<T> uv2 = lds_unit<T>(base + off);
-                        Unit<T> uyn;
-#pragma unroll
-                        for (int k = 0; k < EPT; k++) uyn.v[k] = (k < cnt) ? gv[k] - uv2.v[k] : T(0);
-                        T* g1row = const_cast<T*>(hist) + (size_t)2 * c * TE;
-                        *reinterpret_cast<float4*>(base + off) = *reinterpret_cast<const float4*>(uyn.v);            // y' over v
-                        *reinterpret_cast<float4*>(g1row + off) = *reinterpret_cast<const float4*>(ug.v);            // g1: first spare row
-                        *reinterpret_cast<float4*>(g1row + TE + off) = *reinterpret_cast<const float4*>(usn_keep.v); // s': second spare row
-                        T* s_new = h.s_at(sp.new_slot, e0);
-                        st_unit<T>(s_new, off, cnt, usn_keep);
-                        st_unit<T>(s_new + TE, off, cnt, uyn);
-                    }
             }
-            if constexpr (SPEC)
-                if (spec)
-                {
-                    __syncthreads();
-                    const T* g1row = hist + (size_t)2 * c * TE;
-                    spec_dots(g1row, g1row + TE, base, hist, len);
-                }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
@@ -1015,32 +916,8 @@ __device__ __forceinline__ void p_combine(const OBJ& obj, const Own& own, const 
     }
     if (FUSE)
     {
-        double* dst_trial = dst;
-        if constexpr (SPEC)
-            if (spec)
-            {
-                // the dots first (the Gram recursion of the next pass finds them where a DOTS_FORM round leaves them), the five sums of
-                // the trial after them; reduction exactly as at the end of p_dots
-                __syncthreads();   // sh.red may still be read from the previous use
-#pragma unroll
-                for (int k = 0; k < kGramVals; k++)
-                {
-                    const double w = warp_sum((double)accd[k]);
-                    if (lane == 0) sh.red[warp][k] = w;
-                }
-                __syncthreads();
-                const int nvals = sp.c * kGramVals;
-                for (int idx = tid; idx < nvals; idx += kPThreads)
-                {
-                    const int j = idx / kGramVals, k = idx % kGramVals;
-                    double t = 0.0;
-                    for (int p = 0; p < sp.split; p++) t += sh.red[j * sp.split + p][k];
-                    dst[(size_t)idx * G] = t;
-                }
-                dst_trial = dst + (size_t)nvals * G;
-            }
         const double dacc[5] = {(double)acc[0], (double)acc[1], (double)acc[2], (double)acc[3], (double)acc[4]};
-        block_sums<5>(dacc, sh, dst_trial, G);
+        block_sums<5>(dacc, sh, dst, G);
     }
     else
     {
@@ -1118,7 +995,6 @@ template <class T> __device__ __forceinline__ void digest_trial(PState<T>* st, T
     const T step_tried = ls_step_ref(st);
     const int rc = ls_advance(st, fx, dg, keep);
     if (is_first && st->adaptive_first_store) st->first_store = (rc == LBFGSpp::LSC_ACCEPT) ? 1 : 0;
-    if (is_first) st->last_first_accepted = (rc == LBFGSpp::LSC_ACCEPT) ? 1 : 0;
     if (keep)
     {
         if (is_virtual) { st->lo_virtual = 1; st->lo_step = step_tried; }
@@ -1182,36 +1058,7 @@ template <class T> __device__ __forceinline__ bool begin_search(PState<T>* st, T
     return true;
 }
 
-// number of columns of the DOTS_FORM pass that follows a search at the current ring state
-template <class T> __device__ __forceinline__ int dots_form_columns(const PState<T>* st) { return st->ncorr < st->m ? st->ncorr + 1 : st->m; }
-
-// the COMBINE(_TRIAL) round about to be scheduled: does it take the speculative pair dots along?  spec_cmax: the largest number of
-// combined columns for which two stages with the spare rows still fit the staging ring (-1: this instantiation cannot speculate)
-template <class T> __device__ __forceinline__ void schedule_combine(PState<T>* st, int spec_cmax)
-{
-    st->op = st->fuse_first_trial ? POP_COMBINE_TRIAL : POP_COMBINE;
-    const bool want = st->spec_policy == 1 || (st->spec_policy == 2 && st->last_first_accepted);
-    st->spec_now = (want && st->fuse_first_trial && st->first_store && st->c_round <= spec_cmax) ? 1 : 0;
-}
-
-// curvature gate on the pair's own dots (age-0 column: [2] = s'y, [3] = y'y), LBFGS.h:161; commit = BFGSMat.h:89-97
-template <class T> __device__ __forceinline__ void after_pair_dots(PState<T>* st, const double* vals, int spec_cmax)
-{
-    const T sy = (T)vals[2], yy = (T)vals[3];
-    if (sy > st->eps_gate * yy)
-    {
-        st->ys[st->head] = sy;
-        *st->theta = yy / sy;
-        st->pending = st->head;
-        st->head = (st->head + 1) % st->M;
-        st->ncorr = st->c_round;
-        schedule_combine(st, spec_cmax);
-    }
-    else if (st->ncorr > 0) { st->op = POP_DOTS_PLAIN; st->c_round = st->ncorr; }
-    else { st->c_round = 0; schedule_combine(st, spec_cmax); }
-}
-
-template <class T> __device__ void advance_problem(PState<T>* st, const double* vals, int spec_cmax)
+template <class T> __device__ void advance_problem(PState<T>* st, const double* vals)
 {
     st->rounds++;
     switch (st->op)
@@ -1238,31 +1085,36 @@ template <class T> __device__ void advance_problem(PState<T>* st, const double* 
         after_search(st);
         return;
     case POP_DOTS_FORM:
-        after_pair_dots(st, vals, spec_cmax);
+    {
+        // curvature gate on the pair's own dots (age-0 column: [2] = s'y, [3] = y'y), LBFGS.h:161; commit = BFGSMat.h:89-97
+        const T sy = (T)vals[2], yy = (T)vals[3];
+        if (sy > st->eps_gate * yy)
+        {
+            st->ys[st->head] = sy;
+            *st->theta = yy / sy;
+            st->pending = st->head;
+            st->head = (st->head + 1) % st->M;
+            st->ncorr = st->c_round;
+            st->op = st->fuse_first_trial ? POP_COMBINE_TRIAL : POP_COMBINE;
+        }
+        else if (st->ncorr > 0) { st->op = POP_DOTS_PLAIN; st->c_round = st->ncorr; }
+        else { st->op = st->fuse_first_trial ? POP_COMBINE_TRIAL : POP_COMBINE; st->c_round = 0; }
         return;
+    }
     case POP_DOTS_PLAIN:
-        schedule_combine(st, spec_cmax);
+        st->op = st->fuse_first_trial ? POP_COMBINE_TRIAL : POP_COMBINE;
         return;
     case POP_COMBINE:
     case POP_COMBINE_TRIAL:
     {
         const bool fused = st->op == POP_COMBINE_TRIAL;
         const bool stored = st->first_store != 0;      // what this pass was told (the policy flag changes in digest_trial)
-        const bool spec = fused && st->spec_now != 0;  // the pass also left the DOTS_FORM sums of the pair (x1 - x, g1 - g) in vals[0 ..)
-        const double* tv = vals + (spec ? dots_form_columns(st) * kGramVals : 0);   // {g.d, f1, g1.d, g1.g1, x1.x1}
-        st->spec_now = 0;
         if (st->pending >= 0) { st->gram_cur = 1 - st->gram_cur; st->pending = -1; }
-        st->dg = (T)tv[0];                  // LBFGS.h:123 for the next pass
+        st->dg = (T)vals[0];                // LBFGS.h:123 for the next pass
         st->k += 1;
         if (!begin_search(st, T(1))) return;   // LBFGS.h:168
         // the pass already evaluated x + 1*d into the buffers that the rotation just made (x, g)
-        if (fused && ls_step_ref(st) == T(1))
-        {
-            digest_trial(st, (T)tv[1], (T)tv[2], (T)tv[3], (T)tv[4], true, !stored);
-            // accepted and not converged: the search is over, the pair it leads to is the one the pass formed -- its DOTS_FORM round
-            // has already happened
-            if (spec && st->op == POP_DOTS_FORM) after_pair_dots(st, vals, spec_cmax);
-        }
+        if (fused && ls_step_ref(st) == T(1)) digest_trial(st, (T)vals[1], (T)vals[2], (T)vals[3], (T)vals[4], true, !stored);
         return;
     }
     default: return;
@@ -1270,7 +1122,7 @@ template <class T> __device__ void advance_problem(PState<T>* st, const double* 
 }
 
 // n-words a pass has to move (reads + writes of whole vectors): the roofline numerator of the persistent kernel
-__device__ __forceinline__ double words_of(int op, int c, int data_vectors, int store_first, int spec = 0)
+__device__ __forceinline__ double words_of(int op, int c, int data_vectors, int store_first)
 {
     switch (op)
     {
@@ -1280,7 +1132,7 @@ __device__ __forceinline__ double words_of(int op, int c, int data_vectors, int 
     case POP_DOTS_FORM: return 2.0 * c + 4.0;               // R x, xp, g, gp, 2(c-1) columns ; W s, y
     case POP_DOTS_PLAIN: return 2.0 * c + 1.0;              // R g, 2c columns
     case POP_COMBINE: return 2.0 * c + 2.0;                 // R g, 2c columns ; W d
-    case POP_COMBINE_TRIAL: return 2.0 * c + 3.0 + (store_first ? 2.0 : 0.0) + (spec ? 2.0 : 0.0) + data_vectors;   // R g, x, 2c columns ; W d (, x1, g1) (, s', y')
+    case POP_COMBINE_TRIAL: return 2.0 * c + 3.0 + (store_first ? 2.0 : 0.0) + data_vectors;   // R g, x, 2c columns ; W d (, x1, g1)
     default: return 0.0;
     }
 }
@@ -1292,7 +1144,7 @@ template <class T> __device__ __forceinline__ int nvals_of(const PState<T>* st)
     case POP_FIRST: case POP_TRIAL: case POP_MATERIALIZE: return 4;
     case POP_DOTS_FORM: case POP_DOTS_PLAIN: return st->c_round * kGramVals;
     case POP_COMBINE: return 1;
-    case POP_COMBINE_TRIAL: return 5 + (st->spec_now ? dots_form_columns(st) * kGramVals : 0);
+    case POP_COMBINE_TRIAL: return 5;
     default: return 0;
     }
 }
@@ -1301,7 +1153,7 @@ template <class T> __device__ __forceinline__ int nvals_of(const PState<T>* st)
 // publication of the next round's descriptors.  Called by all threads of CTA 0 once every CTA has arrived.  Returns (in every
 // thread) the number of problems still running.
 template <class T, bool HALO>
-__device__ int leader_round(const PArgs<T>& a, int G, PShared& sh, PState<T>* cache, int spec_cmax)
+__device__ int leader_round(const PArgs<T>& a, int G, PShared& sh, PState<T>* cache)
 {
     const int tid = threadIdx.x;
     // the leader's working copies: the first kPCache problems live in shared memory for the duration of the kernel
@@ -1411,13 +1263,12 @@ __device__ int leader_round(const PArgs<T>& a, int G, PShared& sh, PState<T>* ca
         if (b < a.B && state_of(b)->op != POP_IDLE)
         {
             PState<T>* st = state_of(b);
-            advance_problem(st, st->raw, spec_cmax);
+            advance_problem(st, st->raw);
             PRound<T>* rd = a.rounds + b;
             rd->x = st->x; rd->xp = st->xp; rd->g = st->g; rd->gp = st->gp; rd->drt = st->drt;
             rd->step = st->step;
             rd->c_round = st->c_round; rd->head = st->head; rd->pending = st->pending; rd->gram_cur = st->gram_cur;
             rd->store_first = st->first_store;
-            rd->spec = st->spec_now;
             rd->op = st->op;
             running = st->op != POP_IDLE;
         }
@@ -1494,15 +1345,6 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
     __shared__ __align__(16) double s_gram[kPGramScratch];   // the coefficient recursion's own scratch (c <= 21: it then runs while the first tiles of the pass are in flight)
     __shared__ PState<T> s_state[kPCache];     // CTA 0: working copies of the first problems' states (scalar logic at shared-memory latency)
     const int ncache = a.B < kPCache ? a.B : kPCache;
-    // speculative pair dots (PSpec): the largest number of combined columns for which two stages with the spare rows fit the ring
-    int spec_cmax = -1;
-    if (ROUNDS == 1)
-    {
-        constexpr int EPT = 16 / (int)sizeof(T);
-        constexpr int NRHS_CT = 2 + (HALO ? kDataVectors : 0);
-        for (int c = 0; c <= kMaxM; c++)
-            if (2 * (((size_t)(NRHS_CT + 2 * c + (HALO ? 2 : 1)) << a.probs[0].hist.bt_log) + (HALO ? 2 * EPT : 0)) * sizeof(T) <= (size_t)kPStageBytes) spec_cmax = c;
-    }
     if (cta == 0)
     {
         const unsigned* src = reinterpret_cast<const unsigned*>(a.probs);
@@ -1581,10 +1423,9 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
             const T step = ldv(&rd->step);
             const int c_round = ldv(&rd->c_round), head = ldv(&rd->head), pending = ldv(&rd->pending), gram_cur = ldv(&rd->gram_cur);
             const int store_first = ldv(&rd->store_first);
-            const int spec_round = ldv(&rd->spec);
             if (op == POP_IDLE) continue;
             acct_bucket = (acct_bucket == -1 || acct_bucket == op) ? op : 0;
-            acct_words += words_of(op, c_round, kDataVectors, store_first, spec_round);
+            acct_words += words_of(op, c_round, kDataVectors, store_first);
             double* dst = a.partials + (size_t)b * a.pstride * G + cta;
             const OBJ obj = PObjMaker<T, OBJ>::make(a, st->data0, st->data1, (HALO && a.xc != nullptr) ? st->halo : nullptr);
             switch (op)
@@ -1659,26 +1500,15 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persist(PArgs<T> a)
                 };
                 if (!own_scratch) solve_into(tiles);   // a long history: the staging ring is the scratch, the copies start afterwards
                 auto between = [&]() { if (own_scratch) solve_into(reinterpret_cast<T*>(s_gram)); };
-                PSpec sp{0, 0, 1, 1, head};
-                if (fuse && spec_round && store_first)
-                {
-                    sp.on = 1;
-                    sp.c = g.c + 1 < g.M - 1 ? g.c + 1 : g.M - 1;      // = dots_form_columns: the new pair + the newest old ones (M = m + 1)
-                    dots_geometry(sp.c, st->hist.BT() / (16 / (int)sizeof(T)), sp.split, sp.cols_per_round);
-                }
-                if (fuse && sp.on)
-                {
-                    if constexpr (ROUNDS == 1) p_combine<T, OBJ, true, OBJ::kHalo, true>(obj, own, st->hist, g.c, head, tiles, vd, vxp, vgp, sh, phase_bits, dst, G, sp, between);
-                }
-                else if (fuse) p_combine<T, OBJ, true, OBJ::kHalo, false>(obj, own, st->hist, g.c, head, tiles, vd, store_first ? vxp : nullptr, store_first ? vgp : nullptr, sh, phase_bits, dst, G, sp, between);
-                else p_combine<T, OBJ, false, false, false>(obj, own, st->hist, g.c, head, tiles, vd, nullptr, nullptr, sh, phase_bits, dst, G, sp, between);
+                if (fuse) p_combine<T, OBJ, true, OBJ::kHalo>(obj, own, st->hist, g.c, head, tiles, vd, store_first ? vxp : nullptr, store_first ? vgp : nullptr, sh, phase_bits, dst, G, between);
+                else p_combine<T, OBJ, false, false>(obj, own, st->hist, g.c, head, tiles, vd, nullptr, nullptr, sh, phase_bits, dst, G, between);
                 break;
             }
             default: break;
             }
         }
         if (acct_bucket < 0) acct_bucket = 0;
-        if (grid_barrier([&]() { return leader_round<T, HALO>(a, G, sh, s_state, spec_cmax) == 0 || ldv(&a.ctl->abort) != 0; })) break;
+        if (grid_barrier([&]() { return leader_round<T, HALO>(a, G, sh, s_state) == 0 || ldv(&a.ctl->abort) != 0; })) break;
     }
     if (cta == 0)
     {

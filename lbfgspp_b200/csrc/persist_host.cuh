@@ -122,9 +122,6 @@ static lbfgs_b200_status solver_minimize(lbfgs_b200_solver* s, int objective, co
         p.fuse_first_trial = (coupled && ctx->nranks > 1) ? 0 : 1;
         p.adaptive_first_store = (getenv("LBFGS_B200_VIRTUAL_FIRST_TRIAL") && atoi(getenv("LBFGS_B200_VIRTUAL_FIRST_TRIAL")) != 0) ? 1 : 0;
         p.first_store = p.adaptive_first_store ? 0 : 1;
-        p.spec_policy = 0;                       // speculative pair dots: off (LBFGS_B200_SPECULATE = 1 always, 2 iff the previous search accepted its first trial)
-        if (const char* e = getenv("LBFGS_B200_SPECULATE")) { const int v = atoi(e); if (v >= 0 && v <= 2) p.spec_policy = v; }
-        p.spec_now = 0; p.last_first_accepted = 0;
         p.ls_opt.linesearch = (ls_kind == 3) ? 3 : prm->linesearch;
         p.ls_opt.max_linesearch = prm->max_linesearch;
         p.ls_opt.min_step = (T)prm->min_step; p.ls_opt.max_step = (T)prm->max_step; p.ls_opt.ftol = (T)prm->ftol; p.ls_opt.wolfe = (T)prm->wolfe;
@@ -138,7 +135,7 @@ static lbfgs_b200_status solver_minimize(lbfgs_b200_solver* s, int objective, co
     {
         const PState<T>& p = hs[b];
         hr[b].x = p.x; hr[b].xp = p.xp; hr[b].g = p.g; hr[b].gp = p.gp; hr[b].drt = p.drt;
-        hr[b].step = T(0); hr[b].op = p.op; hr[b].c_round = 0; hr[b].head = 0; hr[b].pending = -1; hr[b].gram_cur = p.gram_cur; hr[b].store_first = p.first_store; hr[b].spec = 0;
+        hr[b].step = T(0); hr[b].op = p.op; hr[b].c_round = 0; hr[b].head = 0; hr[b].pending = -1; hr[b].gram_cur = p.gram_cur; hr[b].store_first = p.first_store;
     }
     // BFGSMat::reset (BFGSMat.h:61-78): no pairs, theta = 1, Gram matrices cleared
     CU(ctx, cudaMemsetAsync(s->d_small, 0, sizeof(T) * s->small_elems * (size_t)B, ctx->stream));
@@ -280,7 +277,7 @@ lbfgs_b200_status lbfgs_b200_solver_create_batch(lbfgs_b200_ctx* ctx, int64_t n,
     s->exported.assign((size_t)batch, nullptr); s->export_fresh.assign((size_t)batch, 0);
     cudaError_t e = cudaSuccess;
     s->vec_elems = (((size_t)n * elem_bytes + 255) & ~size_t(255)) / elem_bytes;
-    s->pstride = (m * lb::kGramVals + 5 + 7) & ~7;      // a dots pass leaves 6 sums per column pair, a combination pass with speculative pair dots 5 more
+    s->pstride = ((m * lb::kGramVals > 8 ? m * lb::kGramVals : 8) + 7) & ~7;
     const size_t state_bytes = (elem_bytes == 8 ? sizeof(lb::PState<double>) : sizeof(lb::PState<float>)) * (size_t)batch;
     if (e == cudaSuccess) e = pool_alloc(ctx, (void**)&s->vec_slab, (size_t)batch * 7 * s->vec_elems * elem_bytes);
     if (e == cudaSuccess) e = pool_alloc(ctx, (void**)&s->d_hist, (size_t)batch * s->hist_elems * elem_bytes);

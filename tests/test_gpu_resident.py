@@ -152,33 +152,3 @@ def test_resident_large_history(orc, m, iters):
     h = lb.LBFGSSolver(prm, "Bracketing", resident=False).minimize(lb.OBJ_QUAD_TRIDIAG, np.zeros(n), data0=d, data1=b)
     assert (h["niter"], h["nfev"]) == (g["niter"], g["nfev"]) and abs(h["fx"] - g["fx"]) <= 1e-9 * abs(g["fx"])
 
-
-def test_speculative_pair_dots_are_bit_identical(monkeypatch):
-    """LBFGS_B200_SPECULATE: a combination pass that stores its first trial also forms the pair an accepted trial leads to and takes
-    its dots from the columns it has staged (persist.cuh, PSpec); the DOTS_FORM round of that iteration then disappears.  The sums are
-    taken in the mapping and order of the separate pass, so the whole solve must not change by a bit -- only the number of rounds."""
-    cases = [(lb.OBJ_ROSENBROCK_PAIRED, np.random.default_rng(5).uniform(-1, 1, 50000), 10, "MoreThuente", None, None),
-             (lb.OBJ_ROSENBROCK_PAIRED, np.zeros(4098), 6, "NocedalWright", None, None)]
-    d, b, _ = po.quad_tridiag_data(30000, kappa=1e3, seed=0)
-    cases.append((lb.OBJ_QUAD_TRIDIAG, np.zeros(30000), 20, "Bracketing", d, b))
-    for obj, x0, m, ls, d0, d1 in cases:
-        out = {}
-        for policy in ("0", "1", "2"):
-            monkeypatch.setenv("LBFGS_B200_SPECULATE", policy)
-            out[policy] = resident(lb.LBFGSParam(m=m, max_iterations=120), ls).minimize(obj, x0, data0=d0, data1=d1)
-        for policy in ("1", "2"):
-            assert (out[policy]["niter"], out[policy]["nfev"], out[policy]["fx"]) == (out["0"]["niter"], out["0"]["nfev"], out["0"]["fx"])
-            assert np.array_equal(out[policy]["x"], out["0"]["x"])
-    # a batch (rounds are reported per problem): fewer rounds, same bits
-    X0 = np.stack([np.random.default_rng(7 + b).uniform(-1, 1, 20000) for b in range(3)])
-    got = {}
-    for policy in ("0", "1"):
-        monkeypatch.setenv("LBFGS_B200_SPECULATE", policy)
-        bs = lb.BatchSession(lb.OBJ_ROSENBROCK_PAIRED, X0, lb.LBFGSParam(m=10, max_iterations=100), "MoreThuente")
-        got[policy] = bs.solve()
-        bs.close()
-    for b in range(3):
-        r0, r1 = got["0"][0][b], got["1"][0][b]
-        assert (r0["niter"], r0["nfev"], r0["fx"]) == (r1["niter"], r1["nfev"], r1["fx"])
-        assert r1["rounds"] < r0["rounds"]
-    assert np.array_equal(got["0"][1], got["1"][1])
