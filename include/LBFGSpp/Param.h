@@ -3,6 +3,11 @@
 // Drop-in for the reference's include/LBFGSpp/Param.h: same struct names, same public fields, same
 // defaults (reference Param.h:171-182 and :330-341), same enum values (:23-62) and the same
 // std::invalid_argument messages from check_param() (:191-218, :350-376).  No device work happens here.
+//
+// One difference in range, not in meaning: the reference accepts any positive m; the device history holds at most m = 64 pairs
+// (LBFGSSolver) / m = 20 (LBFGSBSolver).  check_param() keeps the reference's messages, so a larger m is reported by minimize() when
+// the history is created (std::invalid_argument: "hist_create: need n >= 1 and 1 <= m <= 64", "the bound-constrained path supports
+// m <= 20").
 #ifndef LBFGSPP_B200_PARAM_H
 #define LBFGSPP_B200_PARAM_H
 

@@ -75,6 +75,7 @@ def abi():
     lib.lbfgs_b200_memcpy_d2d.argtypes = [vp, vp, vp, sz]
     lib.lbfgs_b200_memset_zero.argtypes = [vp, vp, sz]
     lib.lbfgs_b200_sync.argtypes = [vp]
+    lib.lbfgs_b200_trim.argtypes = [vp]
     lib.lbfgs_b200_timer_start.argtypes = [vp]
     lib.lbfgs_b200_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     lib.lbfgs_b200_set_index_offset.argtypes = [vp, i64]
@@ -352,6 +353,10 @@ class Context:
 
     def sync(self):
         self.check(self.lib.lbfgs_b200_sync(self.h))
+
+    def trim(self):
+        """Give the context's cached device blocks back to the driver (lbfgs_b200_trim)."""
+        self.check(self.lib.lbfgs_b200_trim(self.h))
 
     def launches(self):
         return self.lib.lbfgs_b200_launch_count(self.h)

@@ -1,7 +1,6 @@
 #!/bin/bash
 # profiles/run_multi_gpu_bench.sh <round> -- on an 8-GPU box: gpurun --gpus 8 --timeout 900 -- 'bash profiles/run_multi_gpu_bench.sh r02'
-# one bench line per sharded configuration (config 2 n-sharded; config 5 problem-parallel and n-sharded, the latter also with the
-# speculative pair dots, LBFGS_B200_SPECULATE=1: with n / 8 per rank the rounds are synchronisation-bound)
+# one bench line per sharded configuration (config 2 n-sharded; config 5 problem-parallel and n-sharded)
 ROUND=${1:-rXX}
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
@@ -24,4 +23,3 @@ N=${2:-8}
 run ${ROUND}_bench_c2_n$N $N "A=0" --steps 10 --warmup 3
 run ${ROUND}_bench_c5_n${N}_problems $N "A=0" --config c5 --sharding problems --steps 2 --warmup 1
 run ${ROUND}_bench_c5_n${N}_nsharded $N "A=0" --config c5 --sharding n --steps 2 --warmup 1
-run ${ROUND}_bench_c5_n${N}_nsharded_spec1 $N "LBFGS_B200_SPECULATE=1" --config c5 --sharding n --steps 2 --warmup 1

@@ -337,3 +337,41 @@ def test_fused_update_apply_Hv_float32(gpu_ctx, n):
     va, vb = ra.get(), rb_.get()
     assert np.max(np.abs(va - vb)) <= 2e-4 * np.max(np.abs(va))
     assert abs(dot_a - dot_b) <= 2e-4 * abs(dot_a)
+
+
+def test_device_memory_pool_hands_released_blocks_out_again():
+    """Blocks released through the ABI stay with the context and come back on an exact size match (internal.cuh: pool_alloc), so the
+    reference's reallocate-per-minimize() pattern costs no cudaMalloc / cudaFree; lbfgs_b200_trim returns them to the driver."""
+    ctx = lb.Context(0)
+    a = ctx.array(np.arange(5000.0))
+    pa = a.base.value
+    del a
+    b = ctx.empty(5000)                      # same size: the same block
+    assert b.base.value == pa
+    c = ctx.empty(5000)                      # the pool is empty again: a fresh block
+    assert c.base.value not in (pa, None)
+    d = ctx.empty(7001)                      # another size never reuses it
+    assert d.base.value not in (pa, c.base.value)
+    # a recycled block starts with a cleared last line (ragged tails are read as whole 256-byte lines)
+    e = ctx.array(np.full(5000 + 13, 7.0))
+    pe = e.base.value
+    del e
+    f = ctx.empty(5000 + 13)
+    assert f.base.value == pe
+    tail = lb.DeviceArray(ctx, None, np.float64, 32, offset_elems=0)   # (only to keep the API exercised)
+    del tail
+    h = lb.History(ctx, 4096, 5)
+    del h
+    h2 = lb.History(ctx, 4096, 5)            # a history rebuilt from its own released blocks still works
+    s = np.random.default_rng(0).standard_normal(4096)
+    h2.add(ctx.array(s), ctx.array(s + 0.1))
+    res = ctx.empty(4096)
+    h2.apply_Hv(ctx.array(s), -1.0, res, lb.HV_AUTO)
+    assert np.all(np.isfinite(res.get()))
+    del b, c, d, f, h2, res
+    ctx.trim()
+    g = ctx.empty(5000)                      # after a trim the pool starts over
+    assert g.base.value is not None
+    del g
+    ctx.close()
+
