@@ -604,6 +604,16 @@ class BatchSession:
                for it, r in zip(items, rounds)]
         return res, X, secs.value
 
+    def upload(self, X0):
+        """New start points (host array, B x n) for the following solves: the host -> device leg of the end-to-end path."""
+        X0 = np.ascontiguousarray(X0, dtype=np.float64)
+        assert X0.shape == (self.B, self.n)
+        err = C.create_string_buffer(256)
+        self.drv.lbfgsb200_drv_batch_session_upload.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_char_p, C.c_int]
+        if self.drv.lbfgsb200_drv_batch_session_upload(self.h, X0.ctypes.data_as(C.POINTER(C.c_double)), err, 256):
+            raise RuntimeError("batch upload failed: " + err.value.decode())
+        return X0.nbytes
+
     def profile(self):
         """Accounting of the last batched solve (one kernel launch for the whole batch): same dict as Session.profile()."""
         ms, rounds, nbytes = (C.c_double * 10)(), (C.c_ulonglong * 10)(), (C.c_double * 10)()

@@ -738,6 +738,22 @@ extern "C" void* lbfgsb200_drv_batch_session_create(int device_ordinal, int obje
 }
 extern "C" void lbfgsb200_drv_batch_session_destroy(void* handle) { delete static_cast<BatchSession*>(handle); }
 
+// new start points for the next solve(s), from host memory (B*n doubles): the end-to-end path of a batch
+extern "C" int lbfgsb200_drv_batch_session_upload(void* handle, const double* x0s_host, char* err, int errlen)
+{
+    BatchSession* s = static_cast<BatchSession*>(handle);
+    try
+    {
+        s->X0.copy_from_host(x0s_host, std::ptrdiff_t(s->n) * s->B);
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        if (err && errlen > 0) { std::strncpy(err, e.what(), size_t(errlen) - 1); err[errlen - 1] = 0; }
+        return -1;
+    }
+}
+
 // One batched solve from the resident start points.  items[B]; rounds_out[B] (optional); seconds_out: host wall clock around the
 // synchronised call; xs_out_host (optional, B*n): the solutions.  Returns the number of problems that did not finish cleanly.
 extern "C" int lbfgsb200_drv_batch_session_solve(void* handle, drv_batch_item* items, long* rounds_out, double* xs_out_host, double* seconds_out,
