@@ -20,6 +20,7 @@ except Exception as e:
 P
 }
 N=${2:-8}
+timeout 300 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > gpurun_out/${ROUND}_gpu_multi_suite.log 2>&1; echo "2-GPU parity suite rc=$?"; tail -2 gpurun_out/${ROUND}_gpu_multi_suite.log
 run ${ROUND}_bench_c2_n$N $N "A=0" --steps 10 --warmup 3
 run ${ROUND}_bench_c5_n${N}_problems $N "A=0" --config c5 --sharding problems --steps 2 --warmup 1
 run ${ROUND}_bench_c5_n${N}_nsharded $N "A=0" --config c5 --sharding n --steps 2 --warmup 1
