@@ -14,7 +14,7 @@
 //     RESTORE        x = xp, g = gp (a search that never improved on its start point; LineSearchMoreThuente.h:602-614)
 //     MATERIALIZE    x = xp + step*d, g = grad f(x) for a trial whose sums are already known: optional policy in which the fused first trial
 //                    does not store x1, g1 while first trials keep being rejected (see digest_trial; off by default)
-// Every CTA owns the same contiguous chunk (256-element granularity) of EVERY vector in EVERY pass, so a CTA only ever reads vector
+// Every CTA owns the same contiguous chunk (granularity: the block length of the tiled history) of EVERY vector in EVERY pass, so a CTA only ever reads vector
 // elements it wrote itself (halo coordinates excepted, those are read through L2) and streams long contiguous runs.  Between rounds there is one
 // grid-wide synchronisation: CTAs deposit their partial sums in fixed slots, CTA 0 adds them in a fixed order (deterministic: no
 // floating-point atomics, result independent of which other problems are in flight), exchanges them with the other ranks when
@@ -24,11 +24,13 @@
 // (pointer swaps) -- and publishes one 128-byte descriptor per problem that tells every CTA what the next round does.  The host is
 // not involved between launch and completion: 1 launch per minimize(), 2 + (T - 1) rounds per iteration with T line-search trials.
 //
-// Data movement: the right-hand vectors of the dots pass and ALL operands of the combination pass (g, x and the 2c history
-// columns, tile by tile) are staged into shared memory by TMA bulk copies (cp.async.bulk + mbarrier) in a multi-stage ring, so the
-// bytes in flight per SM are set by the ring (~90-180 KB), not by registers; the S/Y columns of the dots pass stream into registers
-// with 256-bit evict-first loads (one warp per column pair).  Vectors owned by the solver are padded to whole 256-byte lines, so
-// every tile -- the ragged end of a vector included -- is a legal bulk copy; lanes past n are masked in the arithmetic.
+// Data movement: ALL operands of the dots and combination passes -- the right-hand vectors and the 2c history columns, which live in
+// a tiled layout (PHist) so that the columns of a tile are one or two contiguous runs -- are staged into shared memory by TMA bulk
+// copies (cp.async.bulk + mbarrier) in a two-stage ring of ~90 KB stages: the bytes in flight per SM are set by the ring, not by
+// registers.  The trial pass streams through registers (256-bit loads / stores).  Vectors owned by the solver are padded to whole
+// 256-byte lines, so every tile -- the ragged end of a vector included -- is a legal bulk copy; lanes past n are masked in the
+// arithmetic.  The coefficient recursion of a combination pass runs from a scratch area of its own while the pass's first tiles
+// are in flight.  DESIGN.md section 10 has what was measured about the limits of this arrangement.
 #pragma once
 
 #include "../../include/LBFGSpp/LineSearchCore.h"
