@@ -1,5 +1,8 @@
 #!/bin/bash
 # profiles/env_sweep.sh <round> <config> "<ENV=val ...>" ... -- one bench line (no CPU leg) per environment setting
+# switches of the shipped library: LBFGS_B200_STAGES (2|3|4 stages of the staging ring), LBFGS_B200_TUNE (4 = evict-first trial stores),
+# LBFGS_B200_VIRTUAL_FIRST_TRIAL, LBFGS_B200_CTAS_PER_SM (host-driven loop).  LBFGS_B200_SPECULATE existed at commit 2f7dc75 only
+# (DESIGN.md section 10); the r02c/r02d/r02e lines under r02_experiments/ were taken with that build.
 ROUND=$1; CFG=$2; shift 2
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
