@@ -70,40 +70,82 @@ def load_traffic(key):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md's clocks line).  Sampled in-process through NVML -- the
+    library nvidia-smi itself reads -- every 50 ms: starting an nvidia-smi per sample re-initialises NVML every time and was seen to
+    stall the solver's own driver calls (a 14 ms solve took 39 ms of wall clock on one box), and `nvidia-smi -lms` block-buffers its
+    output into a pipe.  Falls back to one nvidia-smi process per sample when NVML cannot be loaded."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, gpu_uuid=None):
         super().__init__(daemon=True)
         self.idx = gpu_index
-        self.samples = []
+        self.uuid = gpu_uuid
+        self.samples = []          # (sm_mhz, sm_max_mhz, set of active reasons)
         self.stop_flag = False
+        self.source = None
 
-    def run(self):
+    def _nvml_loop(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = None
+        if self.uuid:
+            for cand in (self.uuid, "GPU-" + self.uuid):
+                try:
+                    h = nv.nvmlDeviceGetHandleByUUID(cand.encode() if isinstance(cand, str) else cand)
+                    break
+                except Exception:
+                    try:
+                        h = nv.nvmlDeviceGetHandleByUUID(cand)
+                        break
+                    except Exception:
+                        h = None
+        if h is None:
+            h = nv.nvmlDeviceGetHandleByIndex(self.idx)
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        mx = int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        self.source = "nvml"
+        while not self.stop_flag:
+            mask = int(get_reasons(h))
+            self.samples.append((int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), mx, {k for k, b in bits.items() if mask & b}))
+            time.sleep(0.05)
+        try:
+            nv.nvmlShutdown()
+        except Exception:
+            pass
+
+    def _smi_loop(self):
+        self.source = "nvidia-smi"
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([v.strip() for v in out.split(",")])
+                f = [v.strip() for v in out.split(",")]
+                if len(f) >= 7 and f[0].replace(".", "").isdigit():
+                    self.samples.append((int(float(f[0])), int(float(f[1])), {k for k, v in zip(self.REASONS, f[3:7]) if v.lower().startswith("active")}))
             except Exception:
                 pass
             time.sleep(0.1)
 
+    def run(self):
+        try:
+            self._nvml_loop()
+        except Exception:
+            if not self.stop_flag:
+                self._smi_loop()
+
     def summary(self):
         self.stop_flag = True
-        self.join(timeout=6)
-        sm = sorted(int(float(s[0])) for s in self.samples if s and s[0].replace(".", "").isdigit())
-        mx = [int(float(s[1])) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        self.join(timeout=8)
+        sm = sorted(s[0] for s in self.samples)
         reasons = set()
         for s in self.samples:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+            reasons |= s[2]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(s[1] for s in self.samples) if self.samples else None,
+                "reasons": sorted(reasons), "samples": len(self.samples), "source": self.source}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -281,7 +323,11 @@ def main():
     ctx = lb.driver_ctx(local_rank)
     abi = lb.abi()
     peak, peak_src = load_peaks()
-    sampler = ClockSampler(local_rank)
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(local_rank, gpu_uuid)
 
     line = {"metric": "lbfgs_iterations_per_sec", "unit": "iters/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(name)}
