@@ -699,7 +699,7 @@ extern "C" int lbfgsb200_drv_batch_f64(int device_ordinal, int objective, long n
 
 // ----------------------------------------------------------------------------------------------------------
 // The same batch as ONE persistent kernel launch (LBFGSBatchSolver, include/LBFGSBatch.h): the start points stay
-// resident, solve() can be repeated (bench_batched.py), every problem bit-identical to a lone resident solve.
+// resident, solve() can be repeated (bench.py --config c5), every problem bit-identical to a lone resident solve.
 // ----------------------------------------------------------------------------------------------------------
 namespace {
 struct BatchSession
